@@ -1,0 +1,18 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "slow: long-running CPU check of the oracle at full model size")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return REPO / "tests" / "golden"

@@ -1,0 +1,121 @@
+"""CPU tests: pin the oracle (`oracle/`) against outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by tests/golden/make_golden.py, which imports
+the reference from /root/reference.  Here nothing of the reference is needed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.drafting import make_drafts
+from oracle.greedy_speculative import GreedySpeculativeOracle
+from oracle.topk_emulation import topk_indices
+from oracle.transformer import OracleTransformer
+from translation_transformer_b200.weights import ModelConfig, random_init_state_dict, state_dict_checksum
+
+from helpers import case_weights, load_json, load_npz, sha_tokens, test_file_sources
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_transformer_forward_matches_reference(name):
+    z, meta = load_npz("model_forward.npz"), load_json("model_forward.json")
+    m = meta["meta"][name]
+    cfg = ModelConfig(**m["config"])
+    sd = random_init_state_dict(cfg, m["seed"])
+    assert state_dict_checksum(sd) == m["checksum"]
+    o = OracleTransformer(sd, cfg.num_heads)
+    src, tgt = torch.from_numpy(z[name + "_src"]), torch.from_numpy(z[name + "_tgt"])
+    pad = src == 0
+    ref_mem = torch.from_numpy(z[name + "_memory"])
+    mem = o.encode_src(src, pad)
+    # padded source positions are never read (masked keys); the reference's nested-tensor
+    # fast path returns zeros there, so compare real positions only
+    assert (mem - ref_mem)[~pad].abs().max() < 1e-5
+    assert (o.decode_tgt(tgt, ref_mem, pad) - torch.from_numpy(z[name + "_logits"])).abs().max() < 1e-5
+    assert (o(src, tgt) - torch.from_numpy(z[name + "_forward_logits"])).abs().max() < 1e-5
+    # bf16-contract emulation stays within the bf16 tolerance of the fp32 reference
+    ob = OracleTransformer(sd, cfg.num_heads, gemm_dtype="bf16")
+    assert torch.allclose(ob(src, tgt), torch.from_numpy(z[name + "_forward_logits"]), atol=1e-2, rtol=1e-2)
+
+
+def test_make_drafts_matches_reference():
+    cases, dz, meta = load_json("drafts.json"), load_npz("drafts.npz"), load_json("model_forward.json")
+    _, src, _ = test_file_sources(meta["vocab"])
+    src = src.numpy()
+    syn = dz["syn_src"].astype(np.int64)
+    for c in cases:
+        if c.get("synthetic"):
+            s = syn[:, 1:]
+        else:
+            s = src[:c["B"]] if c["with_bos"] else src[:c["B"], 1:]
+        d = make_drafts(s, c["D"], c["N"], c["min_draft_len"], c["max_draft_len"], c["eos"], c["pad"], c["replace"])
+        assert d.shape == (s.shape[0], c["N"], min(max(c["min_draft_len"], c["D"]), c["max_draft_len"]))
+        assert np.array_equal(d, dz[f"d{c['id']}"].astype(np.int64)), c
+
+
+def test_make_drafts_argument_checks():
+    s = np.array([[5, 6, 7, 2, 0]])
+    with pytest.raises(AssertionError):
+        make_drafts(s, 2, 0, 1, 10, 2, 0, 5)
+    with pytest.raises(AssertionError):
+        make_drafts(s, 2, 1, 5, 4, 2, 0, 5)
+    with pytest.raises(AssertionError):
+        make_drafts(s, 2, 1, 1, 10, 2, 0, 0)
+    with pytest.raises(AssertionError):
+        make_drafts(s, 2, 1, 1, 10, 2, 0, 2)
+    with pytest.raises(AssertionError):
+        make_drafts(s, 2, 1, 1, 10, 2, 2, 5)
+
+
+def test_topk_tie_emulation_matches_torch_cpu():
+    g = torch.Generator().manual_seed(0)
+    for n in list(range(1, 70)) + [100, 128, 640]:
+        for hi in (1, 2, 11):
+            for _ in range(8):
+                x = torch.randint(0, hi + 1, (n,), generator=g)
+                for k in (1, 2, 5):
+                    if k <= n:
+                        assert x.topk(k).indices.tolist() == topk_indices(x.numpy(), k), (n, k, x.tolist())
+
+
+def _greedy_cases():
+    return [c for c in load_json("greedy_speculative.json")]
+
+
+@pytest.mark.parametrize("case", _greedy_cases(), ids=lambda c: c["id"])
+def test_greedy_speculative_oracle_matches_reference(case):
+    if case["arch"] == "full" and case.get("row", 0) != 0:
+        pytest.skip("one full-size case is enough for the CPU suite")
+    z = load_npz("greedy_speculative.npz")
+    cfg, sd = case_weights(case)
+    model = OracleTransformer(sd, cfg.num_heads)
+    seen = []
+    inner = model.decode_tgt
+
+    def spy(tgt, memory, mask):
+        seen.append(sha_tokens(tgt.numpy()))
+        return inner(tgt, memory, mask)
+
+    model.decode_tgt = spy
+    gen = GreedySpeculativeOracle(model, case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2,
+                                  case["replace"], keep_trace=True)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+    err = None
+    try:
+        out = gen.generate(src)
+    except RuntimeError as e:
+        err = type(e).__name__
+    assert err == case["error"]
+    assert gen.model_calls_num == case["model_calls"]
+    assert seen == case["decoder_input_sha1"]          # every decoder input, every iteration
+    if err is None:
+        assert np.array_equal(out.numpy(), z[case["id"] + "_out"].astype(np.int64))
+    # accepted lengths and chosen draft indices of every completed iteration
+    ref_nacc = z[case["id"] + "_nacc"].reshape(-1, case["n_drafts"])
+    ref_pick = z[case["id"] + "_pick"]
+    nacc = np.array([a for t in gen.trace for a in t["n_accepted"]], dtype=np.int64)
+    pick = np.array([p for t in gen.trace for p in t["draft_index"]], dtype=np.int64)
+    n = len(pick)
+    assert n <= len(ref_pick)
+    assert np.array_equal(pick, ref_pick[:n])
+    assert np.array_equal(nacc, ref_nacc[np.arange(n), ref_pick[:n]])

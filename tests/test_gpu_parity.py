@@ -1,0 +1,183 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI of
+libttb200 via the package's reference-shaped Python interface and is compared with
+  * the golden vectors produced by the unmodified reference (tests/golden/), and
+  * the CPU oracle (oracle/) on fresh seeded inputs.
+Bit-exact for tokens / accepted lengths / draft indices; logits within the tolerance written
+in each test (1e-5 class for the fp32 path, 1e-2 for bf16)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import case_weights, load_json, load_npz, test_file_sources
+from translation_transformer_b200.weights import ModelConfig, random_init_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _engine(cfg, sd, precision):
+    from translation_transformer_b200.model import B200Transformer
+    return B200Transformer(cfg, sd, precision=precision, device=0)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_make_drafts_matches_reference_golden(dev):
+    from translation_transformer_b200.utils.drafting import make_drafts
+    cases, dz, meta = load_json("drafts.json"), load_npz("drafts.npz"), load_json("model_forward.json")
+    _, src, _ = test_file_sources(meta["vocab"])
+    src = src.to(dev)
+    syn = torch.from_numpy(dz["syn_src"].astype(np.int64)).to(dev)
+    for c in cases:
+        if c.get("synthetic"):
+            s = syn[:, 1:]
+        else:
+            s = src[:c["B"]] if c["with_bos"] else src[:c["B"], 1:]
+        d = make_drafts(s, c["D"], c["N"], c["min_draft_len"], c["max_draft_len"], c["eos"], c["pad"], c["replace"])
+        assert d.dtype == torch.int64 and d.is_cuda
+        assert np.array_equal(d.cpu().numpy(), dz[f"d{c['id']}"].astype(np.int64)), c
+
+
+def test_make_drafts_argument_checks(dev):
+    from translation_transformer_b200.utils.drafting import make_drafts
+    s = torch.tensor([[5, 6, 7, 2, 0]], device=dev)
+    for args in ((2, 0, 1, 10, 2, 0, 5), (2, 1, 5, 4, 2, 0, 5), (2, 1, 1, 10, 2, 0, 0), (2, 1, 1, 10, 2, 0, 2), (2, 1, 1, 10, 2, 2, 5)):
+        with pytest.raises(AssertionError):
+            make_drafts(s, *args)
+
+
+def test_make_drafts_random_vs_oracle(dev):
+    from oracle.drafting import make_drafts as oracle_drafts
+    from translation_transformer_b200.utils.drafting import make_drafts
+    g = torch.Generator().manual_seed(7)
+    for trial in range(40):
+        B = int(torch.randint(1, 9, (1,), generator=g))
+        L = int(torch.randint(2, 220, (1,), generator=g))
+        src = torch.zeros(B, L, dtype=torch.int64)
+        for b in range(B):
+            n = int(torch.randint(0, L, (1,), generator=g))
+            src[b, :n] = torch.randint(3, 300, (n,), generator=g)
+            src[b, n] = 2
+        D = int(torch.randint(1, 60, (1,), generator=g))
+        N = int(torch.randint(1, 70, (1,), generator=g))
+        ref = oracle_drafts(src.numpy(), D, N, 1, 200, 2, 0, 9)
+        got = make_drafts(src.to(dev), D, N, 1, 200, 2, 0, 9).cpu().numpy()
+        assert np.array_equal(ref, got), (B, L, D, N)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_forward_fp32_matches_reference_golden(dev, name):
+    z, meta = load_npz("model_forward.npz"), load_json("model_forward.json")
+    m = meta["meta"][name]
+    cfg = ModelConfig(**m["config"])
+    eng = _engine(cfg, random_init_state_dict(cfg, m["seed"]), "fp32")
+    src, tgt = torch.from_numpy(z[name + "_src"]).to(dev), torch.from_numpy(z[name + "_tgt"]).to(dev)
+    pad = src == 0
+    mem = eng.encode_src(src, pad).cpu()
+    ref_mem = torch.from_numpy(z[name + "_memory"])
+    assert (mem - ref_mem)[~pad.cpu()].abs().max() < 2e-5          # fp32 tolerance
+    logits = eng.decode_tgt(tgt, ref_mem.to(dev), pad).cpu()
+    assert (logits - torch.from_numpy(z[name + "_logits"])).abs().max() < 2e-5
+    full = eng(src, tgt).cpu()
+    assert (full - torch.from_numpy(z[name + "_forward_logits"])).abs().max() < 2e-5
+    eng.close()
+
+
+def test_gemm_fp32_vs_torch(dev):
+    import ctypes as C
+    from translation_transformer_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    for (M, N, K, relu) in ((1, 30, 64, 0), (77, 300, 256, 1), (253, 768, 256, 0), (130, 256, 2048, 0)):
+        A = torch.randn(M, K, generator=g).to(dev)
+        W = torch.randn(N, K, generator=g).to(dev)
+        b = torch.randn(N, generator=g).to(dev)
+        Cm = torch.empty(M, N, device=dev)
+        _lib.check(lib.ttb_gemm(0, A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, relu, None), "ttb_gemm")
+        ref = A.double() @ W.double().t() + b.double()
+        if relu:
+            ref = ref.clamp_min(0)
+        assert (Cm.double() - ref).abs().max() < 1e-3 * (K ** 0.5) / 16
+
+
+# ---------------------------------------------------------------------------------------------
+def _greedy_cases():
+    return load_json("greedy_speculative.json")
+
+
+@pytest.mark.parametrize("case", _greedy_cases(), ids=lambda c: c["id"])
+def test_greedy_speculative_fp32_matches_reference_golden(dev, case):
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    z = load_npz("greedy_speculative.npz")
+    cfg, sd = case_weights(case)
+    eng = _engine(cfg, sd, "fp32")
+    gen = TranslationInferenceGreedySpeculative(eng, case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2,
+                                                case["replace"], keep_trace=True)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)).to(dev)
+    err = None
+    try:
+        out = gen.generate(src)
+    except RuntimeError as e:
+        err = "RuntimeError"
+        msg = str(e)
+    assert err == case["error"], (err, case["error"])
+    if err is None:
+        assert out.shape == (case["B"], 1, case["max_len"]) and out.dtype == torch.int64
+        assert np.array_equal(out.cpu().numpy(), z[case["id"] + "_out"].astype(np.int64))   # bit-exact tokens
+        assert gen.model_calls_num == case["model_calls"]
+    else:
+        # the reference fails inside iteration `model_calls` (after the decoder call for the
+        # shape error, before it for the index error); the engine stops at the same iteration
+        assert gen.model_calls_num in (case["model_calls"], case["model_calls"] - 1), (gen.model_calls_num, case["model_calls"], msg)
+    ref_nacc = z[case["id"] + "_nacc"].reshape(-1, case["n_drafts"])
+    ref_pick = z[case["id"] + "_pick"]
+    nacc = np.array([a for t in gen.trace for a in t["n_accepted"]], dtype=np.int64)
+    pick = np.array([p for t in gen.trace for p in t["draft_index"]], dtype=np.int64)
+    n = len(pick)
+    assert n <= len(ref_pick) and (err is not None or n == len(ref_pick))
+    assert np.array_equal(pick, ref_pick[:n])                                   # bit-exact draft indices
+    assert np.array_equal(nacc, ref_nacc[np.arange(n), ref_pick[:n]])           # bit-exact accepted lengths
+    assert [len(t["rows"]) for t in gen.trace] == case["rows_per_iter"][:len(gen.trace)]
+    eng.close()
+
+
+def test_greedy_speculative_fp32_vs_oracle_fresh_inputs(dev):
+    """Seeded inputs that are not in the fixtures: synthetic ragged sources, vocab 300."""
+    from oracle.greedy_speculative import GreedySpeculativeOracle
+    from oracle.transformer import OracleTransformer
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    from helpers import SMALL
+    cfg = ModelConfig(src_vocab_size=300, tgt_vocab_size=300, **SMALL)
+    for seed, eos_bias, B, max_len, D, N in ((101, 0.9, 6, 90, 8, 9), (102, 1.0, 9, 70, 4, 25), (103, 0.8, 3, 120, 12, 2)):
+        sd = {k: v.clone() for k, v in random_init_state_dict(cfg, seed).items()}
+        sd["tgt_token_featurizer.embedding.weight"] = sd["src_token_featurizer.embedding.weight"]
+        sd["next_token_classifier.bias"][2] += eos_bias
+        sd["next_token_classifier.bias"][0] -= 5.0
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(10, 80, (B,), generator=g)
+        src = torch.zeros(B, int(lens.max()) + 2, dtype=torch.int64)
+        for b in range(B):
+            n = int(lens[b])
+            src[b, 0] = 1
+            src[b, 1:n + 1] = torch.randint(4, 300, (n,), generator=g)
+            src[b, n + 1] = 2
+        oracle = GreedySpeculativeOracle(OracleTransformer(sd, cfg.num_heads), max_len, D, N, 0, 1, 2, 7, keep_trace=True)
+        eng = _engine(cfg, sd, "fp32")
+        gen = TranslationInferenceGreedySpeculative(eng, max_len, D, N, 0, 1, 2, 7, keep_trace=True)
+        try:
+            ref = oracle.generate(src)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                gen.generate(src.to(dev))
+            continue
+        out = gen.generate(src.to(dev))
+        assert np.array_equal(out.cpu().numpy(), ref.numpy())
+        assert gen.model_calls_num == oracle.model_calls_num
+        assert [t["n_accepted"] for t in gen.trace] == [t["n_accepted"] for t in oracle.trace]
+        assert [t["draft_index"] for t in gen.trace] == [t["draft_index"] for t in oracle.trace]
+        eng.close()

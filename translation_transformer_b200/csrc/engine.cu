@@ -1,0 +1,692 @@
+// Host side of libttb200: weight store, workspace, forward orchestration and the C ABI
+// (include/ttb200.h).  One engine = one model on one GPU; calls on an engine are not re-entrant.
+#include "kernels.cuh"
+#include "../../include/ttb200.h"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace ttb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        TTB_CUDA_OK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Param {
+    int64_t numel = 0;
+    float* dev = nullptr;
+    __nv_bfloat16* devh = nullptr;  // bf16 copy (GEMM weights, precision = bf16)
+    bool is_gemm_weight = false;
+    bool set = false;
+};
+
+struct Lin {
+    const float* w = nullptr;
+    const float* b = nullptr;
+    const __nv_bfloat16* wh = nullptr;
+    int N = 0, K = 0;
+    Lin rows(int r0, int n) const {
+        Lin l = *this;
+        l.w = w + (long long)r0 * K;
+        l.wh = wh ? wh + (long long)r0 * K : nullptr;
+        l.b = b ? b + r0 : nullptr;
+        l.N = n;
+        return l;
+    }
+};
+
+struct Norm { const float* g = nullptr; const float* b = nullptr; };
+
+struct EncLayer { Lin in_proj, out_proj, ff1, ff2; Norm n1, n2; };
+struct DecLayer { Lin self_in, self_out, cross_in, cross_out, ff1, ff2; Norm n1, n2, n3; };
+
+}  // namespace ttb
+
+using namespace ttb;
+
+struct ttb_engine {
+    ttb_model_desc d{};
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, Param> params;
+    std::vector<EncLayer> enc;
+    std::vector<DecLayer> dec;
+    Norm enc_norm, dec_norm;
+    Lin classifier;
+    const float* src_emb = nullptr;
+    const float* tgt_emb = nullptr;
+    const float* pe = nullptr;
+
+    // forward workspace (typed by the precision's activation type at use)
+    DevBuf x, xh, y, qkv, att, q2, hid, logits, tok32, keytok32, pred;
+    // encoder products / decoding state
+    DevBuf src32, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
+    int* h_ctrl = nullptr;  // pinned snapshots of ctrl for lagged polling
+    cudaEvent_t poll_ev[4]{};
+    cudaEvent_t t0{}, t1{};
+    long long launches = 0;
+
+    int E() const { return d.embedding_dim; }
+    int HD() const { return d.embedding_dim / d.num_heads; }
+};
+
+namespace ttb {
+
+static int add_param(ttb_engine* e, const std::string& name, int64_t numel, bool gemm_w) {
+    Param p;
+    p.numel = numel;
+    p.is_gemm_weight = gemm_w;
+    TTB_CUDA_OK(cudaMalloc(&p.dev, (size_t)numel * sizeof(float)));
+    e->params[name] = p;
+    return 0;
+}
+
+static int register_params(ttb_engine* e) {
+    const ttb_model_desc& d = e->d;
+    const int64_t E = d.embedding_dim, F = d.feedforward_dim;
+    int rc = 0;
+    rc |= add_param(e, "src_token_featurizer.embedding.weight", (int64_t)d.src_vocab_size * E, false);
+    rc |= add_param(e, "tgt_token_featurizer.embedding.weight", (int64_t)d.tgt_vocab_size * E, false);
+    rc |= add_param(e, "positional_encoding.pe", (int64_t)(d.max_positions + 1) * E, false);
+    auto attn = [&](const std::string& p) {
+        rc |= add_param(e, p + ".in_proj_weight", 3 * E * E, true);
+        rc |= add_param(e, p + ".in_proj_bias", 3 * E, false);
+        rc |= add_param(e, p + ".out_proj.weight", E * E, true);
+        rc |= add_param(e, p + ".out_proj.bias", E, false);
+    };
+    auto ffn = [&](const std::string& p, int norms) {
+        rc |= add_param(e, p + ".linear1.weight", F * E, true);
+        rc |= add_param(e, p + ".linear1.bias", F, false);
+        rc |= add_param(e, p + ".linear2.weight", E * F, true);
+        rc |= add_param(e, p + ".linear2.bias", E, false);
+        for (int j = 1; j <= norms; ++j) {
+            rc |= add_param(e, p + ".norm" + std::to_string(j) + ".weight", E, false);
+            rc |= add_param(e, p + ".norm" + std::to_string(j) + ".bias", E, false);
+        }
+    };
+    for (int i = 0; i < d.num_encoder_layers; ++i) {
+        std::string p = "transformer.encoder.layers." + std::to_string(i);
+        attn(p + ".self_attn");
+        ffn(p, 2);
+    }
+    rc |= add_param(e, "transformer.encoder.norm.weight", E, false);
+    rc |= add_param(e, "transformer.encoder.norm.bias", E, false);
+    for (int i = 0; i < d.num_decoder_layers; ++i) {
+        std::string p = "transformer.decoder.layers." + std::to_string(i);
+        attn(p + ".self_attn");
+        attn(p + ".multihead_attn");
+        ffn(p, 3);
+    }
+    rc |= add_param(e, "transformer.decoder.norm.weight", E, false);
+    rc |= add_param(e, "transformer.decoder.norm.bias", E, false);
+    rc |= add_param(e, "next_token_classifier.weight", (int64_t)d.tgt_vocab_size * E, true);
+    rc |= add_param(e, "next_token_classifier.bias", d.tgt_vocab_size, false);
+    return rc;
+}
+
+static Lin make_lin(ttb_engine* e, const std::string& w, const std::string& b, int N, int K) {
+    Lin l;
+    l.w = e->params[w].dev;
+    l.wh = e->params[w].devh;
+    l.b = e->params[b].dev;
+    l.N = N;
+    l.K = K;
+    return l;
+}
+static Norm make_norm(ttb_engine* e, const std::string& p) {
+    Norm n;
+    n.g = e->params[p + ".weight"].dev;
+    n.b = e->params[p + ".bias"].dev;
+    return n;
+}
+
+// ---- typed forward helpers ---------------------------------------------------------------------
+template <typename ActT> struct Prec;
+template <> struct Prec<float> { static constexpr bool lowp = false; };
+template <> struct Prec<__nv_bfloat16> { static constexpr bool lowp = true; };
+
+template <typename OutT>
+static int linear(ttb_engine* e, const float* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
+    launch_gemm_f32<OutT>(A, lda, L.w, L.b, C, ldc, rows, L.N, L.K, relu, s);
+    e->launches++;
+    return 0;
+}
+template <typename OutT>
+static int linear(ttb_engine* e, const __nv_bfloat16* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
+    e->launches++;
+    return launch_gemm_bf16_tc<OutT>(A, lda, L.wh, L.b, C, ldc, rows, L.N, L.K, relu, s);
+}
+
+// GEMM A-operand view of the residual stream: fp32 path reads x itself, bf16 path its bf16 copy
+template <typename ActT> static const ActT* a_view(const float* x, const ActT* xh);
+template <> const float* a_view<float>(const float* x, const float*) { return x; }
+template <> const __nv_bfloat16* a_view<__nv_bfloat16>(const float*, const __nv_bfloat16* xh) { return xh; }
+
+template <typename ActT>
+static int ensure_work(ttb_engine* e, long long T, int qkv_layers) {
+    const long long E = e->E(), F = e->d.feedforward_dim, V = e->d.tgt_vocab_size;
+    int rc = 0;
+    rc |= e->x.ensure(T * E * sizeof(float));
+    if (Prec<ActT>::lowp) rc |= e->xh.ensure(T * E * sizeof(ActT));
+    rc |= e->y.ensure(T * E * sizeof(float));
+    rc |= e->qkv.ensure(T * 3 * E * sizeof(ActT) * qkv_layers);
+    rc |= e->att.ensure(T * E * sizeof(ActT));
+    rc |= e->q2.ensure(T * E * sizeof(ActT));
+    rc |= e->hid.ensure(T * F * sizeof(ActT));
+    rc |= e->logits.ensure(T * V * sizeof(float));
+    rc |= e->tok32.ensure(T * sizeof(int));
+    rc |= e->pred.ensure(T * sizeof(int));
+    return rc;
+}
+
+// Encoder stack on tokens src32 (B, Ls); writes memory (fp32) and, on the bf16 path, memh.
+template <typename ActT>
+static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int B, int Ls, float* mem_out, ActT* memh_out, cudaStream_t s) {
+    const int E = e->E(), F = e->d.feedforward_dim, T = B * Ls, H = e->d.num_heads, HD = e->HD();
+    if (ensure_work<ActT>(e, T, 1)) return 1;
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    float* y = e->y.as<float>();
+    ActT* qkv = e->qkv.as<ActT>();
+    ActT* att = e->att.as<ActT>();
+    ActT* hid = e->hid.as<ActT>();
+    RowCount rows(T);
+    launch_embed_seq<ActT>(src32, T, Ls, e->src_emb, e->pe, E, x, xh, s);
+    e->launches++;
+    const int n_layers = (int)e->enc.size();
+    for (int l = 0; l < n_layers; ++l) {
+        const EncLayer& L = e->enc[l];
+        const bool last = l + 1 == n_layers;
+        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.in_proj, qkv, 3 * E, rows, false, s)) return 1;
+        launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
+                               key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+        e->launches++;
+        if (linear<float>(e, att, E, L.out_proj, y, E, rows, false, s)) return 1;
+        launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s);
+        e->launches++;
+        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
+        if (linear<float>(e, hid, F, L.ff2, y, E, rows, false, s)) return 1;
+        float* dst = last ? mem_out : x;
+        ActT* dsth = last ? memh_out : xh;
+        launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, last ? e->enc_norm.g : nullptr, last ? e->enc_norm.b : nullptr,
+                                   dst, dsth, rows, E, s);
+        e->launches++;
+    }
+    return 0;
+}
+
+// Cross-attention K/V of every decoder layer from the encoder memory: crosskv[l] = (B*Ls, 2E)
+template <typename ActT>
+static int cross_kv_impl(ttb_engine* e, const float* mem, const ActT* memh, int rows_n, ActT* crosskv, cudaStream_t s) {
+    const int E = e->E();
+    RowCount rows(rows_n);
+    for (size_t l = 0; l < e->dec.size(); ++l) {
+        Lin kv = e->dec[l].cross_in.rows(E, 2 * E);
+        if (linear<ActT>(e, a_view<ActT>(mem, memh), E, kv, crosskv + (long long)l * rows_n * 2 * E, 2 * E, rows, false, s)) return 1;
+    }
+    return 0;
+}
+
+// Decoder layers l on the token matrix in e->x / e->xh (`rows` live rows).  `self_attn` enqueues the
+// layer's self-attention given the freshly projected qkv of that layer.
+template <typename ActT, typename SelfAttn, typename CrossAttn>
+static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long qkv_layer_stride,
+                         SelfAttn self_attn, CrossAttn cross_attn, cudaStream_t s) {
+    const int E = e->E(), F = e->d.feedforward_dim;
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    float* y = e->y.as<float>();
+    ActT* att = e->att.as<ActT>();
+    ActT* q2 = e->q2.as<ActT>();
+    ActT* hid = e->hid.as<ActT>();
+    const int n_layers = (int)e->dec.size();
+    for (int l = 0; l < n_layers; ++l) {
+        const DecLayer& L = e->dec[l];
+        const bool last = l + 1 == n_layers;
+        ActT* qkv = e->qkv.as<ActT>() + (qkv_layers > 1 ? (long long)l * qkv_layer_stride : 0);
+        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.self_in, qkv, 3 * E, rows, false, s)) return 1;
+        self_attn(l, qkv, att);
+        e->launches++;
+        if (linear<float>(e, att, E, L.self_out, y, E, rows, false, s)) return 1;
+        launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s);
+        e->launches++;
+        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
+        cross_attn(l, q2, att);
+        e->launches++;
+        if (linear<float>(e, att, E, L.cross_out, y, E, rows, false, s)) return 1;
+        launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, nullptr, nullptr, x, xh, rows, E, s);
+        e->launches++;
+        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
+        if (linear<float>(e, hid, F, L.ff2, y, E, rows, false, s)) return 1;
+        launch_add_layernorm<ActT>(x, y, L.n3.g, L.n3.b, last ? e->dec_norm.g : nullptr, last ? e->dec_norm.b : nullptr,
+                                   x, xh, rows, E, s);
+        e->launches++;
+    }
+    return 0;
+}
+
+template <typename ActT>
+static int encode_api(ttb_engine* e, const int64_t* src_dev, const uint8_t* mask_dev, int B, int Ls, float* mem_out, cudaStream_t s) {
+    const long long T = (long long)B * Ls;
+    if (e->src32.ensure(T * sizeof(int))) return 1;
+    int* src32 = e->src32.as<int>();
+    launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, T, s);
+    e->launches++;
+    const int* key_src = src32;
+    if (mask_dev) {  // explicit mask: express it as a token-like array for the attention kernels
+        if (e->keytok32.ensure(T * sizeof(int))) return 1;
+        launch_mask_to_tokens(mask_dev, e->keytok32.as<int>(), T, e->d.src_pad_token_idx, s);
+        e->launches++;
+        key_src = e->keytok32.as<int>();
+    }
+    if (Prec<ActT>::lowp && e->memh.ensure(T * e->E() * sizeof(ActT))) return 1;
+    int rc = encode_impl<ActT>(e, src32, key_src, B, Ls, mem_out, Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr, s);
+    if (rc) return rc;
+    TTB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename ActT>
+static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, const float* memory_dev,
+                      const uint8_t* mem_mask_dev, int Ls, float* logits_out, cudaStream_t s) {
+    const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
+    const long long T = (long long)B * Lt, TS = (long long)B * Ls;
+    if (ensure_work<ActT>(e, T, 1)) return 1;
+    if (e->keytok32.ensure(TS * sizeof(int))) return 1;
+    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * e->dec.size())) return 1;
+    int* tgt32 = e->tok32.as<int>();
+    int* memtok = e->keytok32.as<int>();
+    launch_i64_to_i32(reinterpret_cast<const long long*>(tgt_dev), tgt32, T, s);
+    launch_mask_to_tokens(mem_mask_dev, memtok, TS, e->d.src_pad_token_idx, s);
+    e->launches += 2;
+    const ActT* memh = nullptr;
+    if (Prec<ActT>::lowp) {
+        if (e->memh.ensure(TS * E * sizeof(ActT))) return 1;
+        launch_f32_to_bf16(memory_dev, reinterpret_cast<__nv_bfloat16*>(e->memh.p), TS * E, s);
+        e->launches++;
+        memh = e->memh.as<ActT>();
+    }
+    ActT* crosskv = e->crosskv.as<ActT>();
+    if (cross_kv_impl<ActT>(e, memory_dev, memh, (int)TS, crosskv, s)) return 1;
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    launch_embed_seq<ActT>(tgt32, (int)T, Lt, e->tgt_emb, e->pe, E, x, xh, s);
+    e->launches++;
+    RowCount rows((int)T);
+    auto self_attn = [&](int, ActT* qkv, ActT* att) {
+        launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Lt, Lt, Lt, nullptr,
+                               tgt32, Lt, e->d.tgt_pad_token_idx, true, H, HD, s);
+    };
+    auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+        const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+        launch_attention<ActT>(q2, E, kv, kv + E, 2 * E, att, E, B, nullptr, Lt, Ls, Ls, nullptr,
+                               memtok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+    };
+    if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
+    if (linear<float>(e, a_view<ActT>(x, xh), E, e->classifier, logits_out, V, rows, false, s)) return 1;
+    TTB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename ActT>
+static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int draft_len, int N,
+                      int pad, int bos, int eos, int replace, int tie_break, int64_t* out_dev, int32_t* trace_dev,
+                      ttb_generate_stats* stats, cudaStream_t s) {
+    const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
+    const int n_dec = (int)e->dec.size();
+    const int D = std::min(std::max(1, draft_len), max_len);  // make_drafts(min_draft_len=1, max_draft_len=max_len)
+    const long long TS = (long long)B * Ls;
+    const int per_q = N * (D + 1);
+    const long long T = (long long)B * per_q;
+    const int gen_ld = max_len + D + 2;
+    const int P = gen_ld;  // cache positions per query
+    const long long launches0 = e->launches;
+
+    // encoder + cross-attention K/V (computed once per query, not once per draft row and iteration)
+    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (e->kcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT)) || e->vcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT))) return 1;
+    if (e->drafts.ensure((size_t)B * N * D * sizeof(int)) || e->gen.ensure((size_t)B * gen_ld * sizeof(int))) return 1;
+    if (e->front.ensure(B * sizeof(int)) || e->active.ensure(B * sizeof(int)) || e->ctrl.ensure(CTRL_COUNT * sizeof(int))) return 1;
+    if (e->sel.ensure((size_t)B * 4 * sizeof(int)) || e->out64.ensure((size_t)B * max_len * sizeof(long long))) return 1;
+
+    TTB_CUDA_OK(cudaEventRecord(e->t0, s));
+    int* src32 = e->src32.as<int>();
+    launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s);
+    e->launches++;
+    float* mem = e->memory.as<float>();
+    ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
+    if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
+    ActT* crosskv = e->crosskv.as<ActT>();
+    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
+    // drafts from the source without its BOS column (speculative_decoding.py:64-73)
+    launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s);
+    e->launches++;
+
+    if (ensure_work<ActT>(e, T, n_dec)) return 1;
+    GreedyState st{};
+    st.B = B; st.N = N; st.D = D; st.max_len = max_len; st.gen_ld = gen_ld; st.pad = pad; st.bos = bos; st.eos = eos;
+    st.gen = e->gen.as<int>(); st.front = e->front.as<int>(); st.active = e->active.as<int>(); st.ctrl = e->ctrl.as<int>();
+    st.drafts = e->drafts.as<int>(); st.pred = e->pred.as<int>(); st.out = e->out64.as<long long>();
+    st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break;
+    launch_greedy_init(st, s);
+    e->launches++;
+
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    ActT* kc = e->kcache.as<ActT>();
+    ActT* vc = e->vcache.as<ActT>();
+    const long long cache_q_stride = (long long)P * E, cache_l_stride = (long long)B * P * E;
+    const long long qkv_l_stride = T * 3 * E;
+    const int* n_active = st.ctrl + CTRL_N_ACTIVE;
+    RowCount rows((int)T, n_active, per_q);
+
+    auto self_attn = [&](int l, ActT* qkv, ActT* att) {
+        launch_spec_self_attention<ActT>(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
+                                         att, E, B, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
+                                         N, D, H, HD, P, s);
+    };
+    auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+        const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+        launch_attention<ActT>(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
+                               src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+    };
+
+    // Lagged polling: the host looks at the control words of iteration (it - LAG) while iterations up
+    // to `it` are already queued, so the GPU never waits for the host.
+    constexpr int LAG = 2, RING = 4;
+    int it = 0;
+    bool done = false;
+    const int max_iters = max_len + 1;
+    while (!done && it < max_iters) {
+        launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s);
+        e->launches++;
+        if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
+        if (linear<float>(e, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
+        launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s);
+        launch_greedy_accept(st, s);
+        launch_greedy_cache_append<ActT>(st, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, E, kc, vc, cache_l_stride,
+                                         cache_q_stride, E, s);
+        e->launches += 3;
+        TTB_CUDA_OK(cudaMemcpyAsync(e->h_ctrl + (it % RING) * CTRL_COUNT, st.ctrl, CTRL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TTB_CUDA_OK(cudaEventRecord(e->poll_ev[it % RING], s));
+        if (it >= LAG) {
+            const int j = (it - LAG) % RING;
+            TTB_CUDA_OK(cudaEventSynchronize(e->poll_ev[j]));
+            if (e->h_ctrl[j * CTRL_COUNT + CTRL_DONE]) done = true;
+        }
+        ++it;
+    }
+    TTB_CUDA_OK(cudaMemcpyAsync(out_dev, st.out, (size_t)B * max_len * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    TTB_CUDA_OK(cudaMemcpyAsync(e->h_ctrl, st.ctrl, CTRL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TTB_CUDA_OK(cudaEventRecord(e->t1, s));
+    TTB_CUDA_OK(cudaStreamSynchronize(s));
+    TTB_CUDA_OK(cudaGetLastError());
+    const int* c = e->h_ctrl;
+    TTB_CHECK(c[CTRL_DONE] == 1, "greedy decoding loop did not terminate within max_len + 1 iterations");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->t0, e->t1);
+    if (stats) {
+        stats->model_calls = c[CTRL_ITERS];
+        stats->accepted_tokens = c[CTRL_ACCEPTED];
+        stats->produced_tokens = c[CTRL_TOKENS];
+        stats->unfinished = c[CTRL_N_LEFT];
+        stats->error = c[CTRL_ERROR] == 1 ? TTB_ERR_REF_INDEX : (c[CTRL_ERROR] == 2 ? TTB_ERR_REF_SHAPE : 0);
+        stats->gpu_launches = (int32_t)(e->launches - launches0);
+        stats->gpu_ms = ms;
+    }
+    if (c[CTRL_ERROR] == 1) {
+        set_last_error("index out of bounds while splicing drafts into the token matrix (reference scatter, speculative_decoding.py:111)");
+        return TTB_ERR_REF_INDEX;
+    }
+    if (c[CTRL_ERROR] == 2) {
+        set_last_error("shape mismatch: a finished row is wider than max_len (reference speculative_decoding.py:158)");
+        return TTB_ERR_REF_SHAPE;
+    }
+    return 0;
+}
+
+}  // namespace ttb
+
+// =================================================================================================
+extern "C" {
+
+int ttb_abi_version(void) { return TTB_ABI_VERSION; }
+const char* ttb_last_error(void) { return g_last_error.c_str(); }
+
+int ttb_device_check(int device) {
+    int n = 0;
+    TTB_CUDA_OK(cudaGetDeviceCount(&n));
+    TTB_CHECK(device >= 0 && device < n, "no such CUDA device");
+    cudaDeviceProp p{};
+    TTB_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    TTB_CHECK(p.major == 10, "libttb200 is built for sm_100a (B200) only");
+    return 0;
+}
+
+int ttb_engine_create(const ttb_model_desc* desc, int device, ttb_engine** out) {
+    TTB_CHECK(desc && out, "null argument");
+    TTB_CHECK(desc->embedding_dim % desc->num_heads == 0, "embedding_dim must be divisible by num_heads");
+    const int hd = desc->embedding_dim / desc->num_heads;
+    TTB_CHECK(hd == 16 || hd == 32 || hd == 64, "head_dim must be 16, 32 or 64");
+    TTB_CHECK(desc->embedding_dim % 16 == 0 && desc->feedforward_dim % 16 == 0, "embedding_dim and feedforward_dim must be multiples of 16");
+    TTB_CHECK(desc->embedding_dim <= 1024, "embedding_dim above 1024 is not supported");
+    if (desc->precision == TTB_PRECISION_BF16)
+        TTB_CHECK(desc->embedding_dim % 64 == 0 && desc->feedforward_dim % 64 == 0, "bf16 path needs embedding_dim and feedforward_dim multiples of 64");
+    if (int rc = ttb_device_check(device)) return rc;
+    TTB_CUDA_OK(cudaSetDevice(device));
+    ttb_engine* e = new ttb_engine();
+    e->d = *desc;
+    e->device = device;
+    if (register_params(e)) { ttb_engine_destroy(e); return 1; }
+    TTB_CUDA_OK(cudaMallocHost(&e->h_ctrl, 4 * CTRL_COUNT * sizeof(int)));
+    for (auto& ev : e->poll_ev) TTB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    TTB_CUDA_OK(cudaEventCreate(&e->t0));
+    TTB_CUDA_OK(cudaEventCreate(&e->t1));
+    *out = e;
+    return 0;
+}
+
+void ttb_engine_destroy(ttb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (auto& kv : e->params) {
+        if (kv.second.dev) cudaFree(kv.second.dev);
+        if (kv.second.devh) cudaFree(kv.second.devh);
+    }
+    DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
+                      &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
+                      &e->active, &e->ctrl, &e->sel, &e->out64};
+    for (DevBuf* b : bufs) b->release();
+    if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
+    for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
+    if (e->t0) cudaEventDestroy(e->t0);
+    if (e->t1) cudaEventDestroy(e->t1);
+    delete e;
+}
+
+int ttb_engine_set_param(ttb_engine* e, const char* name, const float* data, int64_t numel) {
+    TTB_CHECK(e && name && data, "null argument");
+    std::string n(name);
+    if (n.rfind("model.", 0) == 0) n = n.substr(6);
+    auto it = e->params.find(n);
+    TTB_CHECK(it != e->params.end(), std::string("unexpected parameter name: ") + n);
+    TTB_CHECK(it->second.numel == numel, std::string("size mismatch for ") + n + ": expected " +
+              std::to_string(it->second.numel) + " elements, got " + std::to_string(numel));
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    TTB_CUDA_OK(cudaMemcpy(it->second.dev, data, (size_t)numel * sizeof(float), cudaMemcpyDefault));
+    it->second.set = true;
+    e->finalized = false;
+    return 0;
+}
+
+int ttb_engine_finalize(ttb_engine* e) {
+    TTB_CHECK(e, "null engine");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    for (auto& kv : e->params) TTB_CHECK(kv.second.set, std::string("missing parameter: ") + kv.first);
+    if (e->d.precision == TTB_PRECISION_BF16) {
+        for (auto& kv : e->params) {
+            Param& p = kv.second;
+            if (!p.is_gemm_weight) continue;
+            if (!p.devh) TTB_CUDA_OK(cudaMalloc(&p.devh, (size_t)p.numel * sizeof(__nv_bfloat16)));
+            launch_f32_to_bf16(p.dev, p.devh, p.numel, 0);
+        }
+        TTB_CUDA_OK(cudaDeviceSynchronize());
+    }
+    const int E = e->d.embedding_dim, F = e->d.feedforward_dim;
+    e->enc.clear();
+    e->dec.clear();
+    for (int i = 0; i < e->d.num_encoder_layers; ++i) {
+        std::string p = "transformer.encoder.layers." + std::to_string(i);
+        EncLayer L;
+        L.in_proj = make_lin(e, p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias", 3 * E, E);
+        L.out_proj = make_lin(e, p + ".self_attn.out_proj.weight", p + ".self_attn.out_proj.bias", E, E);
+        L.ff1 = make_lin(e, p + ".linear1.weight", p + ".linear1.bias", F, E);
+        L.ff2 = make_lin(e, p + ".linear2.weight", p + ".linear2.bias", E, F);
+        L.n1 = make_norm(e, p + ".norm1");
+        L.n2 = make_norm(e, p + ".norm2");
+        e->enc.push_back(L);
+    }
+    for (int i = 0; i < e->d.num_decoder_layers; ++i) {
+        std::string p = "transformer.decoder.layers." + std::to_string(i);
+        DecLayer L;
+        L.self_in = make_lin(e, p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias", 3 * E, E);
+        L.self_out = make_lin(e, p + ".self_attn.out_proj.weight", p + ".self_attn.out_proj.bias", E, E);
+        L.cross_in = make_lin(e, p + ".multihead_attn.in_proj_weight", p + ".multihead_attn.in_proj_bias", 3 * E, E);
+        L.cross_out = make_lin(e, p + ".multihead_attn.out_proj.weight", p + ".multihead_attn.out_proj.bias", E, E);
+        L.ff1 = make_lin(e, p + ".linear1.weight", p + ".linear1.bias", F, E);
+        L.ff2 = make_lin(e, p + ".linear2.weight", p + ".linear2.bias", E, F);
+        L.n1 = make_norm(e, p + ".norm1");
+        L.n2 = make_norm(e, p + ".norm2");
+        L.n3 = make_norm(e, p + ".norm3");
+        e->dec.push_back(L);
+    }
+    e->enc_norm = make_norm(e, "transformer.encoder.norm");
+    e->dec_norm = make_norm(e, "transformer.decoder.norm");
+    e->classifier = make_lin(e, "next_token_classifier.weight", "next_token_classifier.bias", e->d.tgt_vocab_size, E);
+    e->src_emb = e->params["src_token_featurizer.embedding.weight"].dev;
+    e->tgt_emb = e->params["tgt_token_featurizer.embedding.weight"].dev;
+    e->pe = e->params["positional_encoding.pe"].dev;
+    e->finalized = true;
+    return 0;
+}
+
+int ttb_make_drafts(const int64_t* src_dev, int64_t src_ld, int32_t B, int32_t L, int32_t draft_len,
+                    int32_t n_drafts, int32_t min_draft_len, int32_t max_draft_len, int32_t eos,
+                    int32_t pad, int32_t replace, int64_t* out_dev, int32_t* d_out, void* stream) {
+    // same argument checks, same order, as drafting.py:38-42 (the wrappers raise AssertionError)
+    TTB_CHECK(n_drafts > 0, "The number of drafts must be greater than 0");
+    TTB_CHECK(min_draft_len <= max_draft_len, "The minimum draft length must not be greater than the maximum draft length");
+    TTB_CHECK(pad != replace, "The pad token and the replace token must be different");
+    TTB_CHECK(eos != replace, "The eos token and the replace token must be different");
+    TTB_CHECK(eos != pad, "The eos token and the pad token must be different");
+    TTB_CHECK(src_dev && out_dev && B > 0 && L > 0, "bad source tensor");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int D = std::min(std::max(min_draft_len, draft_len), max_draft_len);
+    if (d_out) *d_out = D;
+    int *src32 = nullptr, *out32 = nullptr;
+    TTB_CUDA_OK(cudaMallocAsync(&src32, (size_t)B * L * sizeof(int), s));
+    TTB_CUDA_OK(cudaMallocAsync(&out32, (size_t)B * n_drafts * D * sizeof(int), s));
+    if (src_ld == L) {
+        launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, (long long)B * L, s);
+    } else {
+        for (int b = 0; b < B; ++b)
+            launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev) + (long long)b * src_ld, src32 + (long long)b * L, L, s);
+    }
+    launch_make_drafts(src32, L, B, L, D, n_drafts, eos, pad, replace, out32, s);
+    launch_i32_to_i64(out32, reinterpret_cast<long long*>(out_dev), (long long)B * n_drafts * D, s);
+    TTB_CUDA_OK(cudaFreeAsync(src32, s));
+    TTB_CUDA_OK(cudaFreeAsync(out32, s));
+    TTB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+#define TTB_DISPATCH(e, call_f32, call_bf16) ((e)->d.precision == TTB_PRECISION_FP32 ? (call_f32) : (call_bf16))
+
+int ttb_encode_src(ttb_engine* e, const int64_t* src_dev, const uint8_t* src_pad_mask_dev, int32_t B,
+                   int32_t Ls, float* memory_out_dev, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(src_dev && memory_out_dev && B > 0 && Ls > 0, "bad arguments");
+    TTB_CHECK(Ls <= e->d.max_positions, "source longer than the positional table");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, encode_api<float>(e, src_dev, src_pad_mask_dev, B, Ls, memory_out_dev, s),
+                        encode_api<__nv_bfloat16>(e, src_dev, src_pad_mask_dev, B, Ls, memory_out_dev, s));
+}
+
+int ttb_decode_tgt(ttb_engine* e, const int64_t* tgt_dev, int32_t B, int32_t Lt, const float* memory_dev,
+                   const uint8_t* memory_pad_mask_dev, int32_t Ls, float* logits_out_dev, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(tgt_dev && memory_dev && memory_pad_mask_dev && logits_out_dev && B > 0 && Lt > 0 && Ls > 0, "bad arguments");
+    TTB_CHECK(Lt <= e->d.max_positions, "target longer than the positional table");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, decode_api<float>(e, tgt_dev, B, Lt, memory_dev, memory_pad_mask_dev, Ls, logits_out_dev, s),
+                        decode_api<__nv_bfloat16>(e, tgt_dev, B, Lt, memory_dev, memory_pad_mask_dev, Ls, logits_out_dev, s));
+}
+
+int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls,
+                                    int32_t max_len, int32_t draft_len, int32_t n_drafts, int32_t pad_token,
+                                    int32_t bos_token, int32_t eos_token, int32_t replace_token,
+                                    int32_t tie_break, int64_t* out_dev, int32_t* trace_dev,
+                                    ttb_generate_stats* stats, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(src_dev && out_dev && B > 0 && Ls > 1 && max_len > 1, "bad arguments");
+    TTB_CHECK(n_drafts > 0, "The number of drafts must be greater than 0");
+    TTB_CHECK(pad_token != replace_token, "The pad token and the replace token must be different");
+    TTB_CHECK(eos_token != replace_token, "The eos token and the replace token must be different");
+    TTB_CHECK(eos_token != pad_token, "The eos token and the pad token must be different");
+    TTB_CHECK(Ls <= e->d.max_positions && max_len + draft_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
+                                             replace_token, tie_break, out_dev, trace_dev, stats, s),
+                        greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
+                                                  replace_token, tie_break, out_dev, trace_dev, stats, s));
+}
+
+int ttb_gemm(int32_t precision, const void* A_dev, const void* W_dev, const float* bias_dev, float* C_dev,
+             int32_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
+    TTB_CHECK(A_dev && W_dev && C_dev && M > 0 && N > 0 && K > 0, "bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (precision == TTB_PRECISION_FP32) {
+        TTB_CHECK(K % 16 == 0, "K must be a multiple of 16");
+        launch_gemm_f32<float>(static_cast<const float*>(A_dev), K, static_cast<const float*>(W_dev), bias_dev, C_dev, N,
+                               RowCount(M), N, K, relu != 0, s);
+    } else {
+        TTB_CHECK(K % 64 == 0, "K must be a multiple of 64");
+        if (int rc = launch_gemm_bf16_tc<float>(static_cast<const __nv_bfloat16*>(A_dev), K, static_cast<const __nv_bfloat16*>(W_dev),
+                                                bias_dev, C_dev, N, RowCount(M), N, K, relu != 0, s))
+            return rc;
+    }
+    TTB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

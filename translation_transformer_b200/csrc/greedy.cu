@@ -1,0 +1,304 @@
+// Device-resident state machine of speculative greedy decoding
+// (reference: /root/reference/src/decoding/speculative_decoding.py:39-174).
+//
+// The host never looks at tokens while decoding.  Per iteration the engine launches
+//   greedy_embed -> decoder layers -> classifier + argmax -> greedy_accept -> cache_append
+// and the accept kernel (a single CTA: the bookkeeping of a whole batch is a few KB) does what the
+// reference does with ~40 tensor ops and two host syncs per iteration:
+//   * accepted length of every draft  (verification / cumsum / sum, :129-131)
+//   * best draft per query            (topk(1), :133; tie-break = torch CPU topk emulation)
+//   * token append + front index      (:136-146)
+//   * retirement of finished queries into the output buffer and order-preserving compaction of
+//     the live list (:149-168)
+//   * the width bookkeeping of the reference's shared token matrix (:93-102), which decides when
+//     the loop stops and when the reference itself would fail (see oracle/greedy_speculative.py).
+#include "kernels.cuh"
+
+namespace ttb {
+
+// ---- torch CPU topk(1) tie-break: libstdc++ introselect on (value, index) pairs -------------
+struct VI { int v; int i; };
+__device__ __forceinline__ bool gt(const VI& a, const VI& b) { return a.v > b.v; }
+__device__ __forceinline__ void swp(VI& a, VI& b) { VI t = a; a = b; b = t; }
+
+__device__ void push_heap_(VI* e, int first, int hole, int top, VI val) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && gt(e[first + parent], val)) {
+        e[first + hole] = e[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    e[first + hole] = val;
+}
+__device__ void adjust_heap_(VI* e, int first, int hole, int len, VI val) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (gt(e[first + child], e[first + child - 1])) child--;
+        e[first + hole] = e[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        e[first + hole] = e[first + child - 1];
+        hole = child - 1;
+    }
+    push_heap_(e, first, hole, top, val);
+}
+__device__ void heap_select_(VI* e, int first, int middle, int last) {
+    const int len = middle - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            adjust_heap_(e, first, parent, len, e[first + parent]);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    for (int i = middle; i < last; ++i) {
+        if (gt(e[i], e[first])) {
+            VI val = e[i];
+            e[i] = e[first];
+            adjust_heap_(e, first, 0, len, val);
+        }
+    }
+}
+// index torch.topk(vals, 1) returns on the CPU backend (n < 64: std::nth_element, else partial_sort)
+__device__ int topk1_torch_cpu(const int* vals, int n) {
+    if (n >= 64 || n <= 1) {
+        int best = 0;
+        for (int j = 1; j < n; ++j) if (vals[j] > vals[best]) best = j;
+        return best;
+    }
+    VI e[64];
+    for (int j = 0; j < n; ++j) { e[j].v = vals[j]; e[j].i = j; }
+    int first = 0, last = n;
+    const int nth = 0;
+    int depth = 2 * (31 - __clz(n));
+    while (last - first > 3) {
+        if (depth == 0) {
+            heap_select_(e, first, nth + 1, last);
+            swp(e[first], e[nth]);
+            return e[nth].i;
+        }
+        --depth;
+        const int mid = first + (last - first) / 2;
+        {   // __move_median_to_first(first, first + 1, mid, last - 1)
+            const int a = first + 1, b = mid, c = last - 1;
+            if (gt(e[a], e[b])) {
+                if (gt(e[b], e[c])) swp(e[first], e[b]);
+                else if (gt(e[a], e[c])) swp(e[first], e[c]);
+                else swp(e[first], e[a]);
+            } else if (gt(e[a], e[c])) swp(e[first], e[a]);
+            else if (gt(e[b], e[c])) swp(e[first], e[c]);
+            else swp(e[first], e[b]);
+        }
+        int lo = first + 1, hi = last;  // __unguarded_partition(first + 1, last, pivot = first)
+        while (true) {
+            while (gt(e[lo], e[first])) ++lo;
+            --hi;
+            while (gt(e[first], e[hi])) --hi;
+            if (!(lo < hi)) break;
+            swp(e[lo], e[hi]);
+            ++lo;
+        }
+        if (lo <= nth) first = lo; else last = lo;
+    }
+    for (int i = first + 1; i < last; ++i) {  // __insertion_sort
+        VI val = e[i];
+        if (gt(val, e[first])) {
+            for (int j = i; j > first; --j) e[j] = e[j - 1];
+            e[first] = val;
+        } else {
+            int j = i;
+            while (gt(val, e[j - 1])) { e[j] = e[j - 1]; --j; }
+            e[j] = val;
+        }
+    }
+    return e[nth].i;
+}
+
+// ---- width plan of the coming iteration (speculative_decoding.py:93-102) -----------------------
+// Executed by one CTA after the live list is final.  `W` is the current width of the reference's
+// token matrix.
+__device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, int* s_tmp) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tmp[0] = 0, s_tmp[1] = 0;
+    __syncthreads();
+    if (n_active == 0 || W >= st.max_len) {
+        if (threadIdx.x == 0) { st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
+        return;
+    }
+    int dead = 0;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        bool all_pad = true;
+        for (int g = 0; g < n_active && all_pad; ++g) {
+            const int b = st.active[g];
+            if (c <= st.front[b] && st.gen[(long long)b * st.gen_ld + c] != st.pad) all_pad = false;
+        }
+        dead += all_pad ? 1 : 0;
+    }
+    if (dead) atomicAdd(&s_tmp[0], dead);
+    __syncthreads();
+    const int Wn = W + st.D + 1 - s_tmp[0];
+    int oob = 0;
+    for (int g = threadIdx.x; g < n_active; g += blockDim.x)
+        if (st.front[st.active[g]] + 1 + st.D > Wn - 1) oob = 1;
+    if (oob) atomicOr(&s_tmp[1], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.ctrl[CTRL_PREV_WIDTH] = W;
+        st.ctrl[CTRL_WIDTH] = Wn;
+        if (s_tmp[1]) { st.ctrl[CTRL_ERROR] = 1; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
+    __shared__ int s_tmp[2];
+    for (long long idx = threadIdx.x; idx < (long long)st.B * st.gen_ld; idx += blockDim.x)
+        st.gen[idx] = (idx % st.gen_ld == 0) ? st.bos : st.pad;
+    for (long long idx = threadIdx.x; idx < (long long)st.B * st.max_len; idx += blockDim.x) st.out[idx] = st.pad;
+    for (int b = threadIdx.x; b < st.B; b += blockDim.x) { st.front[b] = 0; st.active[b] = b; }
+    if (threadIdx.x < CTRL_COUNT) st.ctrl[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) st.ctrl[CTRL_N_ACTIVE] = st.B;
+    plan_next_iteration(st, st.B, 1, s_tmp);
+}
+void launch_greedy_init(const GreedyState& st, cudaStream_t s) { greedy_init_kernel<<<1, 256, 0, s>>>(st); }
+
+// ---- step-token embedding ---------------------------------------------------------------------
+template <typename ActT>
+__global__ void greedy_embed_kernel(GreedyState st, const float* __restrict__ table, const float* __restrict__ pe,
+                                    int E, float* __restrict__ x, ActT* __restrict__ xh) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int per_q = st.N * (st.D + 1);
+    if (st.ctrl[CTRL_DONE] || t >= st.ctrl[CTRL_N_ACTIVE] * per_q) return;
+    const int g = t / per_q, r = t % per_q, n = r / (st.D + 1), i = r % (st.D + 1);
+    const int b = st.active[g];
+    const int f = st.front[b];
+    const int tok = (i == 0) ? st.gen[(long long)b * st.gen_ld + f] : st.drafts[((long long)b * st.N + n) * st.D + i - 1];
+    const float* e = table + (long long)tok * E;
+    const float* p = pe + (long long)(f + i + 1) * E;
+    for (int c = lane; c < E; c += 32) {
+        float v = e[c] + p[c];
+        x[(long long)t * E + c] = v;
+        if (xh) xh[(long long)t * E + c] = from_f32<ActT>(v);
+    }
+}
+template <typename ActT>
+void launch_greedy_embed(const GreedyState& st, const float* table, const float* pe, int E,
+                         float* x, ActT* xh, cudaStream_t s) {
+    const int T = st.B * st.N * (st.D + 1);
+    greedy_embed_kernel<ActT><<<(T + 7) / 8, 256, 0, s>>>(st, table, pe, E, x, xh);
+}
+template void launch_greedy_embed<float>(const GreedyState&, const float*, const float*, int, float*, float*, cudaStream_t);
+template void launch_greedy_embed<__nv_bfloat16>(const GreedyState&, const float*, const float*, int, float*, __nv_bfloat16*, cudaStream_t);
+
+// ---- accept / retire / plan ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) greedy_accept_kernel(GreedyState st) {
+    __shared__ int s_tmp[2];
+    __shared__ int s_acc, s_tok, s_err;
+    extern __shared__ int s_fin[];  // [B] finished flag per pre-retirement slot
+    if (st.ctrl[CTRL_DONE]) return;
+    const int n_active = st.ctrl[CTRL_N_ACTIVE];
+    const int Wn = st.ctrl[CTRL_WIDTH];
+    const int iter = st.ctrl[CTRL_ITERS];
+    const int D = st.D, N = st.N;
+    if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; }
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_active; g += blockDim.x) {
+        const int b = st.active[g];
+        const int f = st.front[b];
+        int nacc[64];
+        int best_first = 0, best_val = -1;
+        for (int n = 0; n < N; ++n) {
+            const int* pr = st.pred + ((long long)g * N + n) * (D + 1);
+            const int* dr = st.drafts + ((long long)b * N + n) * D;
+            int a = 0;
+            while (a < D && dr[a] == pr[a]) ++a;
+            if (n < 64) nacc[n] = a;
+            if (a > best_val) { best_val = a; best_first = n; }
+        }
+        int pick = best_first;
+        if (st.tie_break == 0 && N < 64) pick = topk1_torch_cpu(nacc, N);
+        const int a = best_val;
+        const int* pr = st.pred + ((long long)g * N + pick) * (D + 1);
+        int* row = st.gen + (long long)b * st.gen_ld;
+        bool fin = false;
+        for (int j = 0; j <= D; ++j) {
+            const int t = (j <= a) ? pr[j] : st.pad;
+            row[f + 1 + j] = t;
+            fin |= (j <= a) && (t == st.eos);
+        }
+        st.front[b] = f + a + 1;
+        st.sel[g * 4 + 0] = b; st.sel[g * 4 + 1] = f; st.sel[g * 4 + 2] = pick; st.sel[g * 4 + 3] = a;
+        if (st.trace) {
+            int* tr = st.trace + ((long long)iter * st.B + g) * 4;
+            tr[0] = b; tr[1] = a; tr[2] = pick; tr[3] = Wn;
+        }
+        atomicAdd(&s_acc, a);
+        atomicAdd(&s_tok, a + 1);
+        s_fin[g] = fin ? 1 : 0;
+        if (fin) {
+            if (Wn > st.max_len) {
+                s_err = 2;  // the reference cannot store a finished row wider than max_len (:158)
+            } else {
+                long long* o = st.out + (long long)b * st.max_len;
+                for (int c = 0; c < Wn; ++c) o[c] = (c <= f + a + 1) ? row[c] : st.pad;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int w = 0;
+        for (int g = 0; g < n_active; ++g)
+            if (!s_fin[g]) st.active[w++] = st.active[g];
+        st.ctrl[CTRL_N_SEL] = n_active;
+        st.ctrl[CTRL_N_ACTIVE] = w;
+        st.ctrl[CTRL_ITERS] = iter + 1;
+        st.ctrl[CTRL_ACCEPTED] += s_acc;
+        st.ctrl[CTRL_TOKENS] += s_tok;
+        if (s_err) { st.ctrl[CTRL_ERROR] = s_err; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = w; st.ctrl[CTRL_N_ACTIVE] = 0; }
+        s_tmp[0] = w;
+    }
+    __syncthreads();
+    if (s_err) return;
+    const int n_left = s_tmp[0];
+    plan_next_iteration(st, n_left, Wn, s_tmp);
+}
+void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
+    greedy_accept_kernel<<<1, 256, (size_t)st.B * sizeof(int), s>>>(st);
+}
+
+// ---- KV-cache append ------------------------------------------------------------------------------
+template <typename ActT>
+__global__ void greedy_cache_append_kernel(GreedyState st, const ActT* __restrict__ qkv_all, long long qkv_layer_stride,
+                                           int qkv_ld, int E, ActT* __restrict__ kcache, ActT* __restrict__ vcache,
+                                           long long cache_layer_stride, long long cache_query_stride, int cache_ld) {
+    const int g = blockIdx.x, l = blockIdx.y;
+    if (st.ctrl[CTRL_DONE] || g >= st.ctrl[CTRL_N_SEL]) return;  // after DONE the cache is never read again
+    const int b = st.sel[g * 4 + 0], f = st.sel[g * 4 + 1], pick = st.sel[g * 4 + 2], a = st.sel[g * 4 + 3];
+    const ActT* src = qkv_all + (long long)l * qkv_layer_stride + ((long long)g * st.N + pick) * (st.D + 1) * qkv_ld;
+    ActT* kd = kcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
+    ActT* vd = vcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
+    for (int idx = threadIdx.x; idx < (a + 1) * E; idx += blockDim.x) {
+        const int i = idx / E, c = idx % E;
+        kd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + E + c];
+        vd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + 2 * E + c];
+    }
+}
+template <typename ActT>
+void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long long qkv_layer_stride,
+                                int n_layers, int qkv_ld, int E, ActT* kcache, ActT* vcache,
+                                long long cache_layer_stride, long long cache_query_stride, int cache_ld,
+                                cudaStream_t s) {
+    dim3 grid(st.B, n_layers);
+    greedy_cache_append_kernel<ActT><<<grid, 256, 0, s>>>(st, qkv_all, qkv_layer_stride, qkv_ld, E, kcache, vcache,
+                                                          cache_layer_stride, cache_query_stride, cache_ld);
+}
+template void launch_greedy_cache_append<float>(const GreedyState&, const float*, long long, int, int, int, float*, float*, long long, long long, int, cudaStream_t);
+template void launch_greedy_cache_append<__nv_bfloat16>(const GreedyState&, const __nv_bfloat16*, long long, int, int, int, __nv_bfloat16*, __nv_bfloat16*, long long, long long, int, cudaStream_t);
+
+}  // namespace ttb

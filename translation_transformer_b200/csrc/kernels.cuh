@@ -1,0 +1,103 @@
+// Kernel launchers of libttb200.  Every launcher enqueues on `stream` and never synchronises.
+//
+// Row counts that are only known on the device (the number of live queries shrinks while
+// decoding) are passed as `RowCount{max_rows, units_dev, rows_per_unit}`: the grid is sized for
+// `max_rows`, each block reads `*units_dev * rows_per_unit` and exits early beyond it.
+#pragma once
+#include "common.cuh"
+
+namespace ttb {
+
+struct RowCount {
+    int max_rows;            // host-side upper bound (grid sizing)
+    const int* units_dev;    // nullptr -> all max_rows rows are live
+    int rows_per_unit;
+    __host__ __device__ RowCount(int m = 0, const int* u = nullptr, int r = 1) : max_rows(m), units_dev(u), rows_per_unit(r) {}
+    __device__ __forceinline__ int live() const { return units_dev ? (*units_dev) * rows_per_unit : max_rows; }
+};
+
+// ---- elementwise.cu ----------------------------------------------------------------------
+void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t s);
+void launch_i32_to_i64(const int* in, long long* out, long long n, cudaStream_t s);
+void launch_mask_to_tokens(const unsigned char* mask, int* out, long long n, int pad_id, cudaStream_t s);
+// x[t] = table[tok[t]] + pe[(t % L) + 1]; also writes the low-precision copy when xh != nullptr
+template <typename ActT>
+void launch_embed_seq(const int* tok, int T, int L, const float* table, const float* pe, int E,
+                      float* x, ActT* xh, cudaStream_t s);
+// out = LN(resid + y) * g + b ; optional second LN (final norm of the stack) applied on top
+template <typename ActT>
+void launch_add_layernorm(const float* resid, const float* y, const float* g, const float* b,
+                          const float* g2, const float* b2, float* out, ActT* outh,
+                          RowCount rows, int E, cudaStream_t s);
+void launch_argmax_rows(const float* logits, int ld, int V, int* out, RowCount rows, cudaStream_t s);
+
+// ---- gemm_simt.cu : C[M,N] = A[M,K] * W[N,K]^T + bias (fp32 FMA, exact-precision path) -------
+template <typename OutT>
+void launch_gemm_f32(const float* A, int lda, const float* W, const float* bias, OutT* C, int ldc,
+                     RowCount rows, int N, int K, bool relu, cudaStream_t s);
+
+// ---- gemm_tcgen05.cu : same contract, bf16 operands, fp32 accumulation in TMEM (tcgen05.mma) ----
+// A is [M,K] bf16 row-major (lda elements), W is [N,K] bf16 row-major; both are TMA-loaded.
+template <typename OutT>
+int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias,
+                        OutT* C, int ldc, RowCount rows, int N, int K, bool relu, cudaStream_t s);
+
+// ---- attention.cu ---------------------------------------------------------------------------
+// Generic masked attention over "groups".  Queries of group g are tokens g*Lq .. g*Lq+Lq-1 of
+// `q`; its keys/values are rows kv_row0 .. kv_row0+Lk-1 with kv_row0 = (kvmap ? kvmap[g] : g) *
+// kv_group_stride.  Key j is masked when key_tok[(kvmap?kvmap[g]:g)*key_tok_stride + j] == pad_id,
+// and, when `causal`, when j > i.
+template <typename ActT>
+void launch_attention(const ActT* q, int q_ld, const ActT* k, const ActT* v, int kv_ld,
+                      ActT* out, int out_ld, int n_groups_max, const int* n_groups_dev,
+                      int Lq, int Lk, long long kv_group_stride, const int* kvmap,
+                      const int* key_tok, int key_tok_stride, int pad_id, bool causal,
+                      int heads, int head_dim, cudaStream_t s);
+
+// Speculative self-attention: group g = live query slot; b = active[g]; f = front[b].
+// Queries: rows (g*N + n)*(D+1) + i of `qkv` (q | k | v packed, row stride qkv_ld).
+// Keys: cache positions 0..f-1 of query b (masked where gen[b][j] == pad) followed by the new
+// keys i' <= i of the same draft row (i' = 0 is masked when gen[b][f] == pad).
+template <typename ActT>
+void launch_spec_self_attention(const ActT* qkv, int qkv_ld, const ActT* kcache, const ActT* vcache,
+                                long long cache_query_stride, int cache_ld, ActT* out, int out_ld,
+                                int B_max, const int* n_active_dev, const int* active, const int* front,
+                                const int* gen, int gen_ld, int pad_id, int N, int D,
+                                int heads, int head_dim, int max_cache_len, cudaStream_t s);
+
+// ---- drafting.cu ------------------------------------------------------------------------------
+// Mirrors utils/drafting.py::make_drafts on device; src is (B, L) int32 with row stride src_ld (the
+// caller skips the BOS column by passing src + 1, L - 1).  out is (B, N, Deff) int32.
+void launch_make_drafts(const int* src, int src_ld, int B, int L, int Deff, int N, int eos, int pad, int replace,
+                        int* out, cudaStream_t s);
+
+// ---- greedy.cu -------------------------------------------------------------------------------
+struct GreedyState {
+    int B, N, D, max_len, gen_ld, pad, bos, eos;
+    int* gen;          // [B][gen_ld] generated tokens (row b of the reference's token matrix)
+    int* front;        // [B] index of the last generated token
+    int* active;       // [B] compact list of live query ids (order preserved, like boolean masking)
+    int* ctrl;         // [CTRL_COUNT]
+    const int* drafts; // [B][N][D]
+    int* pred;         // [B*N*(D+1)] argmax predictions of the current iteration
+    long long* out;    // [B][max_len] finished predictions (int64 like the reference)
+    int* sel;          // [B][4] per pre-retirement slot: {query id, old front, draft index, n_accepted}
+    int* trace;        // optional [max_len][B][4] = {query id, n_accepted, draft index, width}
+    int tie_break;     // 0 = torch-CPU topk(1) emulation, 1 = lowest index
+};
+void launch_greedy_init(const GreedyState& st, cudaStream_t s);
+// embeds the (D+1) step tokens of every live draft row
+template <typename ActT>
+void launch_greedy_embed(const GreedyState& st, const float* table, const float* pe, int E,
+                         float* x, ActT* xh, cudaStream_t s);
+// picks the best draft per live query, appends tokens, retires finished queries, plans next width
+void launch_greedy_accept(const GreedyState& st, cudaStream_t s);
+// copies K/V of the accepted positions of the chosen draft (recorded in st.sel by the accept
+// kernel) into the self-attention cache, for all layers at once
+template <typename ActT>
+void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long long qkv_layer_stride,
+                                int n_layers, int qkv_ld, int E, ActT* kcache, ActT* vcache,
+                                long long cache_layer_stride, long long cache_query_stride, int cache_ld,
+                                cudaStream_t s);
+
+}  // namespace ttb

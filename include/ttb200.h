@@ -94,6 +94,16 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                     int32_t tie_break, int64_t* out_dev, int32_t* trace_dev,
                                     ttb_generate_stats* stats, void* stream);
 
+/* ---- instrumentation (bench.py): per-kernel-class CUDA-event timing on the launching stream.
+ * class_mask bit i enables class i (names via ttb_kernel_class_name); totals accumulate over
+ * generate() calls until the next ttb_engine_set_profiling. */
+int ttb_kernel_class_count(void);
+const char* ttb_kernel_class_name(int32_t id);
+int ttb_engine_set_profiling(ttb_engine* e, uint32_t class_mask);
+int ttb_engine_get_profile(ttb_engine* e, int32_t n_classes, double* ms_out, int64_t* launches_out);
+/* live queries at the start of every decoder iteration of the last generate(); returns their number */
+int ttb_engine_get_history(ttb_engine* e, int32_t* live_queries_out, int32_t capacity);
+
 /* Standalone GEMM entry used by the kernel unit tests and the roofline microbenchmark:
  * C[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU).  precision selects the kernel; A/W are fp32 for
  * TTB_PRECISION_FP32 and bf16 (uint16 storage) for TTB_PRECISION_BF16; C is fp32. */

@@ -45,6 +45,11 @@ SIGNATURES = {
     "ttb_greedy_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
+    "ttb_kernel_class_count": (C.c_int, []),
+    "ttb_kernel_class_name": (C.c_char_p, [C.c_int32]),
+    "ttb_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "ttb_engine_get_profile": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ttb_engine_get_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "ttb_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                            C.c_int32, C.c_void_p]),
 }
@@ -61,6 +66,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    import torch  # noqa: F401  (loads the CUDA runtime the library links against)
     if not LIB_PATH.exists():
         raise LibraryMissing(
             f"{LIB_PATH} not found: build it with `python -m translation_transformer_b200.build` "

@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
     if failed:
         raise RuntimeError("libttb200 build failed")
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -62,6 +62,36 @@ struct Lin {
 
 struct Norm { const float* g = nullptr; const float* b = nullptr; };
 
+// Kernel classes for the optional per-class CUDA-event timing (ttb_engine_set_profiling).
+enum KC : int {
+    KC_EMBED = 0, KC_GEMM_QKV, KC_SELF_ATTN, KC_GEMM_SELF_OUT, KC_LAYERNORM, KC_GEMM_CROSS_Q, KC_CROSS_ATTN,
+    KC_GEMM_CROSS_OUT, KC_GEMM_FFN1, KC_GEMM_FFN2, KC_GEMM_CLASSIFIER, KC_ARGMAX, KC_ACCEPT, KC_CACHE_APPEND,
+    KC_ENCODER, KC_MISC, KC_COUNT
+};
+static const char* kKcNames[KC_COUNT] = {
+    "embed", "gemm_qkv", "self_attn", "gemm_self_out", "add_layernorm", "gemm_cross_q", "cross_attn",
+    "gemm_cross_out", "gemm_ffn1", "gemm_ffn2", "gemm_classifier", "argmax", "accept", "cache_append",
+    "encoder", "misc"};
+
+struct Prof {
+    uint32_t mask = 0;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int kc; size_t e0, e1; };
+    std::vector<Rec> recs;
+    double ms[KC_COUNT] = {};
+    long long n[KC_COUNT] = {};
+    int override_kc = -1;  // when >= 0 every launch is attributed to this class (encoder)
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            pool.push_back(ev);
+        }
+        return pool[used++];
+    }
+};
+
 struct EncLayer { Lin in_proj, out_proj, ff1, ff2; Norm n1, n2; };
 struct DecLayer { Lin self_in, self_out, cross_in, cross_out, ff1, ff2; Norm n1, n2, n3; };
 
@@ -90,6 +120,9 @@ struct ttb_engine {
     cudaEvent_t poll_ev[4]{};
     cudaEvent_t t0{}, t1{};
     long long launches = 0;
+    Prof prof;
+    DevBuf hist;                 // per-iteration live-query count of the last generate()
+    std::vector<int> h_hist;
 
     int E() const { return d.embedding_dim; }
     int HD() const { return d.embedding_dim / d.num_heads; }
@@ -165,20 +198,56 @@ static Norm make_norm(ttb_engine* e, const std::string& p) {
     return n;
 }
 
+// RAII scope around one kernel launch: counts it and, when the class is being profiled, brackets it
+// with CUDA events on the launching stream.
+struct Scope {
+    ttb_engine* e;
+    cudaStream_t s;
+    int kc;
+    bool on;
+    size_t e0 = 0;
+    Scope(ttb_engine* e_, int kc_, cudaStream_t s_) : e(e_), s(s_), kc(e_->prof.override_kc >= 0 ? e_->prof.override_kc : kc_) {
+        e->launches++;
+        on = (e->prof.mask >> kc) & 1u;
+        if (on) {
+            e0 = e->prof.used;
+            cudaEventRecord(e->prof.get(), s);
+        }
+    }
+    ~Scope() {
+        if (on) {
+            size_t e1 = e->prof.used;
+            cudaEventRecord(e->prof.get(), s);
+            e->prof.recs.push_back({kc, e0, e1});
+        }
+    }
+};
+static void prof_collect(ttb_engine* e) {  // call after the stream has been synchronised
+    for (auto& r : e->prof.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->prof.pool[r.e0], e->prof.pool[r.e1]) == cudaSuccess) {
+            e->prof.ms[r.kc] += ms;
+            e->prof.n[r.kc] += 1;
+        }
+    }
+    e->prof.recs.clear();
+    e->prof.used = 0;
+}
+
 // ---- typed forward helpers ---------------------------------------------------------------------
 template <typename ActT> struct Prec;
 template <> struct Prec<float> { static constexpr bool lowp = false; };
 template <> struct Prec<__nv_bfloat16> { static constexpr bool lowp = true; };
 
 template <typename OutT>
-static int linear(ttb_engine* e, const float* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
+static int linear(ttb_engine* e, int kc, const float* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
+    Scope sc(e, kc, s);
     launch_gemm_f32<OutT>(A, lda, L.w, L.b, C, ldc, rows, L.N, L.K, relu, s);
-    e->launches++;
     return 0;
 }
 template <typename OutT>
-static int linear(ttb_engine* e, const __nv_bfloat16* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
-    e->launches++;
+static int linear(ttb_engine* e, int kc, const __nv_bfloat16* A, int lda, const Lin& L, OutT* C, int ldc, RowCount rows, bool relu, cudaStream_t s) {
+    Scope sc(e, kc, s);
     return launch_gemm_bf16_tc<OutT>(A, lda, L.wh, L.b, C, ldc, rows, L.N, L.K, relu, s);
 }
 
@@ -216,26 +285,30 @@ static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int 
     ActT* att = e->att.as<ActT>();
     ActT* hid = e->hid.as<ActT>();
     RowCount rows(T);
-    launch_embed_seq<ActT>(src32, T, Ls, e->src_emb, e->pe, E, x, xh, s);
-    e->launches++;
+    e->prof.override_kc = KC_ENCODER;
+    struct Reset { ttb_engine* e; ~Reset() { e->prof.override_kc = -1; } } reset{e};
+    { Scope sc(e, KC_ENCODER, s); launch_embed_seq<ActT>(src32, T, Ls, e->src_emb, e->pe, E, x, xh, s); }
     const int n_layers = (int)e->enc.size();
     for (int l = 0; l < n_layers; ++l) {
         const EncLayer& L = e->enc[l];
         const bool last = l + 1 == n_layers;
-        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.in_proj, qkv, 3 * E, rows, false, s)) return 1;
-        launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
-                               key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
-        e->launches++;
-        if (linear<float>(e, att, E, L.out_proj, y, E, rows, false, s)) return 1;
-        launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s);
-        e->launches++;
-        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
-        if (linear<float>(e, hid, F, L.ff2, y, E, rows, false, s)) return 1;
+        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(x, xh), E, L.in_proj, qkv, 3 * E, rows, false, s)) return 1;
+        {
+            Scope sc(e, KC_ENCODER, s);
+            launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
+                                   key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+        }
+        if (linear<float>(e, KC_ENCODER, att, E, L.out_proj, y, E, rows, false, s)) return 1;
+        { Scope sc(e, KC_ENCODER, s); launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
+        if (linear<float>(e, KC_ENCODER, hid, F, L.ff2, y, E, rows, false, s)) return 1;
         float* dst = last ? mem_out : x;
         ActT* dsth = last ? memh_out : xh;
-        launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, last ? e->enc_norm.g : nullptr, last ? e->enc_norm.b : nullptr,
-                                   dst, dsth, rows, E, s);
-        e->launches++;
+        {
+            Scope sc(e, KC_ENCODER, s);
+            launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, last ? e->enc_norm.g : nullptr, last ? e->enc_norm.b : nullptr,
+                                       dst, dsth, rows, E, s);
+        }
     }
     return 0;
 }
@@ -247,13 +320,13 @@ static int cross_kv_impl(ttb_engine* e, const float* mem, const ActT* memh, int 
     RowCount rows(rows_n);
     for (size_t l = 0; l < e->dec.size(); ++l) {
         Lin kv = e->dec[l].cross_in.rows(E, 2 * E);
-        if (linear<ActT>(e, a_view<ActT>(mem, memh), E, kv, crosskv + (long long)l * rows_n * 2 * E, 2 * E, rows, false, s)) return 1;
+        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(mem, memh), E, kv, crosskv + (long long)l * rows_n * 2 * E, 2 * E, rows, false, s)) return 1;
     }
     return 0;
 }
 
-// Decoder layers l on the token matrix in e->x / e->xh (`rows` live rows).  `self_attn` enqueues the
-// layer's self-attention given the freshly projected qkv of that layer.
+// Decoder layers on the token matrix in e->x / e->xh (`rows` live rows).  `self_attn` / `cross_attn`
+// enqueue the layer's attention kernels given the freshly projected q/k/v of that layer.
 template <typename ActT, typename SelfAttn, typename CrossAttn>
 static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long qkv_layer_stride,
                          SelfAttn self_attn, CrossAttn cross_attn, cudaStream_t s) {
@@ -269,23 +342,21 @@ static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long
         const DecLayer& L = e->dec[l];
         const bool last = l + 1 == n_layers;
         ActT* qkv = e->qkv.as<ActT>() + (qkv_layers > 1 ? (long long)l * qkv_layer_stride : 0);
-        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.self_in, qkv, 3 * E, rows, false, s)) return 1;
-        self_attn(l, qkv, att);
-        e->launches++;
-        if (linear<float>(e, att, E, L.self_out, y, E, rows, false, s)) return 1;
-        launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s);
-        e->launches++;
-        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
-        cross_attn(l, q2, att);
-        e->launches++;
-        if (linear<float>(e, att, E, L.cross_out, y, E, rows, false, s)) return 1;
-        launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, nullptr, nullptr, x, xh, rows, E, s);
-        e->launches++;
-        if (linear<ActT>(e, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
-        if (linear<float>(e, hid, F, L.ff2, y, E, rows, false, s)) return 1;
-        launch_add_layernorm<ActT>(x, y, L.n3.g, L.n3.b, last ? e->dec_norm.g : nullptr, last ? e->dec_norm.b : nullptr,
-                                   x, xh, rows, E, s);
-        e->launches++;
+        if (linear<ActT>(e, KC_GEMM_QKV, a_view<ActT>(x, xh), E, L.self_in, qkv, 3 * E, rows, false, s)) return 1;
+        { Scope sc(e, KC_SELF_ATTN, s); self_attn(l, qkv, att); }
+        if (linear<float>(e, KC_GEMM_SELF_OUT, att, E, L.self_out, y, E, rows, false, s)) return 1;
+        { Scope sc(e, KC_LAYERNORM, s); launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
+        { Scope sc(e, KC_CROSS_ATTN, s); cross_attn(l, q2, att); }
+        if (linear<float>(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, y, E, rows, false, s)) return 1;
+        { Scope sc(e, KC_LAYERNORM, s); launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear<ActT>(e, KC_GEMM_FFN1, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
+        if (linear<float>(e, KC_GEMM_FFN2, hid, F, L.ff2, y, E, rows, false, s)) return 1;
+        {
+            Scope sc(e, KC_LAYERNORM, s);
+            launch_add_layernorm<ActT>(x, y, L.n3.g, L.n3.b, last ? e->dec_norm.g : nullptr, last ? e->dec_norm.b : nullptr,
+                                       x, xh, rows, E, s);
+        }
     }
     return 0;
 }
@@ -295,13 +366,12 @@ static int encode_api(ttb_engine* e, const int64_t* src_dev, const uint8_t* mask
     const long long T = (long long)B * Ls;
     if (e->src32.ensure(T * sizeof(int))) return 1;
     int* src32 = e->src32.as<int>();
-    launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, T, s);
-    e->launches++;
+    { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, T, s); }
     const int* key_src = src32;
     if (mask_dev) {  // explicit mask: express it as a token-like array for the attention kernels
         if (e->keytok32.ensure(T * sizeof(int))) return 1;
+        Scope sc(e, KC_MISC, s);
         launch_mask_to_tokens(mask_dev, e->keytok32.as<int>(), T, e->d.src_pad_token_idx, s);
-        e->launches++;
         key_src = e->keytok32.as<int>();
     }
     if (Prec<ActT>::lowp && e->memh.ensure(T * e->E() * sizeof(ActT))) return 1;
@@ -321,22 +391,20 @@ static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, cons
     if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * e->dec.size())) return 1;
     int* tgt32 = e->tok32.as<int>();
     int* memtok = e->keytok32.as<int>();
-    launch_i64_to_i32(reinterpret_cast<const long long*>(tgt_dev), tgt32, T, s);
-    launch_mask_to_tokens(mem_mask_dev, memtok, TS, e->d.src_pad_token_idx, s);
-    e->launches += 2;
+    { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(tgt_dev), tgt32, T, s); }
+    { Scope sc(e, KC_MISC, s); launch_mask_to_tokens(mem_mask_dev, memtok, TS, e->d.src_pad_token_idx, s); }
     const ActT* memh = nullptr;
     if (Prec<ActT>::lowp) {
         if (e->memh.ensure(TS * E * sizeof(ActT))) return 1;
+        Scope sc(e, KC_MISC, s);
         launch_f32_to_bf16(memory_dev, reinterpret_cast<__nv_bfloat16*>(e->memh.p), TS * E, s);
-        e->launches++;
         memh = e->memh.as<ActT>();
     }
     ActT* crosskv = e->crosskv.as<ActT>();
     if (cross_kv_impl<ActT>(e, memory_dev, memh, (int)TS, crosskv, s)) return 1;
     float* x = e->x.as<float>();
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
-    launch_embed_seq<ActT>(tgt32, (int)T, Lt, e->tgt_emb, e->pe, E, x, xh, s);
-    e->launches++;
+    { Scope sc(e, KC_EMBED, s); launch_embed_seq<ActT>(tgt32, (int)T, Lt, e->tgt_emb, e->pe, E, x, xh, s); }
     RowCount rows((int)T);
     auto self_attn = [&](int, ActT* qkv, ActT* att) {
         launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Lt, Lt, Lt, nullptr,
@@ -348,7 +416,7 @@ static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, cons
                                memtok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
     };
     if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
-    if (linear<float>(e, a_view<ActT>(x, xh), E, e->classifier, logits_out, V, rows, false, s)) return 1;
+    if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits_out, V, rows, false, s)) return 1;
     TTB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -366,6 +434,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     const int gen_ld = max_len + D + 2;
     const int P = gen_ld;  // cache positions per query
     const long long launches0 = e->launches;
+    const int max_iters = max_len + 1;
 
     // encoder + cross-attention K/V (computed once per query, not once per draft row and iteration)
     if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
@@ -375,28 +444,26 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     if (e->drafts.ensure((size_t)B * N * D * sizeof(int)) || e->gen.ensure((size_t)B * gen_ld * sizeof(int))) return 1;
     if (e->front.ensure(B * sizeof(int)) || e->active.ensure(B * sizeof(int)) || e->ctrl.ensure(CTRL_COUNT * sizeof(int))) return 1;
     if (e->sel.ensure((size_t)B * 4 * sizeof(int)) || e->out64.ensure((size_t)B * max_len * sizeof(long long))) return 1;
+    if (e->hist.ensure((size_t)(max_iters + 1) * sizeof(int))) return 1;
+    if (ensure_work<ActT>(e, std::max(T, TS), n_dec)) return 1;
 
     TTB_CUDA_OK(cudaEventRecord(e->t0, s));
     int* src32 = e->src32.as<int>();
-    launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s);
-    e->launches++;
+    { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s); }
     float* mem = e->memory.as<float>();
     ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
     ActT* crosskv = e->crosskv.as<ActT>();
     if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
     // drafts from the source without its BOS column (speculative_decoding.py:64-73)
-    launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s);
-    e->launches++;
+    { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s); }
 
-    if (ensure_work<ActT>(e, T, n_dec)) return 1;
     GreedyState st{};
     st.B = B; st.N = N; st.D = D; st.max_len = max_len; st.gen_ld = gen_ld; st.pad = pad; st.bos = bos; st.eos = eos;
     st.gen = e->gen.as<int>(); st.front = e->front.as<int>(); st.active = e->active.as<int>(); st.ctrl = e->ctrl.as<int>();
     st.drafts = e->drafts.as<int>(); st.pred = e->pred.as<int>(); st.out = e->out64.as<long long>();
-    st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break;
-    launch_greedy_init(st, s);
-    e->launches++;
+    st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break; st.hist = e->hist.as<int>();
+    { Scope sc(e, KC_MISC, s); launch_greedy_init(st, s); }
 
     float* x = e->x.as<float>();
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
@@ -423,17 +490,17 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     constexpr int LAG = 2, RING = 4;
     int it = 0;
     bool done = false;
-    const int max_iters = max_len + 1;
     while (!done && it < max_iters) {
-        launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s);
-        e->launches++;
+        { Scope sc(e, KC_EMBED, s); launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s); }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
-        if (linear<float>(e, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
-        launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s);
-        launch_greedy_accept(st, s);
-        launch_greedy_cache_append<ActT>(st, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, E, kc, vc, cache_l_stride,
-                                         cache_q_stride, E, s);
-        e->launches += 3;
+        if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
+        { Scope sc(e, KC_ARGMAX, s); launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_greedy_accept(st, s); }
+        {
+            Scope sc(e, KC_CACHE_APPEND, s);
+            launch_greedy_cache_append<ActT>(st, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, E, kc, vc, cache_l_stride,
+                                             cache_q_stride, E, s);
+        }
         TTB_CUDA_OK(cudaMemcpyAsync(e->h_ctrl + (it % RING) * CTRL_COUNT, st.ctrl, CTRL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         TTB_CUDA_OK(cudaEventRecord(e->poll_ev[it % RING], s));
         if (it >= LAG) {
@@ -448,8 +515,12 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     TTB_CUDA_OK(cudaEventRecord(e->t1, s));
     TTB_CUDA_OK(cudaStreamSynchronize(s));
     TTB_CUDA_OK(cudaGetLastError());
+    prof_collect(e);
     const int* c = e->h_ctrl;
     TTB_CHECK(c[CTRL_DONE] == 1, "greedy decoding loop did not terminate within max_len + 1 iterations");
+    e->h_hist.assign((size_t)c[CTRL_ITERS], 0);
+    if (c[CTRL_ITERS] > 0)
+        TTB_CUDA_OK(cudaMemcpy(e->h_hist.data(), st.hist, (size_t)c[CTRL_ITERS] * sizeof(int), cudaMemcpyDeviceToHost));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->t0, e->t1);
     if (stats) {
@@ -522,10 +593,11 @@ void ttb_engine_destroy(ttb_engine* e) {
     }
     DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
                       &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
-                      &e->active, &e->ctrl, &e->sel, &e->out64};
+                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist};
     for (DevBuf* b : bufs) b->release();
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->prof.pool) cudaEventDestroy(ev);
     if (e->t0) cudaEventDestroy(e->t0);
     if (e->t1) cudaEventDestroy(e->t1);
     delete e;
@@ -669,6 +741,29 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                              replace_token, tie_break, out_dev, trace_dev, stats, s),
                         greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
                                                   replace_token, tie_break, out_dev, trace_dev, stats, s));
+}
+
+int ttb_kernel_class_count(void) { return KC_COUNT; }
+const char* ttb_kernel_class_name(int32_t id) { return (id >= 0 && id < KC_COUNT) ? kKcNames[id] : ""; }
+
+int ttb_engine_set_profiling(ttb_engine* e, uint32_t class_mask) {
+    TTB_CHECK(e, "null engine");
+    e->prof.mask = class_mask;
+    for (int i = 0; i < KC_COUNT; ++i) { e->prof.ms[i] = 0.0; e->prof.n[i] = 0; }
+    return 0;
+}
+
+int ttb_engine_get_profile(ttb_engine* e, int32_t n_classes, double* ms_out, int64_t* launches_out) {
+    TTB_CHECK(e && ms_out && launches_out, "null argument");
+    for (int i = 0; i < n_classes && i < KC_COUNT; ++i) { ms_out[i] = e->prof.ms[i]; launches_out[i] = e->prof.n[i]; }
+    return 0;
+}
+
+int ttb_engine_get_history(ttb_engine* e, int32_t* live_queries_out, int32_t capacity) {
+    TTB_CHECK(e && live_queries_out, "null argument");
+    const int n = (int)e->h_hist.size();
+    for (int i = 0; i < n && i < capacity; ++i) live_queries_out[i] = e->h_hist[i];
+    return n;
 }
 
 int ttb_gemm(int32_t precision, const void* A_dev, const void* W_dev, const float* bias_dev, float* C_dev,

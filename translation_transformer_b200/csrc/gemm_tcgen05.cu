@@ -1,11 +1,323 @@
-// placeholder replaced below
+// bf16 GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU).
+//
+//   * operands: both K-major bf16 (activations [M,K], nn.Linear weights [N,K]) -> no transposes;
+//   * TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) stages 128 x 64 A tiles and BN x 64 W tiles
+//     into a 3-deep shared-memory ring guarded by full/empty mbarriers;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) with the
+//     fp32 accumulator tile in TMEM; tcgen05.commit releases ring slots and signals the epilogue;
+//   * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per warp
+//     instruction), add bias, apply ReLU, convert and store full 32-byte sectors per thread.
+// One output tile per CTA, two CTAs per SM (96 KB smem, 128 TMEM columns each) so that the epilogue
+// of one tile overlaps the main loop of another.  The live row count is read on the device
+// (RowCount): CTAs beyond it exit before touching any barrier.
 #include "kernels.cuh"
+
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <type_traits>
+
 namespace ttb {
+
+namespace tc {
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major tile stored with the 128-byte swizzle: rows of 128
+// bytes, 8-row atoms 1024 bytes apart (SBO), descriptor version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major), 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <typename OutT>
-int launch_gemm_bf16_tc(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, OutT*, int, RowCount, int, int, bool, cudaStream_t) {
-    set_last_error("bf16 tcgen05 GEMM not built yet");
-    return 3;
+__device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32], int n_valid, bool vec_ok);
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* dst, const float (&v)[32], int n_valid, bool vec_ok) {
+    if (vec_ok && n_valid == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < n_valid) dst[j] = v[j];
+    }
+}
+template <>
+__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32], int n_valid, bool vec_ok) {
+    if (vec_ok && n_valid == 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2);
+            u.w = *reinterpret_cast<uint32_t*>(&p3);
+            reinterpret_cast<uint4*>(dst)[j] = u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < n_valid) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(THREADS, 2)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const float* __restrict__ bias, OutT* __restrict__ C, int ldc, RowCount rows, int N, int K, int relu) {
+    const int M = rows.live();
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= M) return;  // uniform per CTA, before any barrier / TMEM allocation
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024-byte alignment
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    // barriers: full[0..S), empty[S..2S), tmem_full[2S]; tmem base pointer slot after them
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            mbar_init(tmem_full_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                const uint32_t a_dst = base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                tma_load_2d(a_dst, &tmA, kb * BK, m0, full_bar(s));
+                tma_load_2d(b_dst, &tmB, kb * BK, n0, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t a_src = base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(a_src + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(b_src + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);     // accumulator complete
+        }
+    } else {  // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (n0 % 8 == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= N) break;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (row < M) {
+                float v[32];
+                const int n_valid = min(32, N - (n0 + c0));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(r[j]);
+                    if (bias && j < n_valid) t += __ldg(bias + n0 + c0 + j);
+                    if (relu) t = fmaxf(t, 0.f);
+                    v[j] = t;
+                }
+                store_chunk<OutT>(C + (long long)row * ldc + n0 + c0, v, n_valid, vec_ok);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---- host: tensor-map cache -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = box_rows x 64, 128-byte swizzle
+static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    using Key = std::tuple<const void*, int, int, int, int>;
+    static std::map<Key, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Key key{ptr, rows, cols, ld, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+        return 4;
+    }
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows=" + std::to_string(rows) +
+                       " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld) + ")");
+        return 4;
+    }
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+    *out = m;
+    return 0;
+}
+}  // namespace tc
+
+template <typename OutT>
+int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias,
+                        OutT* C, int ldc, RowCount rows, int N, int K, bool relu, cudaStream_t s) {
+    using namespace tc;
+    if (rows.max_rows <= 0 || N <= 0) return 0;
+    if (K % BK != 0 || lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) {
+        set_last_error("tcgen05 GEMM needs K % 64 == 0, lda % 8 == 0 and 16-byte aligned operands");
+        return 4;
+    }
+    CUtensorMap tmA, tmB;
+    if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
+    if (int rc = get_tensor_map(W, N, K, K, BN, &tmB)) return rc;
+    static bool attr_set[2] = {false, false};
+    constexpr int which = std::is_same<OutT, float>::value ? 0 : 1;
+    if (!attr_set[which]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set[which] = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (rows.max_rows + BM - 1) / BM);
+    gemm_bf16_tc_kernel<OutT><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
+    return 0;
 }
 template int launch_gemm_bf16_tc<float>(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, float*, int, RowCount, int, int, bool, cudaStream_t);
 template int launch_gemm_bf16_tc<__nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, RowCount, int, int, bool, cudaStream_t);
-}
+
+}  // namespace ttb

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) greedy_accept_kernel(GreedyState st) {
     const int Wn = st.ctrl[CTRL_WIDTH];
     const int iter = st.ctrl[CTRL_ITERS];
     const int D = st.D, N = st.N;
-    if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; }
+    if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; if (st.hist) st.hist[iter] = n_active; }
     __syncthreads();
     for (int g = threadIdx.x; g < n_active; g += blockDim.x) {
         const int b = st.active[g];

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: speculative greedy decoding, product-prediction Molecular Transformer.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm: libttb200 on B200)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU port of the reference)
+
+One "step" = one batch of `--batch-size` synthetic USPTO-MIT-shape queries decoded to completion
+through `TranslationInferenceGreedySpeculative.generate` (BASELINE.json configs[1]).  Multi-GPU runs
+shard the queries (each rank decodes its own batches, weak scaling) and all-gather the predictions.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+from translation_transformer_b200.synthetic import synthetic_sources  # noqa: E402
+from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, random_init_state_dict  # noqa: E402
+
+PAD, BOS, EOS, REPLACE = 0, 1, 2, 7   # REPLACE plays the role of the "c" token (lightning_model.py:117)
+METRIC = "SMILES/sec (greedy speculative, product prediction)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch-size", type=int, default=32)
+    ap.add_argument("--draft-len", type=int, default=10)
+    ap.add_argument("--n-drafts", type=int, default=23)
+    ap.add_argument("--max-len", type=int, default=200)
+    ap.add_argument("--vocab", type=int, default=288)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--eos-bias", type=float, default=0.0, help="added to the classifier bias of EOS (0 = plain random init)")
+    ap.add_argument("--pad-bias", type=float, default=0.0)
+    ap.add_argument("--cpu-queries", type=int, default=1, help="queries per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_weights(args):
+    cfg = ModelConfig(src_vocab_size=args.vocab, tgt_vocab_size=args.vocab, **PRODUCT_PREDICTION)
+    sd = {k: v.clone() for k, v in random_init_state_dict(cfg, args.seed).items()}
+    sd["tgt_token_featurizer.embedding.weight"] = sd["src_token_featurizer.embedding.weight"]
+    sd["next_token_classifier.bias"][EOS] += args.eos_bias
+    sd["next_token_classifier.bias"][PAD] += args.pad_bias
+    return cfg, sd
+
+
+def workload_name(args):
+    return (f"product-prediction greedy speculative bs={args.batch_size} draft_len={args.draft_len} "
+            f"n_drafts={args.n_drafts} max_len={args.max_len}; Molecular Transformer 256/2048/4+4/8 random-init "
+            f"(seed {args.seed}, eos_bias {args.eos_bias}, pad_bias {args.pad_bias}), vocab {args.vocab}; "
+            f"synthetic USPTO-MIT-shape sources (20..198 tokens, mean 80)")
+
+
+def batch_for(args, rank, step):
+    return synthetic_sources(args.batch_size, args.vocab, seed=100003 * (rank + 1) + step)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def class_work(name, args, cfg, hist, src_lens_mean):
+    """Algorithmic (flops, bytes) of ALL launches of a kernel class over the iterations in `hist`
+    (live queries per iteration); per-unit figures are in DESIGN.md §4."""
+    E, F, V, L = cfg.embedding_dim, cfg.feedforward_dim, cfg.tgt_vocab_size, cfg.num_decoder_layers
+    per_q = args.n_drafts * (args.draft_len + 1)
+    rows = sum(h * per_q for h in hist)           # token rows summed over iterations
+    ab = 2 if args.precision == "bf16" else 4      # activation bytes
+    gemm = {"gemm_qkv": (E, 3 * E, ab), "gemm_self_out": (E, E, 4), "gemm_cross_q": (E, E, ab), "gemm_cross_out": (E, E, 4),
+            "gemm_ffn1": (E, F, ab), "gemm_ffn2": (F, E, 4)}
+    if name in gemm:
+        K, N, ob = gemm[name]
+        return 2.0 * rows * K * N * L, (rows * K * ab + rows * N * ob) * L + K * N * ab * L * len(hist)
+    if name == "gemm_classifier":
+        return 2.0 * rows * E * V, rows * E * ab + rows * V * 4 + E * V * ab * len(hist)
+    if name == "cross_attn":
+        lk = src_lens_mean
+        return 4.0 * rows * lk * E * L, (rows * E * ab * 2 + sum(hist) * lk * 2 * E * ab) * L
+    if name == "self_attn":
+        # keys: accepted prefix (grows ~1 token/iteration on average) + causal half of the draft row
+        flops = sum(4.0 * h * per_q * (it + 1 + (args.draft_len + 2) / 2.0) * E for it, h in enumerate(hist)) * L
+        byts = sum(h * (per_q * 4 * E * ab + (it + 1) * 2 * E * ab) for it, h in enumerate(hist)) * L
+        return flops, byts
+    if name == "add_layernorm":
+        return 8.0 * rows * E * 3 * L, rows * E * (4 + 4 + 4 + ab) * 3 * L
+    return 0.0, 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the CPU port of the reference's algorithm (oracle/), all host threads.
+    Each step decodes a bounded sample (`--cpu-queries` queries) of the step's batch."""
+    if rank != 0:
+        return
+    from oracle.greedy_speculative import GreedySpeculativeOracle
+    from oracle.transformer import OracleTransformer
+    cfg, sd = build_weights(args)
+    model = OracleTransformer(sd, cfg.num_heads)
+    nq = args.cpu_queries
+    times = []
+    for i in range(args.warmup + args.steps):
+        src = batch_for(args, 0, i)[:nq]
+        gen = GreedySpeculativeOracle(model, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
+        t0 = time.perf_counter()
+        gen.generate(src)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = nq * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "SMILES/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": f"{nq} of {args.batch_size} queries per step"},
+            "cpu_baseline": {"value": value, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{nq} query per step, {len(times)} steps, full decode (max_len {args.max_len})"},
+            "e2e": {"value": value, "unit": "SMILES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from translation_transformer_b200 import _lib
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    from translation_transformer_b200.model import B200Transformer
+
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, sd = build_weights(args)
+    eng = B200Transformer(cfg, sd, precision=args.precision, device=local_rank)
+    gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
+    lib = eng.lib
+    n_total = args.warmup + args.steps + 1
+    host = [batch_for(args, rank, i).pin_memory() for i in range(n_total)]
+    devb = [h.to(dev) for h in host]
+    out_host = torch.empty(args.batch_size, 1, args.max_len, dtype=torch.int64).pin_memory()
+    gathered = torch.empty(world * args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    errors = []
+
+    def one_step(i, e2e):
+        flush.zero_()
+        src = host[i].to(dev, non_blocking=True) if e2e else devb[i]
+        try:
+            out = gen.generate(src)
+        except RuntimeError as ex:   # reference-faithful failure modes (see oracle/greedy_speculative.py)
+            errors.append(str(ex)[:80])
+            out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        if e2e:
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, first):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for k in range(args.steps):
+            one_step(first + k, e2e)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up (also sizes every workspace) -------------------------------------------------
+    for i in range(args.warmup):
+        one_step(i, False)
+    # ---- one instrumented step: CUDA-event time of every kernel class -> dominant kernel ---------
+    n_cls = lib.ttb_kernel_class_count()
+    names = [lib.ttb_kernel_class_name(i).decode() for i in range(n_cls)]
+    lib.ttb_engine_set_profiling(eng._h, (1 << n_cls) - 1)
+    one_step(args.warmup + args.steps, False)
+    ms_arr, n_arr = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
+    lib.ttb_engine_get_profile(eng._h, n_cls, ms_arr, n_arr)
+    shares = {names[i]: {"ms": round(ms_arr[i], 3), "launches": int(n_arr[i])} for i in range(n_cls) if n_arr[i]}
+    tot_ms = sum(v["ms"] for v in shares.values()) or 1.0
+    for v in shares.values():
+        v["share"] = round(v["ms"] / tot_ms, 4)
+    dominant = max((n for n in shares if n not in ("encoder", "misc")), key=lambda n: shares[n]["ms"])
+    dom_id = names.index(dominant)
+
+    # ---- timed region 1: inputs resident in HBM; dominant kernel bracketed by events ------------
+    lib.ttb_engine_set_profiling(eng._h, 1 << dom_id)
+    calls0, launches0, acc0, tok0 = gen.model_calls_num, gen.gpu_launches, gen.accepted_tokens_num, gen.produced_tokens_num
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    hists = []
+    ev_ms = timed_ms = None
+    # history is per generate() call: collect it inside the loop through a wrapper
+    orig_generate = gen.generate
+
+    def generate_and_log(src):
+        out = orig_generate(src)
+        buf = (C.c_int32 * (args.max_len + 2))()
+        n = lib.ttb_engine_get_history(eng._h, buf, args.max_len + 2)
+        hists.append(list(buf[:n]))
+        return out
+
+    gen.generate = generate_and_log
+    timed_ms = timed(False, args.warmup)
+    gen.generate = orig_generate
+    clocks = sampler.stop() if rank == 0 else None
+    lib.ttb_engine_get_profile(eng._h, n_cls, ms_arr, n_arr)
+    dom_ms, dom_launches = ms_arr[dom_id], int(n_arr[dom_id])
+    lib.ttb_engine_set_profiling(eng._h, 0)
+    calls = gen.model_calls_num - calls0
+    launches = gen.gpu_launches - launches0
+    accepted, produced = gen.accepted_tokens_num - acc0, gen.produced_tokens_num - tok0
+
+    # ---- timed region 2: end to end through the public API with host buffers ---------------------
+    e2e_ms = timed(True, args.warmup)
+
+    lt = torch.tensor([launches, calls, accepted, produced], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    launches, calls, accepted, produced = [int(x) for x in lt.tolist()]
+
+    if rank == 0:
+        queries = world * args.steps * args.batch_size
+        value = queries / (timed_ms / 1000.0)
+        e2e_value = queries / (e2e_ms / 1000.0)
+        peaks = measured_peaks()
+        src_lens_mean = float(sum((h != PAD).sum().item() for h in host[args.warmup:args.warmup + args.steps])) / (args.steps * args.batch_size)
+        flops = byts = 0.0
+        for h in hists:
+            f, b = class_work(dominant, args, cfg, h, src_lens_mean)
+            flops += f
+            byts += b
+        intensity = flops / max(byts, 1.0)
+        balance = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        dom_s = max(dom_ms, 1e-9) / 1000.0
+        if intensity >= balance:
+            roof = {"bound": "tensor", "achieved": flops / dom_s / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": byts / dom_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": None, "kernel": dominant,
+                     "launches": dom_launches, "avg_launch_us": 1000.0 * dom_ms / max(dom_launches, 1),
+                     "algorithmic_flops_per_launch": flops / max(dom_launches, 1), "algorithmic_bytes_per_launch": byts / max(dom_launches, 1),
+                     "peak_source": peaks["source"], "share_of_step": shares[dominant]["share"]})
+        line = {"metric": METRIC, "value": value, "unit": "SMILES/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_batch": world * args.batch_size,
+                           "parallelism": f"dp{world} (queries sharded, predictions all-gathered)" if world > 1 else "single GPU",
+                           "l2": "256 MiB buffer written between steps (L2 flush)"},
+                "e2e": {"value": e2e_value, "unit": "SMILES/s", "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": int(host[args.warmup].numel() * 8),
+                        "d2h_bytes_per_step": int(out_host.numel() * 8)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_shares": shares,
+                "decoder_calls": calls, "accepted_tokens_per_call": accepted / max(calls, 1),
+                "produced_tokens": produced, "reference_failures": errors[:3]}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.greedy_speculative import GreedySpeculativeOracle
+            from oracle.transformer import OracleTransformer
+            nq = args.cpu_queries
+            o = GreedySpeculativeOracle(OracleTransformer(sd, cfg.num_heads), args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
+            t0 = time.perf_counter()
+            try:
+                o.generate(host[args.warmup][:nq].clone())
+            except RuntimeError:
+                pass
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nq / dt, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"first {nq} query of the first timed batch, full decode, {o.model_calls_num} decoder calls, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

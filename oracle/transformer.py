@@ -92,8 +92,14 @@ class OracleTransformer:
         kh = k.view(B, Lk, H, dh).transpose(1, 2)
         vh = v.view(B, Lk, H, dh).transpose(1, 2)
         s = (qh @ kh.transpose(-1, -2)) * (1.0 / math.sqrt(dh)) + bias
-        p = torch.softmax(s, dim=-1)
-        o = (p @ vh).transpose(1, 2).reshape(B, Lq, E)
+        if self.lowp:
+            # tensor-core attention of the bf16 path: un-normalised probabilities are rounded to
+            # bf16 for the P.V product, the normaliser is summed in fp32 from the unrounded values
+            pu = torch.exp(s - s.amax(dim=-1, keepdim=True))
+            o = (_bf16_round(pu) @ vh) / pu.sum(dim=-1, keepdim=True)
+        else:
+            o = torch.softmax(s, dim=-1) @ vh
+        o = o.transpose(1, 2).reshape(B, Lq, E)
         return self._store(o)
 
     def _mha(self, prefix, xq, xkv, bias):

@@ -53,9 +53,11 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const ActT* __restrict__ q, int q_ld, const ActT* __restrict__ k, const ActT* __restrict__ v, int kv_ld,
                  ActT* __restrict__ out, int out_ld, const int* __restrict__ n_groups_dev,
                  int Lq, int Lk, long long kv_group_stride, const int* __restrict__ kvmap,
-                 const int* __restrict__ key_tok, int key_tok_stride, int pad_id, int causal, float scale) {
+                 const int* __restrict__ key_tok, int key_tok_stride, int pad_id, int causal, float scale,
+                 const int* __restrict__ lk_dev) {
     const int g = blockIdx.z, h = blockIdx.y;
     if (n_groups_dev && g >= *n_groups_dev) return;
+    if (lk_dev) { Lk = *lk_dev; kv_group_stride = Lk; key_tok_stride = Lk; }  // graph replay: source length read on device
     const int kvg = kvmap ? kvmap[g] : g;
     const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
     const bool live = i < Lq;
@@ -106,21 +108,21 @@ void launch_attention(const ActT* q, int q_ld, const ActT* k, const ActT* v, int
                       ActT* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                       int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                       const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                      int heads, int head_dim, cudaStream_t s) {
+                      int heads, int head_dim, cudaStream_t s, const int* lk_dev) {
     if (n_groups_max <= 0 || Lq <= 0) return;
     dim3 grid((Lq + ATT_THREADS - 1) / ATT_THREADS, heads, n_groups_max);
     const float scale = 1.0f / sqrtf((float)head_dim);
 #define TTB_ATT(HDV)                                                                                         \
     attention_kernel<ActT, HDV><<<grid, ATT_THREADS, 0, s>>>(q, q_ld, k, v, kv_ld, out, out_ld, n_groups_dev, \
                                                              Lq, Lk, kv_group_stride, kvmap, key_tok,        \
-                                                             key_tok_stride, pad_id, causal ? 1 : 0, scale)
+                                                             key_tok_stride, pad_id, causal ? 1 : 0, scale, lk_dev)
     if (head_dim == 16) TTB_ATT(16);
     else if (head_dim == 32) TTB_ATT(32);
     else if (head_dim == 64) TTB_ATT(64);
 #undef TTB_ATT
 }
-template void launch_attention<float>(const float*, int, const float*, const float*, int, float*, int, int, const int*, int, int, long long, const int*, const int*, int, int, bool, int, int, cudaStream_t);
-template void launch_attention<__nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, const __nv_bfloat16*, int, __nv_bfloat16*, int, int, const int*, int, int, long long, const int*, const int*, int, int, bool, int, int, cudaStream_t);
+template void launch_attention<float>(const float*, int, const float*, const float*, int, float*, int, int, const int*, int, int, long long, const int*, const int*, int, int, bool, int, int, cudaStream_t, const int*);
+template void launch_attention<__nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, const __nv_bfloat16*, int, __nv_bfloat16*, int, int, const int*, int, int, long long, const int*, const int*, int, int, bool, int, int, cudaStream_t, const int*);
 
 // ------------------------------------------------------------------------------------------------
 constexpr int SPEC_THREADS = 256;

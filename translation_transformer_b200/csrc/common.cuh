@@ -63,6 +63,8 @@ enum Ctrl : int {
     CTRL_N_SEL = 8,      // rows recorded in GreedyState::sel by the last accept (live queries before retirement)
     CTRL_N_LEFT = 9,     // live queries left when DONE was raised (N_ACTIVE is zeroed then so that every
                          // row-counted kernel of an already-enqueued iteration exits immediately)
+    CTRL_LS = 10,        // source length of the batch (read by the cross-attention kernels so that the
+                         // captured decoding graph does not depend on it)
     CTRL_COUNT = 16
 };
 

@@ -124,13 +124,71 @@ __global__ void add_layernorm_kernel(const float* __restrict__ resid, const floa
         }
     }
 }
+// E == 256 fast path: one warp per row, each lane owns 8 consecutive columns (two 16-byte loads per
+// operand, one 16-byte bf16 store), i.e. every warp instruction moves a whole 1 KB / 512 B row.
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+add_layernorm256_kernel(const float* __restrict__ resid, const float* __restrict__ y,
+                        const float* __restrict__ g, const float* __restrict__ b,
+                        const float* __restrict__ g2, const float* __restrict__ b2,
+                        float* __restrict__ out, ActT* __restrict__ outh, RowCount rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows.live()) return;
+    const long long base = (long long)row * 256 + lane * 8;
+    float v[8];
+    {
+        const float4 r0 = *reinterpret_cast<const float4*>(resid + base), r1 = *reinterpret_cast<const float4*>(resid + base + 4);
+        v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w; v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
+        if (y) {
+            const float4 y0 = *reinterpret_cast<const float4*>(y + base), y1 = *reinterpret_cast<const float4*>(y + base + 4);
+            v[0] += y0.x; v[1] += y0.y; v[2] += y0.z; v[3] += y0.w; v[4] += y1.x; v[5] += y1.y; v[6] += y1.z; v[7] += y1.w;
+        }
+    }
+    auto normalise = [&](const float* gg, const float* bb) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[k];
+        const float mean = warp_sum(sum) * (1.0f / 256.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; sq += d * d; }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / 256.0f) + 1e-5f);
+        const float4 g0 = *reinterpret_cast<const float4*>(gg + lane * 8), g1 = *reinterpret_cast<const float4*>(gg + lane * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bb + lane * 8), b1 = *reinterpret_cast<const float4*>(bb + lane * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * gv[k] + bv[k];
+    };
+    normalise(g, b);
+    if (g2) normalise(g2, b2);
+    *reinterpret_cast<float4*>(out + base) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(out + base + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (outh) {
+        if constexpr (sizeof(ActT) == 2) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(outh + base) = u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) outh[base + k] = from_f32<ActT>(v[k]);
+        }
+    }
+}
+
 template <typename ActT>
 void launch_add_layernorm(const float* resid, const float* y, const float* g, const float* b,
                           const float* g2, const float* b2, float* out, ActT* outh,
                           RowCount rows, int E, cudaStream_t s) {
     if (rows.max_rows <= 0) return;
     int grid = (rows.max_rows + 7) / 8;
-    if (E <= 256)
+    if (E == 256)
+        add_layernorm256_kernel<ActT><<<grid, 256, 0, s>>>(resid, y, g, b, g2, b2, out, outh, rows);
+    else if (E <= 256)
         add_layernorm_kernel<ActT, 8><<<grid, 256, 0, s>>>(resid, y, g, b, g2, b2, out, outh, rows, E);
     else
         add_layernorm_kernel<ActT, 32><<<grid, 256, 0, s>>>(resid, y, g, b, g2, b2, out, outh, rows, E);

@@ -4,6 +4,7 @@
 #include "../../include/ttb200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -16,11 +17,14 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 
+static long long g_alloc_gen = 0;  // bumped whenever a workspace buffer moves (invalidates captured graphs)
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
+        ++g_alloc_gen;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -121,6 +125,12 @@ struct ttb_engine {
     cudaEvent_t t0{}, t1{};
     long long launches = 0;
     Prof prof;
+    // decoding loop: private stream + one captured CUDA graph per (shape, buffers) configuration
+    cudaStream_t stream = nullptr;
+    cudaEvent_t join_ev{};
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_key[12] = {};
+    long long graph_launches = 0;
     DevBuf hist;                 // per-iteration live-query count of the last generate()
     std::vector<int> h_hist;
 
@@ -251,6 +261,40 @@ static int linear(ttb_engine* e, int kc, const __nv_bfloat16* A, int lda, const 
     return launch_gemm_bf16_tc<OutT>(A, lda, L.wh, L.b, C, ldc, rows, L.N, L.K, relu, s);
 }
 
+// Attention dispatch: fp32 path -> SIMT kernels (exact), bf16 path -> tensor-core kernels
+// (TTB_ATTN_SIMT=1 forces the SIMT kernels for A/B comparisons).
+static bool attn_simt_forced() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TTB_ATTN_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+static void attn(const float* q, int q_ld, const float* k, const float* v, int kv_ld, float* out, int out_ld, int ng, const int* ng_dev,
+                 int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad, bool causal, int H, int HD, cudaStream_t s,
+                 const int* lk_dev = nullptr) {
+    launch_attention<float>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
+}
+static void attn(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* k, const __nv_bfloat16* v, int kv_ld, __nv_bfloat16* out, int out_ld,
+                 int ng, const int* ng_dev, int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad,
+                 bool causal, int H, int HD, cudaStream_t s, const int* lk_dev = nullptr) {
+    if (attn_simt_forced())
+        launch_attention<__nv_bfloat16>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
+    else
+        launch_attention_mma(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
+}
+static void spec_attn(const float* qkv, int ld, const float* kc, const float* vc, long long cqs, int cld, float* out, int old, int B,
+                      const int* na, const int* active, const int* front, const int* gen, int gen_ld, int pad, int N, int D, int H,
+                      int HD, int P, cudaStream_t s) {
+    launch_spec_self_attention<float>(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, P, s);
+}
+static void spec_attn(const __nv_bfloat16* qkv, int ld, const __nv_bfloat16* kc, const __nv_bfloat16* vc, long long cqs, int cld,
+                      __nv_bfloat16* out, int old, int B, const int* na, const int* active, const int* front, const int* gen,
+                      int gen_ld, int pad, int N, int D, int H, int HD, int P, cudaStream_t s) {
+    if (attn_simt_forced())
+        launch_spec_self_attention<__nv_bfloat16>(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, P, s);
+    else
+        launch_spec_self_attention_mma(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, s);
+}
+
 // GEMM A-operand view of the residual stream: fp32 path reads x itself, bf16 path its bf16 copy
 template <typename ActT> static const ActT* a_view(const float* x, const ActT* xh);
 template <> const float* a_view<float>(const float* x, const float*) { return x; }
@@ -295,7 +339,7 @@ static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int 
         if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(x, xh), E, L.in_proj, qkv, 3 * E, rows, false, s)) return 1;
         {
             Scope sc(e, KC_ENCODER, s);
-            launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
+            attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
                                    key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
         }
         if (linear<float>(e, KC_ENCODER, att, E, L.out_proj, y, E, rows, false, s)) return 1;
@@ -315,12 +359,14 @@ static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int 
 
 // Cross-attention K/V of every decoder layer from the encoder memory: crosskv[l] = (B*Ls, 2E)
 template <typename ActT>
-static int cross_kv_impl(ttb_engine* e, const float* mem, const ActT* memh, int rows_n, ActT* crosskv, cudaStream_t s) {
+static int cross_kv_impl(ttb_engine* e, const float* mem, const ActT* memh, int rows_n, ActT* crosskv, cudaStream_t s,
+                         long long layer_stride = 0) {
     const int E = e->E();
     RowCount rows(rows_n);
+    if (layer_stride == 0) layer_stride = (long long)rows_n * 2 * E;
     for (size_t l = 0; l < e->dec.size(); ++l) {
         Lin kv = e->dec[l].cross_in.rows(E, 2 * E);
-        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(mem, memh), E, kv, crosskv + (long long)l * rows_n * 2 * E, 2 * E, rows, false, s)) return 1;
+        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(mem, memh), E, kv, crosskv + (long long)l * layer_stride, 2 * E, rows, false, s)) return 1;
     }
     return 0;
 }
@@ -407,12 +453,12 @@ static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, cons
     { Scope sc(e, KC_EMBED, s); launch_embed_seq<ActT>(tgt32, (int)T, Lt, e->tgt_emb, e->pe, E, x, xh, s); }
     RowCount rows((int)T);
     auto self_attn = [&](int, ActT* qkv, ActT* att) {
-        launch_attention<ActT>(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Lt, Lt, Lt, nullptr,
+        attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Lt, Lt, Lt, nullptr,
                                tgt32, Lt, e->d.tgt_pad_token_idx, true, H, HD, s);
     };
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
         const ActT* kv = crosskv + (long long)l * TS * 2 * E;
-        launch_attention<ActT>(q2, E, kv, kv + E, 2 * E, att, E, B, nullptr, Lt, Ls, Ls, nullptr,
+        attn(q2, E, kv, kv + E, 2 * E, att, E, B, nullptr, Lt, Ls, Ls, nullptr,
                                memtok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
     };
     if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
@@ -424,11 +470,20 @@ static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, cons
 template <typename ActT>
 static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int draft_len, int N,
                       int pad, int bos, int eos, int replace, int tie_break, int64_t* out_dev, int32_t* trace_dev,
-                      ttb_generate_stats* stats, cudaStream_t s) {
+                      ttb_generate_stats* stats, cudaStream_t user_stream) {
     const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
     const int n_dec = (int)e->dec.size();
+    // the loop runs on the engine's own stream (graph capture is not allowed on the legacy default
+    // stream); it is ordered after the caller's stream and fully synchronised before returning
+    cudaStream_t s = e->stream;
+    TTB_CUDA_OK(cudaEventRecord(e->join_ev, user_stream));
+    TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
     const int D = std::min(std::max(1, draft_len), max_len);  // make_drafts(min_draft_len=1, max_draft_len=max_len)
     const long long TS = (long long)B * Ls;
+    // buffers that depend on the source length are sized for a rounded-up capacity so that batches of
+    // different length neither reallocate nor invalidate the captured graph
+    const int Ls_cap = std::max(256, (Ls + 63) / 64 * 64);
+    const long long TS_cap = (long long)B * Ls_cap;
     const int per_q = N * (D + 1);
     const long long T = (long long)B * per_q;
     const int gen_ld = max_len + D + 2;
@@ -437,15 +492,15 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     const int max_iters = max_len + 1;
 
     // encoder + cross-attention K/V (computed once per query, not once per draft row and iteration)
-    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
-    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
-    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
     if (e->kcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT)) || e->vcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT))) return 1;
     if (e->drafts.ensure((size_t)B * N * D * sizeof(int)) || e->gen.ensure((size_t)B * gen_ld * sizeof(int))) return 1;
     if (e->front.ensure(B * sizeof(int)) || e->active.ensure(B * sizeof(int)) || e->ctrl.ensure(CTRL_COUNT * sizeof(int))) return 1;
     if (e->sel.ensure((size_t)B * 4 * sizeof(int)) || e->out64.ensure((size_t)B * max_len * sizeof(long long))) return 1;
     if (e->hist.ensure((size_t)(max_iters + 1) * sizeof(int))) return 1;
-    if (ensure_work<ActT>(e, std::max(T, TS), n_dec)) return 1;
+    if (ensure_work<ActT>(e, std::max(T, TS_cap), n_dec)) return 1;
 
     TTB_CUDA_OK(cudaEventRecord(e->t0, s));
     int* src32 = e->src32.as<int>();
@@ -454,12 +509,12 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
     ActT* crosskv = e->crosskv.as<ActT>();
-    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
+    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s, TS_cap * 2 * E)) return 1;
     // drafts from the source without its BOS column (speculative_decoding.py:64-73)
     { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s); }
 
     GreedyState st{};
-    st.B = B; st.N = N; st.D = D; st.max_len = max_len; st.gen_ld = gen_ld; st.pad = pad; st.bos = bos; st.eos = eos;
+    st.B = B; st.N = N; st.D = D; st.max_len = max_len; st.gen_ld = gen_ld; st.pad = pad; st.bos = bos; st.eos = eos; st.Ls = Ls;
     st.gen = e->gen.as<int>(); st.front = e->front.as<int>(); st.active = e->active.as<int>(); st.ctrl = e->ctrl.as<int>();
     st.drafts = e->drafts.as<int>(); st.pred = e->pred.as<int>(); st.out = e->out64.as<long long>();
     st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break; st.hist = e->hist.as<int>();
@@ -475,22 +530,17 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     RowCount rows((int)T, n_active, per_q);
 
     auto self_attn = [&](int l, ActT* qkv, ActT* att) {
-        launch_spec_self_attention<ActT>(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
+        spec_attn(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
                                          att, E, B, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
                                          N, D, H, HD, P, s);
     };
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
-        const ActT* kv = crosskv + (long long)l * TS * 2 * E;
-        launch_attention<ActT>(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
-                               src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+        const ActT* kv = crosskv + (long long)l * TS_cap * 2 * E;
+        attn(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
+             src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS);
     };
 
-    // Lagged polling: the host looks at the control words of iteration (it - LAG) while iterations up
-    // to `it` are already queued, so the GPU never waits for the host.
-    constexpr int LAG = 2, RING = 4;
-    int it = 0;
-    bool done = false;
-    while (!done && it < max_iters) {
+    auto enqueue_iteration = [&]() -> int {
         { Scope sc(e, KC_EMBED, s); launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s); }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
         if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
@@ -500,6 +550,47 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
             Scope sc(e, KC_CACHE_APPEND, s);
             launch_greedy_cache_append<ActT>(st, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, E, kc, vc, cache_l_stride,
                                              cache_q_stride, E, s);
+        }
+        return 0;
+    };
+
+    // One decoding iteration is a fixed kernel sequence on fixed buffers (all sizes that change while
+    // decoding live in device memory), so it is captured once into a CUDA graph and replayed.
+    static const bool no_graph = [] { const char* v = getenv("TTB_NO_GRAPH"); return v && v[0] == '1'; }();
+    const bool use_graph = !no_graph && !trace_dev && e->prof.mask == 0;
+    if (use_graph) {
+        const long long key[12] = {B, N, D, 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT), replace};
+        if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            const long long l0 = e->launches;
+            cudaGraph_t graph = nullptr;
+            TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            const int rc = enqueue_iteration();
+            cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if (rc || ce != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) set_last_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce));
+                return 1;
+            }
+            TTB_CUDA_OK(cudaGraphInstantiate(&e->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            e->graph_launches = e->launches - l0;
+            e->launches = l0;  // capturing did not launch anything
+            memcpy(e->graph_key, key, sizeof(key));
+        }
+    }
+
+    // Lagged polling: the host looks at the control words of iteration (it - LAG) while iterations up
+    // to `it` are already queued, so the GPU never waits for the host.
+    constexpr int LAG = 2, RING = 4;
+    int it = 0;
+    bool done = false;
+    while (!done && it < max_iters) {
+        if (use_graph) {
+            TTB_CUDA_OK(cudaGraphLaunch(e->graph_exec, s));
+            e->launches += e->graph_launches;
+        } else if (enqueue_iteration()) {
+            return 1;
         }
         TTB_CUDA_OK(cudaMemcpyAsync(e->h_ctrl + (it % RING) * CTRL_COUNT, st.ctrl, CTRL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         TTB_CUDA_OK(cudaEventRecord(e->poll_ev[it % RING], s));
@@ -580,6 +671,8 @@ int ttb_engine_create(const ttb_model_desc* desc, int device, ttb_engine** out) 
     for (auto& ev : e->poll_ev) TTB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     TTB_CUDA_OK(cudaEventCreate(&e->t0));
     TTB_CUDA_OK(cudaEventCreate(&e->t1));
+    TTB_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    TTB_CUDA_OK(cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming));
     *out = e;
     return 0;
 }
@@ -598,6 +691,9 @@ void ttb_engine_destroy(ttb_engine* e) {
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->prof.pool) cudaEventDestroy(ev);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->join_ev) cudaEventDestroy(e->join_ev);
     if (e->t0) cudaEventDestroy(e->t0);
     if (e->t1) cudaEventDestroy(e->t1);
     delete e;

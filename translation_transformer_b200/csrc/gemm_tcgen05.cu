@@ -95,40 +95,29 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 fp32 accumulator values of one row -> staging row in shared memory (already bias/ReLU'd)
 template <typename OutT>
-__device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32], int n_valid, bool vec_ok);
+__device__ __forceinline__ void stage_chunk(uint8_t* dst, const float (&v)[32]);
 template <>
-__device__ __forceinline__ void store_chunk<float>(float* dst, const float (&v)[32], int n_valid, bool vec_ok) {
-    if (vec_ok && n_valid == 32) {
+__device__ __forceinline__ void stage_chunk<float>(uint8_t* dst, const float (&v)[32]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < n_valid) dst[j] = v[j];
-    }
+    for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 template <>
-__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32], int n_valid, bool vec_ok) {
-    if (vec_ok && n_valid == 32) {
+__device__ __forceinline__ void stage_chunk<__nv_bfloat16>(uint8_t* dst, const float (&v)[32]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2);
-            u.w = *reinterpret_cast<uint32_t*>(&p3);
-            reinterpret_cast<uint4*>(dst)[j] = u;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < n_valid) dst[j] = __float2bfloat16_rn(v[j]);
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        u.z = *reinterpret_cast<uint32_t*>(&p2);
+        u.w = *reinterpret_cast<uint32_t*>(&p3);
+        reinterpret_cast<uint4*>(dst)[j] = u;
     }
 }
 
@@ -205,27 +194,59 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_commit(tmem_full_bar);     // accumulator complete
         }
     } else {  // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        // TMEM -> registers (one row per thread) -> bias/ReLU/convert -> per-warp staging tile in the
+        // (now idle) pipeline shared memory -> fully coalesced 16-byte global stores, whole rows per
+        // warp instruction.  All TMA loads and MMAs have completed once tmem_full fires, so the ring
+        // buffers are free to reuse.
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
+        constexpr int ESZ = (int)sizeof(OutT);
+        constexpr int PITCH = BN * ESZ + 16;          // +16 B: conflict-free 16-byte row-strided writes
+        uint8_t* stage = gen_base + q * 32 * PITCH;
         mbar_wait(tmem_full_bar, 0);
         tcgen05_fence_after();
-        const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (n0 % 8 == 0);
+        const int n_cols = min(BN, N - n0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= N) break;
+            if (c0 >= n_cols) break;
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (row < M) {
-                float v[32];
-                const int n_valid = min(32, N - (n0 + c0));
+            float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = __uint_as_float(r[j]);
-                    if (bias && j < n_valid) t += __ldg(bias + n0 + c0 + j);
-                    if (relu) t = fmaxf(t, 0.f);
-                    v[j] = t;
+            for (int j = 0; j < 32; ++j) {
+                float t = __uint_as_float(r[j]);
+                if (bias && c0 + j < n_cols) t += __ldg(bias + n0 + c0 + j);
+                if (relu) t = fmaxf(t, 0.f);
+                v[j] = t;
+            }
+            stage_chunk<OutT>(stage + lane * PITCH + c0 * ESZ, v);
+        }
+        __syncwarp();
+        const int row_base = m0 + q * 32;
+        constexpr int EPC = 16 / ESZ;                 // elements per 16-byte chunk
+        constexpr int CH = BN / EPC;                  // chunks per row: 16 (bf16) or 32 (fp32)
+        constexpr int RPI = 32 / CH;                  // rows per warp instruction: 2 or 1
+        const bool vec_ok = ((long long)ldc * ESZ) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+        if (vec_ok) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; rr += RPI) {
+                const int rl = rr + lane / CH, ch = lane % CH;
+                const int row = row_base + rl, col = ch * EPC;
+                if (row < M && col < n_cols) {
+                    const uint8_t* sp = stage + rl * PITCH + ch * 16;
+                    OutT* gp = C + (long long)row * ldc + n0 + col;
+                    if (col + EPC <= n_cols) {
+                        *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+                    } else {
+                        for (int j = 0; j < n_cols - col; ++j) gp[j] = reinterpret_cast<const OutT*>(sp)[j];
+                    }
                 }
-                store_chunk<OutT>(C + (long long)row * ldc + n0 + c0, v, n_valid, vec_ok);
+            }
+        } else {
+            for (int rl = 0; rl < 32; ++rl) {
+                const int row = row_base + rl;
+                if (row >= M) break;
+                const OutT* sp = reinterpret_cast<const OutT*>(stage + rl * PITCH);
+                for (int c = lane; c < n_cols; c += 32) C[(long long)row * ldc + n0 + c] = sp[c];
             }
         }
     }

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     for (int b = threadIdx.x; b < st.B; b += blockDim.x) { st.front[b] = 0; st.active[b] = b; }
     if (threadIdx.x < CTRL_COUNT) st.ctrl[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) st.ctrl[CTRL_N_ACTIVE] = st.B;
+    if (threadIdx.x == 0) { st.ctrl[CTRL_N_ACTIVE] = st.B; st.ctrl[CTRL_LS] = st.Ls; }
     plan_next_iteration(st, st.B, 1, s_tmp);
 }
 void launch_greedy_init(const GreedyState& st, cudaStream_t s) { greedy_init_kernel<<<1, 256, 0, s>>>(st); }
@@ -197,57 +197,72 @@ template void launch_greedy_embed<float>(const GreedyState&, const float*, const
 template void launch_greedy_embed<__nv_bfloat16>(const GreedyState&, const float*, const float*, int, float*, __nv_bfloat16*, cudaStream_t);
 
 // ---- accept / retire / plan ---------------------------------------------------------------------
-__global__ void __launch_bounds__(256) greedy_accept_kernel(GreedyState st) {
+// One CTA, one warp per live query: lanes score the drafts in parallel (accepted length = leading
+// matches between draft tokens and the predictions one position earlier), lane 0 applies the
+// tie-break rule, the warp appends the tokens and retires the query if it produced EOS.
+__global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
     __shared__ int s_tmp[2];
     __shared__ int s_acc, s_tok, s_err;
-    extern __shared__ int s_fin[];  // [B] finished flag per pre-retirement slot
+    extern __shared__ int s_dyn[];  // [B] finished flags, then [warps][64] accepted lengths
     if (st.ctrl[CTRL_DONE]) return;
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
     const int Wn = st.ctrl[CTRL_WIDTH];
     const int iter = st.ctrl[CTRL_ITERS];
     const int D = st.D, N = st.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    int* s_fin = s_dyn;
+    int* s_nacc = s_dyn + st.B + warp * 64;
     if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; if (st.hist) st.hist[iter] = n_active; }
     __syncthreads();
-    for (int g = threadIdx.x; g < n_active; g += blockDim.x) {
+    for (int g = warp; g < n_active; g += n_warps) {
         const int b = st.active[g];
         const int f = st.front[b];
-        int nacc[64];
-        int best_first = 0, best_val = -1;
-        for (int n = 0; n < N; ++n) {
+        int best_val = -1, best_first = 0x7fffffff;
+        for (int n = lane; n < N; n += 32) {
             const int* pr = st.pred + ((long long)g * N + n) * (D + 1);
             const int* dr = st.drafts + ((long long)b * N + n) * D;
             int a = 0;
             while (a < D && dr[a] == pr[a]) ++a;
-            if (n < 64) nacc[n] = a;
+            if (n < 64) s_nacc[n] = a;
             if (a > best_val) { best_val = a; best_first = n; }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // max accepted length, lowest draft index among equals
+            const int ov = __shfl_xor_sync(0xffffffffu, best_val, o), oi = __shfl_xor_sync(0xffffffffu, best_first, o);
+            if (ov > best_val || (ov == best_val && oi < best_first)) { best_val = ov; best_first = oi; }
+        }
+        __syncwarp();
         int pick = best_first;
-        if (st.tie_break == 0 && N < 64) pick = topk1_torch_cpu(nacc, N);
+        if (st.tie_break == 0 && N < 64) {
+            if (lane == 0) pick = topk1_torch_cpu(s_nacc, N);
+            pick = __shfl_sync(0xffffffffu, pick, 0);
+        }
         const int a = best_val;
         const int* pr = st.pred + ((long long)g * N + pick) * (D + 1);
         int* row = st.gen + (long long)b * st.gen_ld;
-        bool fin = false;
-        for (int j = 0; j <= D; ++j) {
+        bool fin_l = false;
+        for (int j = lane; j <= D; j += 32) {
             const int t = (j <= a) ? pr[j] : st.pad;
             row[f + 1 + j] = t;
-            fin |= (j <= a) && (t == st.eos);
+            fin_l |= (j <= a) && (t == st.eos);
         }
-        st.front[b] = f + a + 1;
-        st.sel[g * 4 + 0] = b; st.sel[g * 4 + 1] = f; st.sel[g * 4 + 2] = pick; st.sel[g * 4 + 3] = a;
-        if (st.trace) {
-            int* tr = st.trace + ((long long)iter * st.B + g) * 4;
-            tr[0] = b; tr[1] = a; tr[2] = pick; tr[3] = Wn;
-        }
-        atomicAdd(&s_acc, a);
-        atomicAdd(&s_tok, a + 1);
-        s_fin[g] = fin ? 1 : 0;
-        if (fin) {
-            if (Wn > st.max_len) {
-                s_err = 2;  // the reference cannot store a finished row wider than max_len (:158)
-            } else {
-                long long* o = st.out + (long long)b * st.max_len;
-                for (int c = 0; c < Wn; ++c) o[c] = (c <= f + a + 1) ? row[c] : st.pad;
+        const bool fin = __any_sync(0xffffffffu, fin_l);
+        __syncwarp();
+        if (lane == 0) {
+            st.front[b] = f + a + 1;
+            st.sel[g * 4 + 0] = b; st.sel[g * 4 + 1] = f; st.sel[g * 4 + 2] = pick; st.sel[g * 4 + 3] = a;
+            if (st.trace) {
+                int* tr = st.trace + ((long long)iter * st.B + g) * 4;
+                tr[0] = b; tr[1] = a; tr[2] = pick; tr[3] = Wn;
             }
+            atomicAdd(&s_acc, a);
+            atomicAdd(&s_tok, a + 1);
+            s_fin[g] = fin ? 1 : 0;
+            if (fin && Wn > st.max_len) s_err = 2;  // the reference cannot store a finished row wider than max_len (:158)
+        }
+        if (fin && Wn <= st.max_len) {
+            long long* o = st.out + (long long)b * st.max_len;
+            for (int c = lane; c < Wn; c += 32) o[c] = (c <= f + a + 1) ? row[c] : st.pad;
         }
     }
     __syncthreads();
@@ -269,7 +284,8 @@ __global__ void __launch_bounds__(256) greedy_accept_kernel(GreedyState st) {
     plan_next_iteration(st, n_left, Wn, s_tmp);
 }
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
-    greedy_accept_kernel<<<1, 256, (size_t)st.B * sizeof(int), s>>>(st);
+    const int warps = st.B < 32 ? (st.B < 4 ? 4 : st.B) : 32;
+    greedy_accept_kernel<<<1, warps * 32, ((size_t)st.B + warps * 64) * sizeof(int), s>>>(st);
 }
 
 // ---- KV-cache append ------------------------------------------------------------------------------

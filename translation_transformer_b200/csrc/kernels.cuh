@@ -52,7 +52,7 @@ void launch_attention(const ActT* q, int q_ld, const ActT* k, const ActT* v, int
                       ActT* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                       int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                       const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                      int heads, int head_dim, cudaStream_t s);
+                      int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr);
 
 // Speculative self-attention: group g = live query slot; b = active[g]; f = front[b].
 // Queries: rows (g*N + n)*(D+1) + i of `qkv` (q | k | v packed, row stride qkv_ld).
@@ -65,6 +65,18 @@ void launch_spec_self_attention(const ActT* qkv, int qkv_ld, const ActT* kcache,
                                 const int* gen, int gen_ld, int pad_id, int N, int D,
                                 int heads, int head_dim, int max_cache_len, cudaStream_t s);
 
+// ---- attention_mma.cu : tensor-core (mma.sync bf16) versions of the two entry points above ----------
+void launch_attention_mma(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* k, const __nv_bfloat16* v, int kv_ld,
+                          __nv_bfloat16* out, int out_ld, int n_groups_max, const int* n_groups_dev,
+                          int Lq, int Lk, long long kv_group_stride, const int* kvmap,
+                          const int* key_tok, int key_tok_stride, int pad_id, bool causal,
+                          int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr);
+void launch_spec_self_attention_mma(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
+                                    long long cache_query_stride, int cache_ld, __nv_bfloat16* out, int out_ld,
+                                    int B_max, const int* n_active_dev, const int* active, const int* front,
+                                    const int* gen, int gen_ld, int pad_id, int N, int D,
+                                    int heads, int head_dim, cudaStream_t s);
+
 // ---- drafting.cu ------------------------------------------------------------------------------
 // Mirrors utils/drafting.py::make_drafts on device; src is (B, L) int32 with row stride src_ld (the
 // caller skips the BOS column by passing src + 1, L - 1).  out is (B, N, Deff) int32.
@@ -73,7 +85,7 @@ void launch_make_drafts(const int* src, int src_ld, int B, int L, int Deff, int 
 
 // ---- greedy.cu -------------------------------------------------------------------------------
 struct GreedyState {
-    int B, N, D, max_len, gen_ld, pad, bos, eos;
+    int B, N, D, max_len, gen_ld, pad, bos, eos, Ls;
     int* gen;          // [B][gen_ld] generated tokens (row b of the reference's token matrix)
     int* front;        // [B] index of the last generated token
     int* active;       // [B] compact list of live query ids (order preserved, like boolean masking)

@@ -200,6 +200,7 @@ def main():
     import torch.distributed as dist
     from translation_transformer_b200 import _lib
     from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    from translation_transformer_b200.distributed import gather_predictions
     from translation_transformer_b200.model import B200Transformer
 
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path"
@@ -215,7 +216,6 @@ def main():
     host = [batch_for(args, rank, i).pin_memory() for i in range(n_total)]
     devb = [h.to(dev) for h in host]
     out_host = torch.empty(args.batch_size, 1, args.max_len, dtype=torch.int64).pin_memory()
-    gathered = torch.empty(world * args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     errors = []
 
@@ -228,7 +228,7 @@ def main():
             errors.append(str(ex)[:80])
             out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            gather_predictions(out, counts=[args.batch_size] * world)   # NCCL all-gather of the predictions
         if e2e:
             out_host.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -1,0 +1,116 @@
+"""CPU tests of the host-side logic: C-ABI surface, tokenizer, CSV writer, query sharding (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from translation_transformer_b200 import _lib
+    from translation_transformer_b200.build import build
+    build()
+    header = (REPO / "include" / "ttb200.h").read_text()
+    declared = set(re.findall(r"\b(ttb_[a-z0-9_]+)\s*\(", header))
+    assert {"ttb_greedy_speculative_generate", "ttb_encode_src", "ttb_decode_tgt", "ttb_make_drafts"} <= declared
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ttb200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.load().ttb_abi_version() == _lib.ABI_VERSION
+
+
+def test_product_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from translation_transformer_b200.model import B200Transformer
+    from translation_transformer_b200.weights import ModelConfig, random_init_state_dict
+    cfg = ModelConfig(src_vocab_size=30, tgt_vocab_size=30, embedding_dim=64, feedforward_dim=128,
+                      num_encoder_layers=1, num_decoder_layers=1, num_heads=4)
+    with pytest.raises(RuntimeError):
+        B200Transformer(cfg, random_init_state_dict(cfg, 0))
+
+
+def test_no_oracle_import_in_product():
+    for p in (REPO / "translation_transformer_b200").rglob("*.py"):
+        assert "oracle" not in re.sub(r'""".*?"""', "", p.read_text(), flags=re.S), f"{p} references the oracle"
+
+
+def test_tokenizer_roundtrip_and_vocab_file(tmp_path):
+    from translation_transformer_b200.data_handling import ChemSMILESTokenizer
+    lines = [l.strip() for l in open(REPO / "tests/golden/product_prediction_src_test.txt") if l.strip()]
+    tk = ChemSMILESTokenizer()
+    tk.train_tokenizer(lines)
+    ids = tk.encode(lines[0])
+    assert ids[0] == tk.bos_token_idx and ids[-1] == tk.eos_token_idx
+    assert tk.decode(ids) == lines[0]
+    assert tk.decode(ids + [0, 0, 5]) == lines[0]          # stops at EOS, skips PAD
+    tk.save_vocab(tmp_path / "vocab.json")
+    tk2 = ChemSMILESTokenizer()
+    tk2.load_vocab(tmp_path / "vocab.json")
+    assert tk2.encode(lines[3]) == tk.encode(lines[3])
+    assert tk.encode("C[Zz]C")[2] == tk.unk_token_idx
+    with pytest.raises(FileNotFoundError):
+        tk2.load_vocab(tmp_path / "missing.json")
+
+
+def test_prediction_writer_csv_format(tmp_path):
+    from translation_transformer_b200.callbacks import PredictionWriter
+    from translation_transformer_b200.data_handling import ChemSMILESTokenizer
+    tk = ChemSMILESTokenizer()
+    tk.train_tokenizer(["CCO", "c1ccccc1"])
+    w = PredictionWriter(tmp_path / "out" / "pred.csv")
+    batch = {"src_tokens": torch.tensor([tk.encode("CCO")]), "tgt_tokens": torch.tensor([tk.encode("CC")])}
+    a, b = tk.encode("CO"), tk.encode("c1ccccc1")
+    width = max(len(a), len(b)) + 1
+    pred = torch.tensor([[a + [0] * (width - len(a)), b + [0] * (width - len(b))]])
+    w.write(tk, pred, batch)
+    w.write(tk, pred, batch)
+    rows = (tmp_path / "out" / "pred.csv").read_text().strip().split("\n")
+    assert rows[0] == "source,target,prediction_1,prediction_2"
+    assert rows[1].split(",") == ["CCO", "CC", "CO", "c1ccccc1"] and len(rows) == 3
+
+
+def test_shard_bounds_cover_everything():
+    from translation_transformer_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 40000, 40001):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from translation_transformer_b200.distributed import shard_bounds, gather_predictions
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+n = 7                                    # ragged: 4 queries on rank 0, 3 on rank 1
+lo, hi = shard_bounds(n, rank, 2)
+all_preds = torch.arange(n * 2 * 5).reshape(n, 2, 5)      # (queries, n_best, max_len)
+out = gather_predictions(all_preds[lo:hi].clone())
+assert torch.equal(out, all_preds), (rank, out)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_query_sharding_and_prediction_gather_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=port, REPO=str(REPO))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -1,0 +1,92 @@
+"""Inference-side mirror of `VanillaEncoderDecoderTransformerLightning`
+(src/model/lightning_model.py:22-277): same constructor arguments for the model / generation
+options, `predict_step(batch, batch_idx)`, `on_predict_start` / `on_predict_end` timing report.
+Training hooks are out of scope; the class derives from LightningModule when
+Lightning is installed so that `main.py predict` can instantiate it, and from `object` otherwise."""
+from __future__ import annotations
+
+import datetime
+import json
+from pathlib import Path
+from timeit import default_timer as timer
+from typing import Any
+
+from .decoding.speculative_decoding import TranslationInferenceGreedySpeculative
+from .model import B200Transformer
+from .weights import ModelConfig, random_init_state_dict
+
+try:
+    from pytorch_lightning import LightningModule as _Base
+except Exception:  # pragma: no cover
+    _Base = object
+
+
+class VanillaEncoderDecoderTransformerLightning(_Base):
+    def __init__(self, src_tokenizer=None, tgt_tokenizer=None, embedding_dim: int = 128, feedforward_dim: int = 256,
+                 num_encoder_layers: int = 3, num_decoder_layers: int = 3, num_heads: int = 4, dropout_rate: float = 0.0,
+                 activation: str = "relu", share_embeddings: bool = False, generation: str = "greedy_speculative",
+                 beam_size: int = 0, max_len: int = 0, n_drafts: int = 0, draft_len: int = 0, smart_drafts_mode: bool = True,
+                 report_prediction_time: bool = True, report_prediction_file: str | None = None,
+                 state_dict: dict | None = None, precision: str = "bf16", device: int = 0, seed: int = 0, **_unused):
+        if _Base is not object:
+            super().__init__()
+        assert src_tokenizer is not None, "source tokenizer not provided"
+        assert tgt_tokenizer is not None, "target tokenizer not provided"
+        assert activation == "relu", "only the relu activation of the shipped configs is implemented"
+        self.src_tokenizer, self.tgt_tokenizer = src_tokenizer, tgt_tokenizer
+        self.generation, self.beam_size, self.max_len = generation, beam_size, max_len
+        self.n_drafts, self.draft_len, self.smart_drafts_mode = n_drafts, draft_len, smart_drafts_mode
+        self.report_prediction_time, self.report_prediction_file = report_prediction_time, report_prediction_file
+        self.src_pad_token_i, self.tgt_pad_token_i = src_tokenizer.pad_token_idx, tgt_tokenizer.pad_token_idx
+        self.tgt_bos_token_i, self.tgt_eos_token_i = tgt_tokenizer.bos_token_idx, tgt_tokenizer.eos_token_idx
+        cfg = ModelConfig(src_vocab_size=src_tokenizer.n_tokens, tgt_vocab_size=tgt_tokenizer.n_tokens,
+                          embedding_dim=embedding_dim, feedforward_dim=feedforward_dim,
+                          num_encoder_layers=num_encoder_layers, num_decoder_layers=num_decoder_layers,
+                          num_heads=num_heads, share_embeddings=share_embeddings,
+                          src_pad_token_idx=self.src_pad_token_i, tgt_pad_token_idx=self.tgt_pad_token_i)
+        self.model = B200Transformer(cfg, state_dict if state_dict is not None else random_init_state_dict(cfg, seed),
+                                     precision=precision, device=device)
+        self.generator = self._create_generator()
+        self.prediction_start_time = None
+        self.batch_size = None
+
+    def load_checkpoint_state_dict(self, state_dict: dict) -> None:
+        """Accepts the `state_dict` of a reference Lightning checkpoint (keys prefixed `model.`)."""
+        self.model.load_state_dict({k: v for k, v in state_dict.items() if "positional_encoding" not in k})
+
+    def _create_generator(self):
+        if self.generation == "greedy_speculative":
+            assert self.draft_len > 0, "Number of speculative tokens must be a positive integer."
+            return TranslationInferenceGreedySpeculative(
+                self.model, max_len=self.max_len, draft_len=self.draft_len, n_drafts=self.n_drafts,
+                pad_token=self.tgt_pad_token_i, bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
+                replace_token=self.tgt_tokenizer.encoder_dict["c"])
+        options = ", ".join(["beam_search", "greedy", "greedy_speculative", "beam_search_speculative"])
+        if self.generation in ("beam_search", "greedy", "beam_search_speculative"):
+            raise NotImplementedError(f"generation={self.generation} is not on the B200 hot path yet (DESIGN.md §0 row f)")
+        raise ValueError(f"Unknown generation option {self.generation}. Options are {options}.")
+
+    def predict_step(self, batch: Any, batch_idx: int, dataloader_idx: int = 0) -> Any:
+        self.batch_size = batch["src_tokens"].shape[0] if self.batch_size is None else self.batch_size
+        return self.generator.generate(batch["src_tokens"])
+
+    def on_predict_start(self) -> None:
+        if self.report_prediction_time:
+            self.prediction_start_time = timer()
+
+    def on_predict_end(self) -> None:
+        if not self.report_prediction_time:
+            return
+        elapsed = datetime.timedelta(seconds=timer() - self.prediction_start_time)
+        calls = max(self.generator.model_calls_num, 1)
+        report = {"algorithm": self.generation, "batch_size": self.batch_size, "max_len": self.max_len,
+                  "total_seconds": round(elapsed.total_seconds(), 4), "model_calls": self.generator.model_calls_num,
+                  "seconds_per_model_call": round(elapsed.total_seconds() / calls, 4)}
+        if self.generation in ("greedy_speculative", "beam_search_speculative"):
+            report["n_drafts"], report["draft_len"] = self.n_drafts, self.draft_len
+        report = json.dumps(report)
+        print(report)
+        if self.report_prediction_file is not None:
+            Path(self.report_prediction_file).parent.mkdir(exist_ok=True)
+            with open(self.report_prediction_file, "a") as f:
+                print(report, file=f)

@@ -119,3 +119,36 @@ def test_greedy_speculative_oracle_matches_reference(case):
     assert n <= len(ref_pick)
     assert np.array_equal(pick, ref_pick[:n])
     assert np.array_equal(nacc, ref_nacc[np.arange(n), ref_pick[:n]])
+
+
+# ---------------------------------------------------------------------------------------------
+def _beam_cases():
+    return load_json("beam_speculative.json")
+
+
+@pytest.mark.parametrize("case", _beam_cases(), ids=lambda c: c["id"])
+def test_beam_speculative_oracle_matches_reference(case):
+    from oracle.beam_speculative import BeamSearchSpeculativeOracle
+    z = load_npz("beam_speculative.npz")
+    cfg, sd = case_weights(case)
+    model = OracleTransformer(sd, cfg.num_heads)
+    seen = []
+    inner = model.decode_tgt
+
+    def spy(tgt, memory, mask):
+        seen.append(sha_tokens(tgt.numpy()))
+        return inner(tgt, memory, mask)
+
+    model.decode_tgt = spy
+    gen = BeamSearchSpeculativeOracle(model, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                      case["vocab"], 0, 1, 2, case["C_token"], keep_trace=True)
+    out = gen.generate(torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)))
+    assert case["error"] is None
+    assert np.array_equal(out.numpy(), z[case["id"] + "_out"].astype(np.int64))        # all n_best hypotheses, in order
+    assert seen == case["decoder_input_sha1"]                                         # every decoder input
+    assert (gen.model_calls_num, gen.accepted_tokens_num, gen.produced_non_pad_tokens) == \
+        (case["model_calls"], case["accepted_tokens"], case["produced_non_pad_tokens"])
+    nacc = np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace])
+    pick = np.concatenate([t["pick"] for t in gen.trace])
+    assert np.array_equal(nacc, z[case["id"] + "_nacc"].astype(np.int64))               # accepted lengths of every draft
+    assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))               # chosen draft indices

@@ -29,6 +29,7 @@ extern "C" {
 
 #define TTB_ERR_REF_INDEX 10 /* reference: scatter index out of bounds (speculative_decoding.py:111) */
 #define TTB_ERR_REF_SHAPE 11 /* reference: finished row wider than max_len (speculative_decoding.py:158) */
+#define TTB_ERR_REF_ASSERT 12 /* reference: assert in topk_in_each_group (speculative_decoding.py:195) */
 
 typedef struct ttb_engine ttb_engine;
 
@@ -93,6 +94,16 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                     int32_t bos_token, int32_t eos_token, int32_t replace_token,
                                     int32_t tie_break, int64_t* out_dev, int32_t* trace_dev,
                                     ttb_generate_stats* stats, void* stream);
+
+/* ---- speculative_decoding.py:422 TranslationInferenceBeamSearchSpeculative.generate(src),
+ * smart_drafts_mode=False ("try all the drafts", :428-598).  out_dev must hold
+ * B * n_best * (max_len + clamp(draft_len,5,200) + 4) int64; the hypotheses are written densely as
+ * (B, n_best, *out_width).  Optional traces: trace_nacc_dev (max_len, B*n_best, n_drafts) accepted
+ * length of every draft, trace_pick_dev (max_len, B*n_best) chosen draft, per iteration. */
+int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,
+                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t pad_token, int32_t bos_token,
+                                  int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev, int32_t* out_width,
+                                  int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats, void* stream);
 
 /* ---- instrumentation (bench.py): per-kernel-class CUDA-event timing on the launching stream.
  * class_mask bit i enables class i (names via ttb_kernel_class_name); totals accumulate over

@@ -277,3 +277,54 @@ def test_greedy_speculative_bf16_tokens_are_reference_argmax(dev):
                 assert produced[b] == int((row == 2).nonzero()[0])
         eng.close()
     assert total > 200
+
+
+# ---------------------------------------------------------------------------------------------
+# speculative beam search (configs[2], configs[3] of BASELINE.json at test size)
+def _beam_cases():
+    return load_json("beam_speculative.json")
+
+
+@pytest.mark.parametrize("case", _beam_cases(), ids=lambda c: c["id"])
+def test_beam_speculative_fp32_matches_reference_golden(dev, case):
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    z = load_npz("beam_speculative.npz")
+    cfg, sd = case_weights(case)
+    eng = _engine(cfg, sd, "fp32")
+    gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                                    case["vocab"], False, 0, 1, 2, case["C_token"], keep_trace=True)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)).to(dev)
+    out = gen.generate(src).cpu().numpy()
+    ref = z[case["id"] + "_out"].astype(np.int64)
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)                                                    # all hypotheses, best first, bit-exact
+    assert (gen.model_calls_num, gen.accepted_tokens_num, gen.produced_non_pad_tokens) == \
+        (case["model_calls"], case["accepted_tokens"], case["produced_non_pad_tokens"])
+    nacc = np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace])
+    pick = np.concatenate([t["pick"] for t in gen.trace])
+    assert np.array_equal(nacc, z[case["id"] + "_nacc"].astype(np.int64))               # accepted lengths of every draft
+    assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))               # chosen draft indices
+    eng.close()
+
+
+def test_beam_speculative_bf16_runs_and_is_consistent(dev):
+    """bf16 hypotheses may differ from fp32 at near-ties; check structure and that the best hypothesis
+    of most queries matches the fp32 engine."""
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    z = load_npz("beam_speculative.npz")
+    case = [c for c in _beam_cases() if c["id"] == "beam1"][0]
+    cfg, sd = case_weights(case)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)).to(dev)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        eng = _engine(cfg, sd, prec)
+        gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                                        case["vocab"], False, 0, 1, 2, case["C_token"])
+        outs[prec] = gen.generate(src).cpu()
+        eng.close()
+    a, b = outs["fp32"], outs["bf16"]
+    assert a.shape[:2] == b.shape[:2] == (case["B"], case["n_best"])
+    assert (b[:, :, 0] == 1).all()
+    w = min(a.shape[2], b.shape[2])
+    same_top1 = sum(bool(torch.equal(a[i, 0, :w], b[i, 0, :w])) for i in range(case["B"]))
+    assert same_top1 >= case["B"] // 2

@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libttb200.so"
 
 ABI_VERSION = 1
 PRECISION = {"fp32": 0, "bf16": 1}
-ERR_REF_INDEX, ERR_REF_SHAPE = 10, 11
+ERR_REF_INDEX, ERR_REF_SHAPE, ERR_REF_ASSERT = 10, 11, 12
 
 
 class ModelDesc(C.Structure):
@@ -45,6 +45,8 @@ SIGNATURES = {
     "ttb_greedy_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
+    "ttb_beam_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 11 +
+                                      [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_kernel_class_count": (C.c_int, []),
     "ttb_kernel_class_name": (C.c_char_p, [C.c_int32]),
     "ttb_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_uint32]),
@@ -94,6 +96,8 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(msg)          # the reference raises RuntimeError (scatter out of bounds)
     if rc == ERR_REF_SHAPE:
         raise RuntimeError(msg)          # the reference raises RuntimeError (shape mismatch)
+    if rc == ERR_REF_ASSERT:
+        raise AssertionError(msg)        # the reference asserts (topk_in_each_group)
     if rc == 2 and ("must be" in msg or "must not" in msg):
         raise AssertionError(msg)        # argument checks the reference states as `assert`
     raise RuntimeError(f"{what} failed (code {rc}): {msg}")

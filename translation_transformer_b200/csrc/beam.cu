@@ -1,0 +1,375 @@
+// Device side of the speculative beam search ("try all the drafts" mode).
+// Reference: /root/reference/src/decoding/speculative_decoding.py:428-598 (loop), :294-400 (sample),
+// :847-869 (accepted lengths), :871-904 (nucleus truncation), :177-238 (top-k per query).
+//
+// Per iteration the engine runs
+//   beam_prepare  -> per-candidate bookkeeping (first free slot, finished flag, live-row prefix)
+//   beam_fill_rows-> (candidate, draft) decoder input rows, live candidates only
+//   decoder stack on the live rows (full-prefix, causal), gather of the dl+1 scored positions,
+//   classifier GEMM
+//   beam_stats    -> per (row, position): softmax max/sum, the n_best largest logits (sorted), size of
+//                    the nucleus-truncated support
+//   beam_choose   -> accepted length of every draft, best draft per candidate (torch-CPU topk(1) order)
+//   beam_expand   -> per query: scores of all leaves of the continuation trees of its candidates, the
+//                    n_best best become the next candidates
+//   beam_control  -> all-finished flag, number of trailing empty columns, acceptance statistics
+#include "kernels.cuh"
+#include "topk_emul.cuh"
+
+namespace ttb {
+
+// ---- prepare ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int W, int dl) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int* row = st.cand_cur + (long long)c * st.ldw;
+        int slot0 = -1, fin = 0, hole = 0;
+        for (int j = 0; j < W; ++j) {
+            const int t = row[j];
+            if (t == st.eos) fin = 1;
+            if (t == st.pad) { if (slot0 < 0) slot0 = j; }
+            else if (slot0 >= 0) hole = 1;           // a real token after a PAD: draft slots not contiguous
+        }
+        st.c_slot0[c] = slot0;
+        st.c_fin[c] = fin;
+        if (hole || slot0 < 1 || slot0 + dl + 1 > W) atomicExch(&st.ctrl[BC_ERROR], 3);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < C; ++c) {
+            st.c_rowbase[c] = run;
+            if (!st.c_fin[c]) run += st.N;
+        }
+        st.ctrl[BC_NLIVE_ROWS] = run;
+    }
+}
+void launch_beam_prepare(const BeamState& st, int C, int W, int dl, cudaStream_t s) {
+    beam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, W, dl);
+}
+
+__global__ void beam_fill_rows_kernel(BeamState st, int C, int beam, int W, int dl) {
+    const int c = blockIdx.x / st.N, n = blockIdx.x % st.N;
+    if (c >= C || st.c_fin[c]) return;
+    const int q = c / beam;
+    const int r = st.c_rowbase[c] + n;
+    const int slot0 = st.c_slot0[c];
+    const int* src = st.cand_cur + (long long)c * st.ldw;
+    const int* dr = st.drafts + ((long long)q * st.N + n) * st.dl0;
+    int* dst = st.rows_tok + (long long)r * W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        int t = src[j];
+        if (j >= slot0 && j < slot0 + dl) t = dr[j - slot0];
+        dst[j] = t;
+    }
+    if (threadIdx.x == 0) { st.row_cand[r] = c; st.row_query[r] = q; st.row_slot0[r] = slot0; }
+}
+void launch_beam_fill_rows(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s) {
+    beam_fill_rows_kernel<<<C * st.N, 128, 0, s>>>(st, C, beam, W, dl);
+}
+
+// rows of the residual stream that are scored: positions slot0-1 .. slot0+dl-1 of every live row
+template <typename ActT>
+__global__ void beam_gather_kernel(BeamState st, const float* __restrict__ x, const ActT* __restrict__ xh, int W, int dl, int E,
+                                   float* __restrict__ xg, ActT* __restrict__ xgh) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= st.ctrl[BC_NLIVE_ROWS] * (dl + 1)) return;
+    const int r = t / (dl + 1), i = t % (dl + 1);
+    const long long src = ((long long)r * W + st.row_slot0[r] - 1 + i) * E, dst = (long long)t * E;
+    for (int c = lane; c < E; c += 32) {
+        if (xg) xg[dst + c] = x[src + c];
+        if (xgh) xgh[dst + c] = xh[src + c];
+    }
+}
+template <typename ActT>
+void launch_beam_gather(const BeamState& st, const float* x, const ActT* xh, int max_rows, int W, int dl, int E,
+                        float* xg, ActT* xgh, cudaStream_t s) {
+    const int T = max_rows * (dl + 1);
+    if (T <= 0) return;
+    beam_gather_kernel<ActT><<<(T + 7) / 8, 256, 0, s>>>(st, x, xh, W, dl, E, xg, xgh);
+}
+template void launch_beam_gather<float>(const BeamState&, const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+template void launch_beam_gather<__nv_bfloat16>(const BeamState&, const float*, const __nv_bfloat16*, int, int, int, int, float*, __nv_bfloat16*, cudaStream_t);
+
+// ---- per (row, position) statistics -------------------------------------------------------------------
+// One warp per distribution: softmax max / sum, the K largest logits in descending order (ties: lower
+// token id first) and the size of the truncated support (exclusive cumulative probability < 0.9975,
+// the best token always kept; speculative_decoding.py:886-899).
+template <int VPL>
+__global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const float* __restrict__ logits, int dl) {
+    const int rp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (rp >= st.ctrl[BC_NLIVE_ROWS] * (dl + 1)) return;
+    const int V = st.V, K = st.K;
+    const float* p = logits + (long long)rp * V;
+    float v[VPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int c = lane + 32 * k;
+        v[k] = c < V ? p[c] : -INFINITY;
+        mx = fmaxf(mx, v[k]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) sum += (lane + 32 * k < V) ? expf(v[k] - mx) : 0.f;
+    sum = warp_sum(sum);
+    float* topv = st.topv + (long long)rp * K;
+    int* topi = st.topi + (long long)rp * K;
+    for (int j = 0; j < K; ++j) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int c = lane + 32 * k;
+            if (c < V && (v[k] > bv || (v[k] == bv && c < bi))) { bv = v[k]; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+            if (lane + 32 * k == bi) v[k] = -INFINITY;                          // taken
+        if (lane == 0) { topv[j] = bv; topi[j] = bi == 0x7fffffff ? -1 : bi; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        st.lmax[rp] = mx;
+        st.lsum[rp] = sum;
+        int keep = 1;
+        float cum = 0.f;
+        for (int j = 1; j < K && topi[j] >= 0; ++j) {
+            cum += expf(topv[j - 1] - mx) / sum;
+            if (cum < 0.9975f) keep = j + 1; else break;
+        }
+        st.nkeep[rp] = keep;
+    }
+}
+void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s) {
+    const int T = max_rows * (dl + 1);
+    if (T <= 0) return;
+    if (st.V <= 512) beam_stats_kernel<16><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
+    else beam_stats_kernel<32><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
+}
+
+// ---- accepted lengths + best draft per candidate ------------------------------------------------------------
+__global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, int beam, int dl, int iter) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    __shared__ int s_nacc[64];
+    if (c >= C) return;
+    const int q = c / beam, N = st.N, K = st.K;
+    const bool fin = st.c_fin[c] != 0;
+    for (int n = lane; n < N; n += 32) {
+        int a = 0;
+        if (!fin) {
+            const int r = st.c_rowbase[c] + n;
+            const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+            while (a < dl) {
+                const long long rp = (long long)r * (dl + 1) + a;
+                const int keep = st.nkeep[rp];
+                const int* ti = st.topi + rp * K;
+                const int tok = dr[a];
+                bool in = false;
+                for (int j = 0; j < keep; ++j) in |= (ti[j] == tok);
+                if (!in) break;
+                ++a;
+            }
+        }
+        st.c_nacc[(long long)c * N + n] = a;
+        if (n < 64) s_nacc[n] = a;
+        if (st.trace_nacc) st.trace_nacc[((long long)iter * st.B * K + c) * N + n] = a;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int pick = 0;
+        if (st.tie_break == 0 && N < 64) {
+            pick = topk1_torch_cpu(s_nacc, N);
+        } else {
+            for (int n = 1; n < N; ++n) if (st.c_nacc[(long long)c * N + n] > st.c_nacc[(long long)c * N + pick]) pick = n;
+        }
+        st.c_pick[c] = pick;
+        if (st.trace_pick) st.trace_pick[(long long)iter * st.B * K + c] = pick;
+    }
+}
+void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s) {
+    beam_choose_kernel<<<C, 32, 0, s>>>(st, C, beam, dl, iter);
+}
+
+// ---- leaves of the continuation trees, n_best best per query ------------------------------------------------------
+// log softmax exactly as the reference evaluates it: log(exp(x - max) / sum)   (:378)
+__device__ __forceinline__ float ref_logprob(float logit, float mx, float sum) { return logf(expf(logit - mx) / sum); }
+
+__global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam, int W, int dl, const float* __restrict__ logits) {
+    extern __shared__ float s_score[];                 // [beam][(dl+1)][K] leaf scores, -inf when absent
+    __shared__ float s_red_v[256];
+    __shared__ int s_red_i[256];
+    __shared__ int s_sel[64];
+    __shared__ int s_valid;
+    const int q = blockIdx.x, K = st.K, V = st.V, N = st.N;
+    const int per_c = (dl + 1) * K, total = beam * per_c;
+    float* s_pre = s_score + total;                    // [beam][dl+2] running log-prob of the accepted path
+    if (threadIdx.x == 0) s_valid = 0;
+    // accepted-path prefix sums (sequential fp32 adds, same association as the reference's cumsum)
+    for (int cb = threadIdx.x; cb < beam; cb += blockDim.x) {
+        const int c = q * beam + cb;
+        float run = 0.f;
+        s_pre[cb * (dl + 2)] = 0.f;
+        if (!st.c_fin[c]) {
+            const int n = st.c_pick[c], a = st.c_nacc[(long long)c * N + n], r = st.c_rowbase[c] + n;
+            const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+            for (int i = 0; i < a; ++i) {
+                const long long rp = (long long)r * (dl + 1) + i;
+                run += ref_logprob(logits[rp * V + dr[i]], st.lmax[rp], st.lsum[rp]);
+                s_pre[cb * (dl + 2) + i + 1] = run;
+            }
+        }
+    }
+    __syncthreads();
+    int my_valid = 0;
+    for (int L = threadIdx.x; L < total; L += blockDim.x) {
+        const int cb = L / per_c, p = (L % per_c) / K, j = L % K;
+        const int c = q * beam + cb;
+        float score = -INFINITY;
+        if (st.c_fin[c]) {
+            // finished candidate: the artificial distribution leaves exactly one leaf, PAD at position 0,
+            // with log-probability log(1) = 0
+            if (p == 0 && j == 0) score = st.logp_cur[c] + 0.f;
+        } else {
+            const int n = st.c_pick[c], a = st.c_nacc[(long long)c * N + n], r = st.c_rowbase[c] + n;
+            if (p <= a) {
+                const long long rp = (long long)r * (dl + 1) + p;
+                const int tok = st.topi[rp * K + j];
+                const float lg = st.topv[rp * K + j];
+                const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+                // excluded: the draft token that continues the accepted path (p < a), BOS in the slot of the first
+                // rejected draft token (p == a < dl); entries whose logit is exactly 0.0 vanish in the reference
+                const int excl = (p < dl) ? (p < a ? dr[p] : st.bos) : -1;
+                if (tok >= 0 && tok != excl && lg != 0.0f)
+                    score = st.logp_cur[c] + (s_pre[cb * (dl + 2) + p] + ref_logprob(lg, st.lmax[rp], st.lsum[rp]));
+            }
+        }
+        s_score[L] = score;
+        my_valid += score != -INFINITY ? 1 : 0;
+    }
+    if (my_valid) atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    if (s_valid < K) {
+        if (threadIdx.x == 0) atomicExch(&st.ctrl[BC_ERROR], 4);   // reference: assert min(group length) >= k (:195)
+        return;
+    }
+    for (int k = 0; k < K; ++k) {                      // K rounds of block-wide argmax (ties: lower leaf index)
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int L = threadIdx.x; L < total; L += blockDim.x) {
+            const float sc = s_score[L];
+            if (sc > bv || (sc == bv && sc != -INFINITY && L < bi)) { bv = sc; bi = L; }
+        }
+        s_red_v[threadIdx.x] = bv;
+        s_red_i[threadIdx.x] = bi;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                const float ov = s_red_v[threadIdx.x + o];
+                const int oi = s_red_i[threadIdx.x + o];
+                if (ov > s_red_v[threadIdx.x] || (ov == s_red_v[threadIdx.x] && oi < s_red_i[threadIdx.x])) {
+                    s_red_v[threadIdx.x] = ov;
+                    s_red_i[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int L = s_red_i[0];
+            s_sel[k] = L;
+            st.logp_next[q * K + k] = s_red_v[0];
+            s_score[L] = -INFINITY;
+        }
+        __syncthreads();
+    }
+    // materialise the K new candidates
+    for (int k = 0; k < K; ++k) {
+        const int L = s_sel[k];
+        const int cb = L / per_c, p = (L % per_c) / K, j = L % K;
+        const int c = q * beam + cb;
+        const int* src = st.cand_cur + (long long)c * st.ldw;
+        int* dst = st.cand_next + (long long)(q * K + k) * st.ldw;
+        const int slot0 = st.c_slot0[c];
+        const bool fin = st.c_fin[c] != 0;
+        int n = 0, r = 0;
+        if (!fin) { n = st.c_pick[c]; r = st.c_rowbase[c] + n; }
+        const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+        const int tok = fin ? st.pad : st.topi[((long long)r * (dl + 1) + p) * K + j];
+        for (int col = threadIdx.x; col < W; col += blockDim.x) {
+            int t = src[col];
+            if (col >= slot0 && col <= slot0 + dl) {
+                const int o = col - slot0;
+                t = o < p ? dr[o] : (o == p ? tok : st.pad);
+            }
+            dst[col] = t;
+        }
+        if (threadIdx.x == 0) st.acc_stat[q * K + k] = fin ? -1 : p;
+    }
+}
+void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s) {
+    const size_t smem = ((size_t)beam * (dl + 1) * st.K + (size_t)beam * (dl + 2)) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(beam_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    beam_expand_kernel<<<st.B, 256, smem, s>>>(st, beam, W, dl, logits);
+}
+
+// ---- loop control ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) {
+    __shared__ int s_all_fin, s_min_pad, s_acc, s_cnt;
+    if (threadIdx.x == 0) { s_all_fin = 1; s_min_pad = 0x7fffffff; s_acc = 0; s_cnt = 0; }
+    __syncthreads();
+    const int R = st.B * st.K;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int* row = st.cand_next + (long long)r * st.ldw;
+        int pads = 0, fin = 0;
+        for (int j = 0; j < W; ++j) { pads += row[j] == st.pad; fin |= row[j] == st.eos; }
+        if (!fin) atomicAnd(&s_all_fin, 0);
+        atomicMin(&s_min_pad, pads);
+        const int a = st.acc_stat[r];
+        if (a >= 0) { atomicAdd(&s_acc, a); atomicAdd(&s_cnt, 1); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.ctrl[BC_ALL_FINISHED] = s_all_fin;
+        st.ctrl[BC_EMPTY_COLS] = s_min_pad;
+        st.ctrl[BC_ACCEPTED] += s_acc;
+        st.ctrl[BC_PRODUCED] += s_acc + s_cnt;
+    }
+}
+void launch_beam_control(const BeamState& st, int W, cudaStream_t s) { beam_control_kernel<<<1, 256, 0, s>>>(st, W); }
+
+__global__ void beam_init_kernel(BeamState st) {
+    const long long n = (long long)st.B * st.K * st.ldw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        st.cand_cur[i] = (i % st.ldw == 0 && i / st.ldw < st.B) ? st.bos : st.pad;
+        st.cand_next[i] = st.pad;
+    }
+    if (blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < st.B * st.K; b += blockDim.x) { st.logp_cur[b] = 0.f; st.logp_next[b] = 0.f; }
+        if (threadIdx.x < BC_COUNT) st.ctrl[threadIdx.x] = 0;
+    }
+}
+void launch_beam_init(const BeamState& st, cudaStream_t s) { beam_init_kernel<<<64, 256, 0, s>>>(st); }
+
+// (rows, W) int32 with row stride ldw -> dense int64
+__global__ void beam_export_kernel(const int* __restrict__ cand, int ldw, int R, int W, long long* __restrict__ out) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx < (long long)R * W) out[idx] = cand[(idx / W) * ldw + idx % W];
+}
+void launch_beam_export(const int* cand, int ldw, int R, int W, long long* out, cudaStream_t s) {
+    const long long n = (long long)R * W;
+    if (n > 0) beam_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cand, ldw, R, W, out);
+}
+
+}  // namespace ttb

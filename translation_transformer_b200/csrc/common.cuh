@@ -68,4 +68,15 @@ enum Ctrl : int {
     CTRL_COUNT = 16
 };
 
+// Control words of the speculative beam search (read back by the host once per iteration).
+enum BeamCtrl : int {
+    BC_NLIVE_ROWS = 0,    // (candidate, draft) rows of unfinished candidates = decoder batch of the iteration
+    BC_ERROR = 1,         // 0 ok, 3 draft slots not contiguous (PAD inside a hypothesis), 4 fewer leaves than n_best
+    BC_ALL_FINISHED = 2,  // every new candidate contains EOS
+    BC_EMPTY_COLS = 3,    // min over new candidates of the number of PAD columns
+    BC_ACCEPTED = 4,      // accepted draft tokens of the surviving hypotheses (reference accepted_tokens_num)
+    BC_PRODUCED = 5,      // reference produced_non_pad_tokens
+    BC_COUNT = 8
+};
+
 }  // namespace ttb

@@ -131,6 +131,7 @@ struct ttb_engine {
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_key[12] = {};
     long long graph_launches = 0;
+    DevBuf beam;                 // arena of the beam-search state
     DevBuf hist;                 // per-iteration live-query count of the last generate()
     std::vector<int> h_hist;
 
@@ -634,6 +635,152 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     return 0;
 }
 
+
+// ---- speculative beam search (speculative_decoding.py:428-598), host loop + device kernels ---------------
+// The per-iteration shapes (token-matrix width, draft length, live rows) depend on the hypotheses, so the
+// host reads a handful of control words back once per iteration; tokens, scores and logits never leave
+// the device.
+template <typename ActT>
+static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int K, int draft_len, int N,
+                    int pad, int bos, int eos, int c_token, int tie_break, int64_t* out_dev, int32_t* out_width,
+                    int32_t* trace_nacc, int32_t* trace_pick, ttb_generate_stats* stats, cudaStream_t user_stream) {
+    const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
+    const int n_dec = (int)e->dec.size();
+    cudaStream_t s = e->stream;
+    TTB_CUDA_OK(cudaEventRecord(e->join_ev, user_stream));
+    TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
+    const long long launches0 = e->launches;
+    const int D0 = std::min(std::max(5, draft_len), 200);       // speculative_decoding.py:278-284
+    const long long TS = (long long)B * Ls;
+    const int Cmax = B * K, Rmax = Cmax * N;
+    const int ldw = max_len + D0 + 4;
+    const long long Tmax = (long long)Rmax * ldw;
+
+    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (e->drafts.ensure((size_t)B * N * D0 * sizeof(int))) return 1;
+    if (ensure_work<ActT>(e, std::max(Tmax, TS), 1)) return 1;
+    DevBuf& bb = e->beam;
+    // one arena for the small beam buffers
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_cand0 = take((size_t)Cmax * ldw * 4), o_cand1 = take((size_t)Cmax * ldw * 4);
+    const size_t o_lp0 = take(Cmax * 4), o_lp1 = take(Cmax * 4);
+    const size_t o_slot = take(Cmax * 4), o_fin = take(Cmax * 4), o_base = take(Cmax * 4), o_nacc = take((size_t)Cmax * N * 4);
+    const size_t o_pick = take(Cmax * 4), o_acc = take(Cmax * 4), o_ctrl = take(BC_COUNT * 4);
+    const size_t o_rows = take((size_t)Rmax * ldw * 4), o_rc = take(Rmax * 4), o_rq = take(Rmax * 4), o_rs = take(Rmax * 4);
+    const size_t n_rp = (size_t)Rmax * (D0 + 1);
+    const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
+    const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4);
+    if (bb.ensure(off)) return 1;
+    char* base = bb.as<char>();
+
+    TTB_CUDA_OK(cudaEventRecord(e->t0, s));
+    int* src32 = e->src32.as<int>();
+    { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s); }
+    float* mem = e->memory.as<float>();
+    ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
+    if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
+    ActT* crosskv = e->crosskv.as<ActT>();
+    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
+    { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D0, N, eos, pad, c_token, e->drafts.as<int>(), s); }
+
+    BeamState st{};
+    st.B = B; st.K = K; st.N = N; st.dl0 = D0; st.V = V; st.pad = pad; st.bos = bos; st.eos = eos; st.ldw = ldw; st.tie_break = tie_break;
+    st.cand_cur = (int*)(base + o_cand0); st.cand_next = (int*)(base + o_cand1);
+    st.logp_cur = (float*)(base + o_lp0); st.logp_next = (float*)(base + o_lp1);
+    st.drafts = e->drafts.as<int>();
+    st.c_slot0 = (int*)(base + o_slot); st.c_fin = (int*)(base + o_fin); st.c_rowbase = (int*)(base + o_base);
+    st.c_nacc = (int*)(base + o_nacc); st.c_pick = (int*)(base + o_pick); st.acc_stat = (int*)(base + o_acc); st.ctrl = (int*)(base + o_ctrl);
+    st.rows_tok = (int*)(base + o_rows); st.row_cand = (int*)(base + o_rc); st.row_query = (int*)(base + o_rq); st.row_slot0 = (int*)(base + o_rs);
+    st.topv = (float*)(base + o_topv); st.topi = (int*)(base + o_topi); st.nkeep = (int*)(base + o_keep);
+    st.lmax = (float*)(base + o_max); st.lsum = (float*)(base + o_sum);
+    st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
+    float* xg = (float*)(base + o_xg);
+    ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
+    float* logits = (float*)(base + o_lg);
+    { Scope sc(e, KC_MISC, s); launch_beam_init(st, s); }
+
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    const int* n_live = st.ctrl + BC_NLIVE_ROWS;
+    int W = 1, empty_cols = 0, filled = 1, budget = max_len - filled - 1, dl = D0, C = B, beam = 1, iters = 0;
+    int* hc = e->h_ctrl;
+    while (budget >= 1 && filled <= max_len) {
+        dl = std::min(budget, dl);
+        const int grow = dl + 1 - empty_cols;
+        if (grow > 0) W += grow;
+        TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
+        const int R = C * N;
+        { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, W, dl, s); }
+        { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, W, dl, s); }
+        RowCount rows(R * W, n_live, W);
+        { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
+        auto self_attn = [&](int, ActT* qkv, ActT* att) {
+            attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, R, n_live, W, W, W, nullptr,
+                 st.rows_tok, W, e->d.tgt_pad_token_idx, true, H, HD, s);
+        };
+        auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+            const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+            attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, W, Ls, Ls, st.row_query,
+                 src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+        };
+        if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
+        { Scope sc(e, KC_MISC, s); launch_beam_gather<ActT>(st, x, xh, R, W, dl, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
+        RowCount rp_rows(R * (dl + 1), n_live, dl + 1);
+        if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
+        { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, iters, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_control(st, W, s); }
+        TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TTB_CUDA_OK(cudaStreamSynchronize(s));
+        ++iters;
+        if (hc[BC_ERROR]) break;
+        std::swap(st.cand_cur, st.cand_next);
+        std::swap(st.logp_cur, st.logp_next);
+        C = B * K;
+        beam = K;
+        if (hc[BC_ALL_FINISHED]) break;
+        empty_cols = hc[BC_EMPTY_COLS];
+        filled = W - empty_cols;
+        budget = max_len - filled - 1;
+    }
+    TTB_CUDA_OK(cudaGetLastError());
+    const int err = hc[BC_ERROR];
+    if (!err) {
+        TTB_CHECK(iters > 0, "max_len too small for the speculative beam search (the reference fails as well)");
+        launch_beam_export(st.cand_cur, ldw, B * K, W, reinterpret_cast<long long*>(out_dev), s);
+        e->launches++;
+    }
+    TTB_CUDA_OK(cudaEventRecord(e->t1, s));
+    TTB_CUDA_OK(cudaStreamSynchronize(s));
+    TTB_CUDA_OK(cudaGetLastError());
+    prof_collect(e);
+    if (out_width) *out_width = W;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->t0, e->t1);
+    if (stats) {
+        stats->model_calls = iters;
+        stats->accepted_tokens = hc[BC_ACCEPTED];
+        stats->produced_tokens = hc[BC_PRODUCED];
+        stats->unfinished = 0;
+        stats->error = err;
+        stats->gpu_launches = (int32_t)(e->launches - launches0);
+        stats->gpu_ms = ms;
+    }
+    if (err == 3) {
+        set_last_error("PAD predicted inside a hypothesis: draft slots are not contiguous (the reference fails on the reshape at speculative_decoding.py:524-526)");
+        return TTB_ERR_REF_SHAPE;
+    }
+    if (err == 4) {
+        set_last_error("fewer candidate continuations than n_best (reference assert in topk_in_each_group, speculative_decoding.py:195)");
+        return TTB_ERR_REF_ASSERT;
+    }
+    return 0;
+}
+
 }  // namespace ttb
 
 // =================================================================================================
@@ -686,7 +833,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     }
     DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
                       &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
-                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist};
+                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam};
     for (DevBuf* b : bufs) b->release();
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
@@ -837,6 +984,27 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                              replace_token, tie_break, out_dev, trace_dev, stats, s),
                         greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
                                                   replace_token, tie_break, out_dev, trace_dev, stats, s));
+}
+
+int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,
+                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t pad_token, int32_t bos_token,
+                                  int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev, int32_t* out_width,
+                                  int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(src_dev && out_dev && B > 0 && Ls > 1 && max_len > 2, "bad arguments");
+    TTB_CHECK(n_best >= 1 && n_best <= 32, "n_best must be in [1, 32]");
+    TTB_CHECK(n_drafts > 0, "The number of drafts must be greater than 0");
+    TTB_CHECK(pad_token != c_token, "The pad token and the replace token must be different");
+    TTB_CHECK(eos_token != c_token, "The eos token and the replace token must be different");
+    TTB_CHECK(eos_token != pad_token, "The eos token and the pad token must be different");
+    TTB_CHECK(Ls <= e->d.max_positions && max_len + 210 <= e->d.max_positions, "sequence longer than the positional table");
+    TTB_CHECK(e->d.tgt_vocab_size <= 1024, "vocabularies above 1024 tokens are not supported by the beam statistics kernel");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, beam_api<float>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token, eos_token,
+                                           c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s),
+                        beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token,
+                                                eos_token, c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s));
 }
 
 int ttb_kernel_class_count(void) { return KC_COUNT; }

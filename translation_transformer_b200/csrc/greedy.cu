@@ -13,111 +13,9 @@
 //   * the width bookkeeping of the reference's shared token matrix (:93-102), which decides when
 //     the loop stops and when the reference itself would fail (see oracle/greedy_speculative.py).
 #include "kernels.cuh"
+#include "topk_emul.cuh"
 
 namespace ttb {
-
-// ---- torch CPU topk(1) tie-break: libstdc++ introselect on (value, index) pairs -------------
-struct VI { int v; int i; };
-__device__ __forceinline__ bool gt(const VI& a, const VI& b) { return a.v > b.v; }
-__device__ __forceinline__ void swp(VI& a, VI& b) { VI t = a; a = b; b = t; }
-
-__device__ void push_heap_(VI* e, int first, int hole, int top, VI val) {
-    int parent = (hole - 1) / 2;
-    while (hole > top && gt(e[first + parent], val)) {
-        e[first + hole] = e[first + parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
-    }
-    e[first + hole] = val;
-}
-__device__ void adjust_heap_(VI* e, int first, int hole, int len, VI val) {
-    const int top = hole;
-    int child = hole;
-    while (child < (len - 1) / 2) {
-        child = 2 * (child + 1);
-        if (gt(e[first + child], e[first + child - 1])) child--;
-        e[first + hole] = e[first + child];
-        hole = child;
-    }
-    if ((len & 1) == 0 && child == (len - 2) / 2) {
-        child = 2 * (child + 1);
-        e[first + hole] = e[first + child - 1];
-        hole = child - 1;
-    }
-    push_heap_(e, first, hole, top, val);
-}
-__device__ void heap_select_(VI* e, int first, int middle, int last) {
-    const int len = middle - first;
-    if (len >= 2) {
-        int parent = (len - 2) / 2;
-        while (true) {
-            adjust_heap_(e, first, parent, len, e[first + parent]);
-            if (parent == 0) break;
-            parent--;
-        }
-    }
-    for (int i = middle; i < last; ++i) {
-        if (gt(e[i], e[first])) {
-            VI val = e[i];
-            e[i] = e[first];
-            adjust_heap_(e, first, 0, len, val);
-        }
-    }
-}
-// index torch.topk(vals, 1) returns on the CPU backend (n < 64: std::nth_element, else partial_sort)
-__device__ int topk1_torch_cpu(const int* vals, int n) {
-    if (n >= 64 || n <= 1) {
-        int best = 0;
-        for (int j = 1; j < n; ++j) if (vals[j] > vals[best]) best = j;
-        return best;
-    }
-    VI e[64];
-    for (int j = 0; j < n; ++j) { e[j].v = vals[j]; e[j].i = j; }
-    int first = 0, last = n;
-    const int nth = 0;
-    int depth = 2 * (31 - __clz(n));
-    while (last - first > 3) {
-        if (depth == 0) {
-            heap_select_(e, first, nth + 1, last);
-            swp(e[first], e[nth]);
-            return e[nth].i;
-        }
-        --depth;
-        const int mid = first + (last - first) / 2;
-        {   // __move_median_to_first(first, first + 1, mid, last - 1)
-            const int a = first + 1, b = mid, c = last - 1;
-            if (gt(e[a], e[b])) {
-                if (gt(e[b], e[c])) swp(e[first], e[b]);
-                else if (gt(e[a], e[c])) swp(e[first], e[c]);
-                else swp(e[first], e[a]);
-            } else if (gt(e[a], e[c])) swp(e[first], e[a]);
-            else if (gt(e[b], e[c])) swp(e[first], e[c]);
-            else swp(e[first], e[b]);
-        }
-        int lo = first + 1, hi = last;  // __unguarded_partition(first + 1, last, pivot = first)
-        while (true) {
-            while (gt(e[lo], e[first])) ++lo;
-            --hi;
-            while (gt(e[first], e[hi])) --hi;
-            if (!(lo < hi)) break;
-            swp(e[lo], e[hi]);
-            ++lo;
-        }
-        if (lo <= nth) first = lo; else last = lo;
-    }
-    for (int i = first + 1; i < last; ++i) {  // __insertion_sort
-        VI val = e[i];
-        if (gt(val, e[first])) {
-            for (int j = i; j > first; --j) e[j] = e[j - 1];
-            e[first] = val;
-        } else {
-            int j = i;
-            while (gt(val, e[j - 1])) { e[j] = e[j - 1]; --j; }
-            e[j] = val;
-        }
-    }
-    return e[nth].i;
-}
 
 // ---- width plan of the coming iteration (speculative_decoding.py:93-102) -----------------------
 // Executed by one CTA after the live list is final.  `W` is the current width of the reference's

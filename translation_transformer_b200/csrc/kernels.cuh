@@ -113,4 +113,31 @@ void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long
                                 long long cache_layer_stride, long long cache_query_stride, int cache_ld,
                                 cudaStream_t s);
 
+// ---- beam.cu --------------------------------------------------------------------------------------
+struct BeamState {
+    int B, K, N, dl0, V, pad, bos, eos, ldw, tie_break;
+    int* cand_cur; int* cand_next;        // [B*K][ldw] hypotheses (query-major), ping-pong
+    float* logp_cur; float* logp_next;    // [B*K]
+    const int* drafts;                    // [B][N][dl0]
+    int* c_slot0; int* c_fin; int* c_rowbase; int* c_nacc; int* c_pick; int* acc_stat; int* ctrl;
+    int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows
+    float* topv; int* topi; int* nkeep; float* lmax; float* lsum;      // per (row, position) statistics
+    int* trace_nacc; int* trace_pick;     // optional [iter][B*K][N] / [iter][B*K]
+};
+void launch_beam_init(const BeamState& st, cudaStream_t s);
+void launch_beam_prepare(const BeamState& st, int C, int W, int dl, cudaStream_t s);
+void launch_beam_fill_rows(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
+template <typename ActT>
+void launch_beam_gather(const BeamState& st, const float* x, const ActT* xh, int max_rows, int W, int dl, int E,
+                        float* xg, ActT* xgh, cudaStream_t s);
+void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s);
+void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s);
+void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s);
+void launch_beam_control(const BeamState& st, int W, cudaStream_t s);
+void launch_beam_export(const int* cand, int ldw, int R, int W, long long* out, cudaStream_t s);
+// embedding of (rows, L) token matrices whose live row count is on the device
+template <typename ActT>
+void launch_embed_seq_rows(const int* tok, RowCount rows, int L, const float* table, const float* pe, int E,
+                           float* x, ActT* xh, cudaStream_t s);
+
 }  // namespace ttb

@@ -11,7 +11,7 @@ from pathlib import Path
 from timeit import default_timer as timer
 from typing import Any
 
-from .decoding.speculative_decoding import TranslationInferenceGreedySpeculative
+from .decoding.speculative_decoding import TranslationInferenceBeamSearchSpeculative, TranslationInferenceGreedySpeculative
 from .model import B200Transformer
 from .weights import ModelConfig, random_init_state_dict
 
@@ -61,8 +61,14 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
                 self.model, max_len=self.max_len, draft_len=self.draft_len, n_drafts=self.n_drafts,
                 pad_token=self.tgt_pad_token_i, bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
                 replace_token=self.tgt_tokenizer.encoder_dict["c"])
+        if self.generation == "beam_search_speculative":
+            return TranslationInferenceBeamSearchSpeculative(
+                self.model, vocab_size=self.tgt_tokenizer.n_tokens, max_len=self.max_len, n_best=self.beam_size,
+                draft_len=self.draft_len, n_drafts=self.n_drafts, pad_token=self.tgt_pad_token_i,
+                bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
+                C_token=self.tgt_tokenizer.encoder_dict["c"], smart_drafts_mode=self.smart_drafts_mode)
         options = ", ".join(["beam_search", "greedy", "greedy_speculative", "beam_search_speculative"])
-        if self.generation in ("beam_search", "greedy", "beam_search_speculative"):
+        if self.generation in ("beam_search", "greedy"):
             raise NotImplementedError(f"generation={self.generation} is not on the B200 hot path yet (DESIGN.md §0 row f)")
         raise ValueError(f"Unknown generation option {self.generation}. Options are {options}.")
 

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -257,6 +258,193 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// =====================================================================================================
+// Persistent, warp-specialised variant (default).  One CTA per SM loops over output tiles:
+//   warp 0      TMA producer     (4-stage smem ring, runs ahead across tile boundaries)
+//   warp 1      MMA issuer       (tcgen05.mma into one of two TMEM accumulator buffers)
+//   warps 2..9  epilogue         (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4)
+// so the loads and MMAs of tile i+1 overlap the epilogue of tile i (smem full/empty and TMEM
+// full/empty mbarrier pipelines).  Epilogue: tcgen05.ld -> bias/ReLU/convert -> per-warp staging tile
+// -> coalesced 16-byte stores of whole row segments.
+namespace pers {
+constexpr int PSTAGES = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int COLS_PER_WARP = BN / 2;   // 64
+template <typename OutT> constexpr int pitch() { return COLS_PER_WARP * (int)sizeof(OutT) + 16; }
+template <typename OutT> constexpr int smem_bytes() {
+    return PSTAGES * STAGE_BYTES + EPI_WARPS * 32 * pitch<OutT>() + EPI_WARPS * COLS_PER_WARP * 4 + 1024 + 256;
+}
+}  // namespace pers
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(pers::THREADS, 1)
+gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                               const float* __restrict__ bias, OutT* __restrict__ C, int ldc, RowCount rows, int N, int K, int relu) {
+    using namespace pers;
+    constexpr int NST = pers::PSTAGES;
+    const int M = rows.live();
+    const int n_tiles_n = (N + BN - 1) / BN;
+    const int total_tiles = ((M + BM - 1) / BM) * n_tiles_n;
+    if ((int)blockIdx.x >= total_tiles) return;   // uniform per CTA, before any barrier / TMEM allocation
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    constexpr int ESZ = (int)sizeof(OutT);
+    constexpr int PITCH = pitch<OutT>();
+    constexpr int STAGING_BYTES = EPI_WARPS * 32 * PITCH;
+    constexpr int BIAS_BYTES = EPI_WARPS * COLS_PER_WARP * 4;
+    uint8_t* staging = gen_base + NST * STAGE_BYTES;
+    float* bias_sm = reinterpret_cast<float*>(staging + STAGING_BYTES);
+    const uint32_t bar_base = base + NST * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NST + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NST + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(staging + STAGING_BYTES + BIAS_BYTES + 8 * (2 * NST + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    const uint32_t a_dst = base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    tma_load_2d(a_dst, &tmA, kb * BK, m0, full_bar(s));
+                    tma_load_2d(b_dst, &tmB, kb * BK, n0, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                const uint32_t acc_ph = (lt >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_ph ^ 1);      // epilogue has drained this accumulator buffer
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_src = base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(a_src + k * UMMA_K * 2);
+                        const uint64_t bdesc = umma_desc_sw128(b_src + k * UMMA_K * 2);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+    } else {  // ===== epilogue warps =====
+        const int ew = warp - 2;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = ew >> 2;               // which 64 columns of the tile
+        uint8_t* stage = staging + ew * 32 * PITCH;
+        float* my_bias = bias_sm + ew * COLS_PER_WARP;
+        constexpr int EPC = 16 / ESZ;                 // elements per 16-byte chunk
+        constexpr int CH = COLS_PER_WARP / EPC;       // chunks per row segment: 8 (bf16) or 16 (fp32)
+        constexpr int RPI = 32 / CH;                  // rows per warp store instruction: 4 or 2
+        const bool vec_ok = ((long long)ldc * ESZ) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN + half * COLS_PER_WARP;
+            const int acc = lt & 1;
+            const uint32_t acc_ph = (lt >> 1) & 1;
+            const int n_cols = max(0, min(COLS_PER_WARP, N - n0));
+            // bias slice of this warp's columns (overlaps the wait for the accumulator)
+            for (int c = lane; c < COLS_PER_WARP; c += 32) my_bias[c] = (bias && c < n_cols) ? __ldg(bias + n0 + c) : 0.f;
+            __syncwarp();
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS_PER_WARP + c0), r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(r[j]) + my_bias[c0 + j];
+                    if (relu) t = fmaxf(t, 0.f);
+                    v[j] = t;
+                }
+                stage_chunk<OutT>(stage + lane * PITCH + c0 * ESZ, v);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));   // accumulator buffer may be overwritten
+            const int row_base = m0 + q * 32;
+            if (vec_ok) {
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr += RPI) {
+                    const int rl = rr + lane / CH, ch = lane % CH;
+                    const int row = row_base + rl, col = ch * EPC;
+                    if (row < M && col < n_cols) {
+                        const uint8_t* sp = stage + rl * PITCH + ch * 16;
+                        OutT* gp = C + (long long)row * ldc + n0 + col;
+                        if (col + EPC <= n_cols) {
+                            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+                        } else {
+                            for (int j = 0; j < n_cols - col; ++j) gp[j] = reinterpret_cast<const OutT*>(sp)[j];
+                        }
+                    }
+                }
+            } else {
+                for (int rl = 0; rl < 32; ++rl) {
+                    const int row = row_base + rl;
+                    if (row >= M) break;
+                    const OutT* sp = reinterpret_cast<const OutT*>(stage + rl * PITCH);
+                    for (int c = lane; c < n_cols; c += 32) C[(long long)row * ldc + n0 + c] = sp[c];
+                }
+            }
+            __syncwarp();   // staging tile is rewritten by the next iteration
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
 // ---- host: tensor-map cache -----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -324,8 +512,25 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     CUtensorMap tmA, tmB;
     if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
     if (int rc = get_tensor_map(W, N, K, K, BN, &tmB)) return rc;
-    static bool attr_set[2] = {false, false};
+    static const bool use_v1 = [] { const char* v = getenv("TTB_GEMM_V1"); return v && v[0] == '1'; }();
     constexpr int which = std::is_same<OutT, float>::value ? 0 : 1;
+    if (!use_v1) {
+        static bool pattr_set[2] = {false, false};
+        constexpr int PSMEM = pers::smem_bytes<OutT>();
+        if (!pattr_set[which]) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
+            if (e != cudaSuccess) {
+                set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+                return 1;
+            }
+            pattr_set[which] = true;
+        }
+        const int max_tiles = ((N + BN - 1) / BN) * ((rows.max_rows + BM - 1) / BM);
+        const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+        gemm_bf16_tc_persistent_kernel<OutT><<<grid, pers::THREADS, PSMEM, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
+        return 0;
+    }
+    static bool attr_set[2] = {false, false};
     if (!attr_set[which]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {

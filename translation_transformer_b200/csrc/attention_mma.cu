@@ -18,7 +18,7 @@
 namespace ttb {
 namespace amma {
 
-constexpr int WARPS = 8, THREADS = WARPS * 32, ROWS_PER_WARP = 32, ROWS_PER_CTA = WARPS * ROWS_PER_WARP;
+constexpr int WARPS = 4, THREADS = WARPS * 32, ROWS_PER_WARP = 32, ROWS_PER_CTA = WARPS * ROWS_PER_WARP;
 constexpr int KT = 64;  // keys staged per tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,7 +158,8 @@ attn_mma_kernel(Params p) {
     const __nv_bfloat16* vbase = p.v + (long long)kvg * kv_group_stride * p.kv_ld + h * HD;
     const int rA = lane >> 2, c0 = (lane & 3) * 2;
 
-    for (int blk0 = 0; blk0 < p.Lq; blk0 += ROWS_PER_CTA) {
+    {   // one block of ROWS_PER_CTA query rows per CTA (blockIdx.z): more, smaller CTAs balance the 148 SMs better
+        const int blk0 = blockIdx.z * ROWS_PER_CTA;
         const int wrow0 = blk0 + warp * ROWS_PER_WARP;       // first query row of this warp
         const bool warp_live = wrow0 < p.Lq;
         const int wrow_last = min(p.Lq, wrow0 + ROWS_PER_WARP) - 1;
@@ -296,7 +297,7 @@ attn_mma_kernel(Params p) {
 }
 
 static void launch(const Params& p, int heads, int head_dim, int n_groups_max, cudaStream_t s) {
-    dim3 grid(heads, n_groups_max);
+    dim3 grid(heads, n_groups_max, (p.Lq + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
     if (head_dim == 16) attn_mma_kernel<16><<<grid, THREADS, 0, s>>>(p);
     else if (head_dim == 32) attn_mma_kernel<32><<<grid, THREADS, 0, s>>>(p);
     else if (head_dim == 64) attn_mma_kernel<64><<<grid, THREADS, 0, s>>>(p);

@@ -270,10 +270,10 @@ namespace pers {
 constexpr int PSTAGES = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
-constexpr int COLS_PER_WARP = BN / 2;   // 64
-template <typename OutT> constexpr int pitch() { return COLS_PER_WARP * (int)sizeof(OutT) + 16; }
-template <typename OutT> constexpr int smem_bytes() {
-    return PSTAGES * STAGE_BYTES + EPI_WARPS * 32 * pitch<OutT>() + EPI_WARPS * COLS_PER_WARP * 4 + 1024 + 256;
+template <typename OutT, int BN_> constexpr int pitch() { return (BN_ / 2) * (int)sizeof(OutT) + 16; }
+template <int BN_> constexpr int stage_bytes() { return A_BYTES + BN_ * BK * 2; }
+template <typename OutT, int BN_> constexpr int smem_bytes() {
+    return PSTAGES * stage_bytes<BN_>() + EPI_WARPS * 32 * pitch<OutT, BN_>() + EPI_WARPS * (BN_ / 2) * 4 + 1024 + 256;
 }
 }  // namespace pers
 
@@ -281,12 +281,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <typename OutT>
+template <typename OutT, int BN_>
 __global__ void __launch_bounds__(pers::THREADS, 1)
 gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                const float* __restrict__ bias, OutT* __restrict__ C, int ldc, RowCount rows, int N, int K, int relu) {
     using namespace pers;
     constexpr int NST = pers::PSTAGES;
+    constexpr int BN = BN_;                                  // shadows tc::BN inside this kernel
+    constexpr int COLS_PER_WARP = BN_ / 2;
+    constexpr int STAGE_BYTES = pers::stage_bytes<BN_>();   // shadows tc::STAGE_BYTES
     const int M = rows.live();
     const int n_tiles_n = (N + BN - 1) / BN;
     const int total_tiles = ((M + BM - 1) / BM) * n_tiles_n;
@@ -297,7 +300,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - raw);
     constexpr int ESZ = (int)sizeof(OutT);
-    constexpr int PITCH = pitch<OutT>();
+    constexpr int PITCH = pitch<OutT, BN_>();
     constexpr int STAGING_BYTES = EPI_WARPS * 32 * PITCH;
     constexpr int BIAS_BYTES = EPI_WARPS * COLS_PER_WARP * 4;
     uint8_t* staging = gen_base + NST * STAGE_BYTES;
@@ -515,20 +518,29 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     static const bool use_v1 = [] { const char* v = getenv("TTB_GEMM_V1"); return v && v[0] == '1'; }();
     constexpr int which = std::is_same<OutT, float>::value ? 0 : 1;
     if (!use_v1) {
-        static bool pattr_set[2] = {false, false};
-        constexpr int PSMEM = pers::smem_bytes<OutT>();
-        if (!pattr_set[which]) {
-            cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
-            if (e != cudaSuccess) {
-                set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-                return 1;
-            }
-            pattr_set[which] = true;
-        }
-        const int max_tiles = ((N + BN - 1) / BN) * ((rows.max_rows + BM - 1) / BM);
+        // narrow GEMMs (N <= 256 at full batch) get 64-column tiles so that every SM owns more than one
+        // tile and the epilogue/main-loop overlap of the persistent kernel has something to overlap
+        const int tiles128 = ((N + 127) / 128) * ((rows.max_rows + BM - 1) / BM);
+        const bool narrow = tiles128 < 2 * kNumSMs && K <= 512;   // long-K GEMMs (FFN2) would double their A re-reads
+        const int bn = narrow ? 64 : 128;
+        if (int rc = get_tensor_map(W, N, K, K, bn, &tmB)) return rc;
+        const int max_tiles = ((N + bn - 1) / bn) * ((rows.max_rows + BM - 1) / BM);
         const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-        gemm_bf16_tc_persistent_kernel<OutT><<<grid, pers::THREADS, PSMEM, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
-        return 0;
+        static bool pattr_set[2][2] = {{false, false}, {false, false}};
+        auto launch = [&](auto kernel, int smem, bool& flag) -> int {
+            if (!flag) {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e != cudaSuccess) {
+                    set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+                    return 1;
+                }
+                flag = true;
+            }
+            kernel<<<grid, pers::THREADS, smem, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
+            return 0;
+        };
+        if (narrow) return launch(gemm_bf16_tc_persistent_kernel<OutT, 64>, pers::smem_bytes<OutT, 64>(), pattr_set[which][0]);
+        return launch(gemm_bf16_tc_persistent_kernel<OutT, 128>, pers::smem_bytes<OutT, 128>(), pattr_set[which][1]);
     }
     static bool attr_set[2] = {false, false};
     if (!attr_set[which]) {

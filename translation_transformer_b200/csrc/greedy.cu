@@ -28,15 +28,20 @@ __device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, 
         if (threadIdx.x == 0) { st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
         return;
     }
-    int dead = 0;
-    for (int c = threadIdx.x; c < W; c += blockDim.x) {
-        bool all_pad = true;
-        for (int g = 0; g < n_active && all_pad; ++g) {
-            const int b = st.active[g];
-            if (c <= st.front[b] && st.gen[(long long)b * st.gen_ld + c] != st.pad) all_pad = false;
-        }
-        dead += all_pad ? 1 : 0;
+    // a column is dead when every live row holds PAD there; all (row, column) probes are independent
+    // loads (one round of memory latency instead of a serial scan per column)
+    extern __shared__ int s_plan_dyn[];
+    int* col_live = s_plan_dyn + st.plan_smem_offset;      // [W]
+    for (int c = threadIdx.x; c < W; c += blockDim.x) col_live[c] = 0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n_active * W; idx += blockDim.x) {
+        const int g = idx / W, c = idx % W;
+        const int b = st.active[g];
+        if (c <= st.front[b] && st.gen[(long long)b * st.gen_ld + c] != st.pad) col_live[c] = 1;
     }
+    __syncthreads();
+    int dead = 0;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) dead += col_live[c] ? 0 : 1;
     if (dead) atomicAdd(&s_tmp[0], dead);
     __syncthreads();
     const int Wn = W + st.D + 1 - s_tmp[0];
@@ -63,7 +68,9 @@ __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     if (threadIdx.x == 0) { st.ctrl[CTRL_N_ACTIVE] = st.B; st.ctrl[CTRL_LS] = st.Ls; }
     plan_next_iteration(st, st.B, 1, s_tmp);
 }
-void launch_greedy_init(const GreedyState& st, cudaStream_t s) { greedy_init_kernel<<<1, 256, 0, s>>>(st); }
+void launch_greedy_init(const GreedyState& st, cudaStream_t s) {
+    greedy_init_kernel<<<1, 256, (size_t)(st.plan_smem_offset + st.gen_ld) * sizeof(int), s>>>(st);
+}
 
 // ---- step-token embedding ---------------------------------------------------------------------
 template <typename ActT>
@@ -120,7 +127,19 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
             const int* pr = st.pred + ((long long)g * N + n) * (D + 1);
             const int* dr = st.drafts + ((long long)b * N + n) * D;
             int a = 0;
-            while (a < D && dr[a] == pr[a]) ++a;
+            bool open = true;
+            for (int a0 = 0; a0 < D && open; a0 += 8) {          // 8 independent loads per round
+                int dv[8], pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    dv[u] = (a0 + u < D) ? dr[a0 + u] : -1;
+                    pv[u] = (a0 + u < D) ? pr[a0 + u] : -2;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (open && dv[u] == pv[u]) ++a; else open = false;
+                }
+            }
             if (n < 64) s_nacc[n] = a;
             if (a > best_val) { best_val = a; best_first = n; }
         }
@@ -183,7 +202,7 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
 }
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     const int warps = st.B < 32 ? (st.B < 4 ? 4 : st.B) : 32;
-    greedy_accept_kernel<<<1, warps * 32, ((size_t)st.B + warps * 64) * sizeof(int), s>>>(st);
+    greedy_accept_kernel<<<1, warps * 32, ((size_t)st.plan_smem_offset + st.gen_ld) * sizeof(int), s>>>(st);
 }
 
 // ---- KV-cache append ------------------------------------------------------------------------------

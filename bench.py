@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--pad-bias", type=float, default=0.0)
     ap.add_argument("--cpu-queries", type=int, default=1, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tie-break", default="torch_cpu", choices=["torch_cpu", "lowest_index"])
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
 
@@ -210,7 +211,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd = build_weights(args)
     eng = B200Transformer(cfg, sd, precision=args.precision, device=local_rank)
-    gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
+    gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE,
+                                                tie_break=args.tie_break)
     lib = eng.lib
     n_total = args.warmup + args.steps + 1
     host = [batch_for(args, rank, i).pin_memory() for i in range(n_total)]

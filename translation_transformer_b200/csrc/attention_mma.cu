@@ -1,10 +1,12 @@
 // Tensor-core attention for the bf16 path (short sequences, head_dim 16/32/64).
 //
-// One CTA per (group, head).  A warp owns 32 query rows (two m16 tiles): Q fragments live in
-// registers, K/V tiles of 64 keys are staged in shared memory as bf16 (row pitch head_dim + 8
-// elements -> conflict-free ldmatrix), S = Q K^T and O += P V run on mma.sync.m16n8k16 (bf16 in,
-// fp32 accumulate), the softmax is the usual online (flash) formulation in fp32 with exp2.
-// P is rounded to bf16 for the second product (precision contract).
+// One CTA per (group, head, block of 256 query rows).  A warp owns 32 query rows (two m16 tiles): Q
+// fragments live in registers; the K/V rows the CTA needs are staged in shared memory as bf16 (row
+// pitch head_dim + 8 elements -> conflict-free ldmatrix) with cp.async — for the sequence lengths of
+// this model (<= 224 shared keys, <= 288 private keys) ALL of them in one round, i.e. one global
+// memory latency and one barrier per CTA instead of one per 64-key tile.  S = Q K^T and O += P V run
+// on mma.sync.m16n8k16 (bf16 in, fp32 accumulate), the softmax is the usual online (flash) formulation
+// in fp32 with exp2.  P is rounded to bf16 for the second product (precision contract).
 //
 // Key sources
 //   phase A ("shared" keys): all queries of the group see the same keys — encoder self-attention,
@@ -18,8 +20,9 @@
 namespace ttb {
 namespace amma {
 
-constexpr int WARPS = 4, THREADS = WARPS * 32, ROWS_PER_WARP = 32, ROWS_PER_CTA = WARPS * ROWS_PER_WARP;
-constexpr int KT = 64;  // keys staged per tile
+constexpr int WARPS = 8, THREADS = WARPS * 32, ROWS_PER_WARP = 32, ROWS_PER_CTA = WARPS * ROWS_PER_WARP;
+constexpr int KTA = 224;  // shared keys staged per round (covers max_len + draft_len + 2 = 212 and sources <= 224)
+constexpr int KTB = 288;  // private keys staged per round (256 query rows + one draft row of look-back)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -60,13 +63,42 @@ struct Params {
     int row_len;                                 // D + 1
 };
 
+// Staged keys: k/v rows of PITCH = HD + 8 elements ((HD+8)*2 bytes keeps 16-byte row alignment),
+// bias = 0 or -inf per staged key.
 template <int HD>
 struct Tile {
-    static constexpr int PITCH = HD + 8;         // elements; (HD+8)*2 bytes keeps 16-byte row alignment
-    __nv_bfloat16 k[KT][PITCH];
-    __nv_bfloat16 v[KT][PITCH];
-    float bias[KT];                              // 0 or -inf per staged key
+    static constexpr int PITCH = HD + 8;
+    __nv_bfloat16* k;
+    __nv_bfloat16* v;
+    float* bias;
 };
+template <int HD> constexpr int smem_bytes() { return (KTA + KTB) * (HD + 8) * 2 * 2 + (KTA + KTB) * 4; }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Stage rows [0, nk) of a K/V source into a tile (asynchronously) and zero rows [nk, round-up-32(nk)).
+template <int HD>
+__device__ __forceinline__ void stage_rows(const Tile<HD>& t, const __nv_bfloat16* ksrc, const __nv_bfloat16* vsrc, int ld, int nk) {
+    constexpr int CH = HD / 8, PITCH = Tile<HD>::PITCH;
+    const int nfill = (nk + 31) & ~31;
+    for (int idx = threadIdx.x; idx < nfill * CH; idx += THREADS) {
+        const int j = idx / CH, c = idx % CH;
+        __nv_bfloat16* kd = t.k + j * PITCH + c * 8;
+        __nv_bfloat16* vd = t.v + j * PITCH + c * 8;
+        if (j < nk) {
+            cp_async16(kd, ksrc + (long long)j * ld + c * 8);
+            cp_async16(vd, vsrc + (long long)j * ld + c * 8);
+        } else {
+            *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
 
 // One 32-key sub-block (keys kb..kb+31 of the staged tile) for one m16 tile of queries.
 //   MaskFn(row_sel, col) -> true when the (query row, key column) pair is masked; row_sel 0 = row A
@@ -84,7 +116,7 @@ __device__ __forceinline__ void process_block(const Tile<HD>& t, int kb, const u
             // matrices: keys kb+nt*8..+7 x dims ks*16+{0..7 | 8..15}; lanes 0-7 / 8-15 give the row addresses
             const int key = kb + nt * 8 + (lane & 7);
             const int dim = ks * 16 + ((lane >> 3) & 1) * 8;
-            ldsm_x2(b0, b1, smem_u32(&t.k[key][dim]));
+            ldsm_x2(b0, b1, smem_u32(t.k + key * Tile<HD>::PITCH + dim));
             mma16816(s[nt], qa[ks], b0, b1);
         }
     }
@@ -133,7 +165,7 @@ __device__ __forceinline__ void process_block(const Tile<HD>& t, int kb, const u
             uint32_t r0, r1, r2, r3;
             const int key = kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
             const int dim = nd * 8 + (lane >> 4) * 8;
-            ldsm_x4_trans(r0, r1, r2, r3, smem_u32(&t.v[key][dim]));
+            ldsm_x4_trans(r0, r1, r2, r3, smem_u32(t.v + key * Tile<HD>::PITCH + dim));
             mma16816(o[nd], pa, r0, r1);
             mma16816(o[nd + 1], pa, r2, r3);
         }
@@ -141,11 +173,19 @@ __device__ __forceinline__ void process_block(const Tile<HD>& t, int kb, const u
 }
 
 template <int HD>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 attn_mma_kernel(Params p) {
     const int g = blockIdx.y, h = blockIdx.x;
     if (p.n_groups_dev && g >= *p.n_groups_dev) return;
-    __shared__ __align__(16) Tile<HD> tile;
+    extern __shared__ __align__(16) uint8_t attn_smem[];
+    constexpr int PITCH = Tile<HD>::PITCH;
+    Tile<HD> tileA, tileB;
+    tileA.k = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+    tileA.v = tileA.k + KTA * PITCH;
+    tileB.k = tileA.v + KTA * PITCH;
+    tileB.v = tileB.k + KTB * PITCH;
+    tileA.bias = reinterpret_cast<float*>(tileB.v + KTB * PITCH);
+    tileB.bias = tileA.bias + KTA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kvg = p.spec ? p.active[g] : (p.kvmap ? p.kvmap[g] : g);
     const int dynLk = p.lk_dev ? *p.lk_dev : 0;
@@ -163,6 +203,37 @@ attn_mma_kernel(Params p) {
         const int wrow0 = blk0 + warp * ROWS_PER_WARP;       // first query row of this warp
         const bool warp_live = wrow0 < p.Lq;
         const int wrow_last = min(p.Lq, wrow0 + ROWS_PER_WARP) - 1;
+
+        // ---- staging (asynchronous; the Q fragments are fetched while the copies are in flight) ----
+        // phase A window [j0, j0 + KTA): keys shared by the whole group
+        const int kA_end = p.causal ? min(Lk, min(p.Lq, blk0 + ROWS_PER_CTA)) : Lk;
+        auto stage_A = [&](int j0) {
+            const int nk = min(KTA, kA_end - j0);
+            if (nk <= 0) return;
+            stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk);
+            const int nfill = (nk + 31) & ~31;
+            for (int j = threadIdx.x; j < nfill; j += THREADS)
+                tileA.bias[j] = (j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id)) ? 0.f : -INFINITY;
+        };
+        // phase B window [u0, u0 + KTB): freshly projected keys of the draft rows this CTA's queries belong to
+        const int RL = p.spec ? p.row_len : 1;
+        const int endB = p.spec ? min(p.Lq, blk0 + ROWS_PER_CTA) : 0;
+        const int firstB = (blk0 / RL) * RL;   // start of the draft row that contains the CTA's first query
+        const __nv_bfloat16* nkb = p.spec ? p.newk + (long long)g * p.Lq * p.new_ld + h * HD : nullptr;
+        const __nv_bfloat16* nvb = p.spec ? p.newv + (long long)g * p.Lq * p.new_ld + h * HD : nullptr;
+        auto stage_B = [&](int u0) {
+            const int nk = min(KTB, endB - u0);
+            if (nk <= 0) return;
+            stage_rows<HD>(tileB, nkb + (long long)u0 * p.new_ld, nvb + (long long)u0 * p.new_ld, p.new_ld, nk);
+            const int nfill = (nk + 31) & ~31;
+            for (int j = threadIdx.x; j < nfill; j += THREADS) {
+                const bool bad = j >= nk || (first_new_masked && ((u0 + j) % RL) == 0);
+                tileB.bias[j] = bad ? -INFINITY : 0.f;
+            }
+        };
+        stage_A(0);
+        if (p.spec) stage_B(firstB);
+
         uint32_t qa[2][HD / 16][4];
         float o[2][HD / 8][4];
         float m[2][2], l[2][2];
@@ -184,25 +255,18 @@ attn_mma_kernel(Params p) {
                 qa[mt][ks][3] = rowB < p.Lq ? *reinterpret_cast<const uint32_t*>(qB + d + 8) : 0u;
             }
         }
+        cp_async_wait_all();
+        __syncthreads();
 
-        // ---- phase A: keys shared by the whole group -----------------------------------------
-        const int kA_end = p.causal ? min(Lk, min(p.Lq, blk0 + ROWS_PER_CTA)) : Lk;
-        for (int j0 = 0; j0 < kA_end; j0 += KT) {
-            const int nk = min(KT, kA_end - j0);
-            constexpr int CH = HD / 8;  // 16-byte chunks per key row
-            for (int idx = threadIdx.x; idx < KT * CH; idx += THREADS) {
-                const int j = idx / CH, c = idx % CH;
-                uint4 kk4 = make_uint4(0, 0, 0, 0), vv4 = kk4;
-                if (j < nk) {
-                    kk4 = *reinterpret_cast<const uint4*>(kbase + (long long)(j0 + j) * p.kv_ld + c * 8);
-                    vv4 = *reinterpret_cast<const uint4*>(vbase + (long long)(j0 + j) * p.kv_ld + c * 8);
-                }
-                *reinterpret_cast<uint4*>(&tile.k[j][c * 8]) = kk4;
-                *reinterpret_cast<uint4*>(&tile.v[j][c * 8]) = vv4;
+        // ---- phase A ------------------------------------------------------------------------------
+        for (int j0 = 0; j0 < kA_end; j0 += KTA) {
+            if (j0 > 0) {   // sequences longer than one window (not reached by this model's shapes)
+                __syncthreads();
+                stage_A(j0);
+                cp_async_wait_all();
+                __syncthreads();
             }
-            for (int j = threadIdx.x; j < KT; j += THREADS)
-                tile.bias[j] = (j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id)) ? 0.f : -INFINITY;
-            __syncthreads();
+            const int nk = min(KTA, kA_end - j0);
             if (warp_live) {
 #pragma unroll 1
                 for (int kb = 0; kb < nk; kb += 32) {
@@ -212,41 +276,25 @@ attn_mma_kernel(Params p) {
                         const int rowA = wrow0 + mt * 16 + rA;
                         const int colbase = j0 + kb;
                         const int causal = p.causal;
-                        process_block<HD>(tile, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
+                        process_block<HD>(tileA, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
                                           [&](int rs, int col) { return causal && (colbase + col > rowA + rs * 8); });
                     }
                 }
             }
-            __syncthreads();
         }
 
-        // ---- phase B: private keys of the draft row (speculative self-attention) ---------------
+        // ---- phase B ------------------------------------------------------------------------------
         if (p.spec) {
-            const int RL = p.row_len;
             const int lo = warp_live ? (wrow0 / RL) * RL : 0;
             const int hi = warp_live ? min(p.Lq, (wrow_last / RL + 1) * RL) : 0;
-            const __nv_bfloat16* nkb = p.newk + (long long)g * p.Lq * p.new_ld + h * HD;
-            const __nv_bfloat16* nvb = p.newv + (long long)g * p.Lq * p.new_ld + h * HD;
-            const int first_needed = (blk0 / RL) * RL;  // start of the draft row that contains the CTA's first query
-            for (int u0 = (first_needed / KT) * KT; u0 < min(p.Lq, blk0 + ROWS_PER_CTA); u0 += KT) {
-                const int nk = min(KT, p.Lq - u0);
-                constexpr int CH = HD / 8;
-                for (int idx = threadIdx.x; idx < KT * CH; idx += THREADS) {
-                    const int j = idx / CH, c = idx % CH;
-                    uint4 kk4 = make_uint4(0, 0, 0, 0), vv4 = kk4;
-                    if (j < nk) {
-                        kk4 = *reinterpret_cast<const uint4*>(nkb + (long long)(u0 + j) * p.new_ld + c * 8);
-                        vv4 = *reinterpret_cast<const uint4*>(nvb + (long long)(u0 + j) * p.new_ld + c * 8);
-                    }
-                    *reinterpret_cast<uint4*>(&tile.k[j][c * 8]) = kk4;
-                    *reinterpret_cast<uint4*>(&tile.v[j][c * 8]) = vv4;
+            for (int u0 = firstB; u0 < endB; u0 += KTB) {
+                if (u0 > firstB) {
+                    __syncthreads();
+                    stage_B(u0);
+                    cp_async_wait_all();
+                    __syncthreads();
                 }
-                for (int j = threadIdx.x; j < KT; j += THREADS) {
-                    const int r = u0 + j;
-                    const bool bad = j >= nk || (first_new_masked && (r % RL) == 0);
-                    tile.bias[j] = bad ? -INFINITY : 0.f;
-                }
-                __syncthreads();
+                const int nk = min(KTB, endB - u0);
                 if (warp_live) {
 #pragma unroll 1
                     for (int kb = 0; kb < nk; kb += 32) {
@@ -257,7 +305,7 @@ attn_mma_kernel(Params p) {
                             const int rowA = wrow0 + mt * 16 + rA;
                             // a key row is visible iff it lies in the query's own draft row and not after it
                             const int startA = (rowA / RL) * RL, startB = ((rowA + 8) / RL) * RL;
-                            process_block<HD>(tile, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
+                            process_block<HD>(tileB, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
                                               [&](int rs, int col) {
                                                   const int qr = rowA + rs * 8, kr = u + col;
                                                   return kr < (rs ? startB : startA) || kr > qr;
@@ -265,7 +313,6 @@ attn_mma_kernel(Params p) {
                         }
                     }
                 }
-                __syncthreads();
             }
         }
 
@@ -298,9 +345,15 @@ attn_mma_kernel(Params p) {
 
 static void launch(const Params& p, int heads, int head_dim, int n_groups_max, cudaStream_t s) {
     dim3 grid(heads, n_groups_max, (p.Lq + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-    if (head_dim == 16) attn_mma_kernel<16><<<grid, THREADS, 0, s>>>(p);
-    else if (head_dim == 32) attn_mma_kernel<32><<<grid, THREADS, 0, s>>>(p);
-    else if (head_dim == 64) attn_mma_kernel<64><<<grid, THREADS, 0, s>>>(p);
+    static const bool attr_ok = [] {
+        return cudaFuncSetAttribute(attn_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>()) == cudaSuccess &&
+               cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32>()) == cudaSuccess &&
+               cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()) == cudaSuccess;
+    }();
+    (void)attr_ok;
+    if (head_dim == 16) attn_mma_kernel<16><<<grid, THREADS, smem_bytes<16>(), s>>>(p);
+    else if (head_dim == 32) attn_mma_kernel<32><<<grid, THREADS, smem_bytes<32>(), s>>>(p);
+    else if (head_dim == 64) attn_mma_kernel<64><<<grid, THREADS, smem_bytes<64>(), s>>>(p);
 }
 }  // namespace amma
 

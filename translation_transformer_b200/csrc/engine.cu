@@ -519,7 +519,6 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     st.gen = e->gen.as<int>(); st.front = e->front.as<int>(); st.active = e->active.as<int>(); st.ctrl = e->ctrl.as<int>();
     st.drafts = e->drafts.as<int>(); st.pred = e->pred.as<int>(); st.out = e->out64.as<long long>();
     st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break; st.hist = e->hist.as<int>();
-    st.plan_smem_offset = B + 32 * 64;   // finished flags + per-warp accepted-length scratch of the accept kernel
     { Scope sc(e, KC_MISC, s); launch_greedy_init(st, s); }
 
     float* x = e->x.as<float>();

@@ -19,8 +19,10 @@ namespace ttb {
 
 // ---- width plan of the coming iteration (speculative_decoding.py:93-102) -----------------------
 // Executed by one CTA after the live list is final.  `W` is the current width of the reference's
-// token matrix.
-__device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, int* s_tmp) {
+// token matrix.  `active` / `front` / `gen` may point to shared-memory copies of the state (accept
+// kernel) or to the global arrays (init kernel); `col_live` is [W] ints of shared scratch.
+__device__ void plan_next_iteration(const GreedyState& st, const int* active, const int* front, const int* gen,
+                                    int n_active, int W, int* s_tmp, int* col_live) {
     __syncthreads();
     if (threadIdx.x == 0) s_tmp[0] = 0, s_tmp[1] = 0;
     __syncthreads();
@@ -28,16 +30,13 @@ __device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, 
         if (threadIdx.x == 0) { st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
         return;
     }
-    // a column is dead when every live row holds PAD there; all (row, column) probes are independent
-    // loads (one round of memory latency instead of a serial scan per column)
-    extern __shared__ int s_plan_dyn[];
-    int* col_live = s_plan_dyn + st.plan_smem_offset;      // [W]
+    // a column is dead when every live row holds PAD there
     for (int c = threadIdx.x; c < W; c += blockDim.x) col_live[c] = 0;
     __syncthreads();
     for (int idx = threadIdx.x; idx < n_active * W; idx += blockDim.x) {
         const int g = idx / W, c = idx % W;
-        const int b = st.active[g];
-        if (c <= st.front[b] && st.gen[(long long)b * st.gen_ld + c] != st.pad) col_live[c] = 1;
+        const int b = active[g];
+        if (c <= front[b] && gen[(long long)b * st.gen_ld + c] != st.pad) col_live[c] = 1;
     }
     __syncthreads();
     int dead = 0;
@@ -47,7 +46,7 @@ __device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, 
     const int Wn = W + st.D + 1 - s_tmp[0];
     int oob = 0;
     for (int g = threadIdx.x; g < n_active; g += blockDim.x)
-        if (st.front[st.active[g]] + 1 + st.D > Wn - 1) oob = 1;
+        if (front[active[g]] + 1 + st.D > Wn - 1) oob = 1;
     if (oob) atomicOr(&s_tmp[1], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -59,6 +58,7 @@ __device__ void plan_next_iteration(const GreedyState& st, int n_active, int W, 
 
 __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     __shared__ int s_tmp[2];
+    extern __shared__ int s_init_dyn[];   // [gen_ld] column flags
     for (long long idx = threadIdx.x; idx < (long long)st.B * st.gen_ld; idx += blockDim.x)
         st.gen[idx] = (idx % st.gen_ld == 0) ? st.bos : st.pad;
     for (long long idx = threadIdx.x; idx < (long long)st.B * st.max_len; idx += blockDim.x) st.out[idx] = st.pad;
@@ -66,10 +66,10 @@ __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     if (threadIdx.x < CTRL_COUNT) st.ctrl[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) { st.ctrl[CTRL_N_ACTIVE] = st.B; st.ctrl[CTRL_LS] = st.Ls; }
-    plan_next_iteration(st, st.B, 1, s_tmp);
+    plan_next_iteration(st, st.active, st.front, st.gen, st.B, 1, s_tmp, s_init_dyn);
 }
 void launch_greedy_init(const GreedyState& st, cudaStream_t s) {
-    greedy_init_kernel<<<1, 256, (size_t)(st.plan_smem_offset + st.gen_ld) * sizeof(int), s>>>(st);
+    greedy_init_kernel<<<1, 256, (size_t)st.gen_ld * sizeof(int), s>>>(st);
 }
 
 // ---- step-token embedding ---------------------------------------------------------------------
@@ -105,42 +105,59 @@ template void launch_greedy_embed<__nv_bfloat16>(const GreedyState&, const float
 // One CTA, one warp per live query: lanes score the drafts in parallel (accepted length = leading
 // matches between draft tokens and the predictions one position earlier), lane 0 applies the
 // tie-break rule, the warp appends the tokens and retires the query if it produced EOS.
-__global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
+// The whole bookkeeping state (live list, fronts, token matrix) is copied to shared memory with one
+// round of independent loads at kernel entry, so the dependent chains (live list -> front -> tokens,
+// compaction, dead-column scan) never wait on global memory; updates are written through.
+constexpr int ACCEPT_MAX_SMEM_INTS = 50 * 1024;   // token matrices larger than 200 KB stay in global memory
+
+__global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int stage_gen) {
     __shared__ int s_tmp[2];
     __shared__ int s_acc, s_tok, s_err;
-    extern __shared__ int s_dyn[];  // [B] finished flags, then [warps][64] accepted lengths
-    if (st.ctrl[CTRL_DONE]) return;
+    extern __shared__ int s_dyn[];
+    const int B = st.B, D = st.D, N = st.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    int* s_active = s_dyn;                       // [B]
+    int* s_front = s_active + B;                 // [B]
+    int* s_fin = s_front + B;                    // [B]
+    int* s_newact = s_fin + B;                   // [B]
+    int* s_nacc_all = s_newact + B;              // [warps][64]
+    int* col_live = s_nacc_all + n_warps * 64;   // [gen_ld]
+    int* s_gen = col_live + st.gen_ld;           // [B][gen_ld] when stage_gen
+    int* s_nacc = s_nacc_all + warp * 64;
+    // ---- round 1: independent loads --------------------------------------------------------------
+    const int done = st.ctrl[CTRL_DONE];
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
     const int Wn = st.ctrl[CTRL_WIDTH];
     const int iter = st.ctrl[CTRL_ITERS];
-    const int D = st.D, N = st.N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    int* s_fin = s_dyn;
-    int* s_nacc = s_dyn + st.B + warp * 64;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) { s_active[b] = st.active[b]; s_front[b] = st.front[b]; }
+    if (stage_gen)
+        for (int idx = threadIdx.x; idx < B * st.gen_ld; idx += blockDim.x) s_gen[idx] = st.gen[idx];
+    if (done) return;
+    int* G = stage_gen ? s_gen : st.gen;
     if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; if (st.hist) st.hist[iter] = n_active; }
     __syncthreads();
     for (int g = warp; g < n_active; g += n_warps) {
-        const int b = st.active[g];
-        const int f = st.front[b];
+        const int b = s_active[g];
+        const int f = s_front[b];
         int best_val = -1, best_first = 0x7fffffff;
         for (int n = lane; n < N; n += 32) {
             const int* pr = st.pred + ((long long)g * N + n) * (D + 1);
             const int* dr = st.drafts + ((long long)b * N + n) * D;
             int a = 0;
             bool open = true;
-            for (int a0 = 0; a0 < D && open; a0 += 8) {          // 8 independent loads per round
-                int dv[8], pv[8];
+            for (int a0 = 0; a0 < D && open; a0 += 16) {         // 32 independent loads per round
+                int dv[16], pv[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     dv[u] = (a0 + u < D) ? dr[a0 + u] : -1;
                     pv[u] = (a0 + u < D) ? pr[a0 + u] : -2;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     if (open && dv[u] == pv[u]) ++a; else open = false;
                 }
             }
-            if (n < 64) s_nacc[n] = a;
+            if (n < 64) s_nacc[n] = (a << 8) | n;   // packed for the tie-break emulation
             if (a > best_val) { best_val = a; best_first = n; }
         }
 #pragma unroll
@@ -150,22 +167,32 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
         }
         __syncwarp();
         int pick = best_first;
-        if (st.tie_break == 0 && N < 64) {
-            if (lane == 0) pick = topk1_torch_cpu(s_nacc, N);
-            pick = __shfl_sync(0xffffffffu, pick, 0);
+        if (st.tie_break == 0 && N < 64 && N > 1) {
+            // a unique maximum is the answer of any selection algorithm; only ties need the emulation
+            int ties = 0;
+            for (int n = lane; n < N; n += 32) ties += ((s_nacc[n] >> 8) == best_val) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
+            if (ties > 1) {
+                if (lane == 0) pick = topk1_torch_cpu_packed(s_nacc, N);
+                pick = __shfl_sync(0xffffffffu, pick, 0);
+            }
         }
         const int a = best_val;
         const int* pr = st.pred + ((long long)g * N + pick) * (D + 1);
-        int* row = st.gen + (long long)b * st.gen_ld;
+        int* row = G + (long long)b * st.gen_ld;
+        int* grow = st.gen + (long long)b * st.gen_ld;
         bool fin_l = false;
         for (int j = lane; j <= D; j += 32) {
             const int t = (j <= a) ? pr[j] : st.pad;
             row[f + 1 + j] = t;
+            if (stage_gen) grow[f + 1 + j] = t;
             fin_l |= (j <= a) && (t == st.eos);
         }
         const bool fin = __any_sync(0xffffffffu, fin_l);
         __syncwarp();
         if (lane == 0) {
+            s_front[b] = f + a + 1;
             st.front[b] = f + a + 1;
             st.sel[g * 4 + 0] = b; st.sel[g * 4 + 1] = f; st.sel[g * 4 + 2] = pick; st.sel[g * 4 + 3] = a;
             if (st.trace) {
@@ -183,26 +210,48 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // order-preserving compaction of the live list (boolean masking in the reference): warp 0, ballot prefix sums
+    if (warp == 0) {
         int w = 0;
-        for (int g = 0; g < n_active; ++g)
-            if (!s_fin[g]) st.active[w++] = st.active[g];
-        st.ctrl[CTRL_N_SEL] = n_active;
-        st.ctrl[CTRL_N_ACTIVE] = w;
-        st.ctrl[CTRL_ITERS] = iter + 1;
-        st.ctrl[CTRL_ACCEPTED] += s_acc;
-        st.ctrl[CTRL_TOKENS] += s_tok;
-        if (s_err) { st.ctrl[CTRL_ERROR] = s_err; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = w; st.ctrl[CTRL_N_ACTIVE] = 0; }
-        s_tmp[0] = w;
+        for (int g0 = 0; g0 < n_active; g0 += 32) {
+            const int g = g0 + lane;
+            const bool alive = g < n_active && !s_fin[g];
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (alive) {
+                const int pos = w + __popc(m & ((1u << lane) - 1u));
+                const int b = s_active[g];
+                s_newact[pos] = b;
+                st.active[pos] = b;
+            }
+            w += __popc(m);
+        }
+        if (lane == 0) {
+            st.ctrl[CTRL_N_SEL] = n_active;
+            st.ctrl[CTRL_N_ACTIVE] = w;
+            st.ctrl[CTRL_ITERS] = iter + 1;
+            st.ctrl[CTRL_ACCEPTED] += s_acc;
+            st.ctrl[CTRL_TOKENS] += s_tok;
+            if (s_err) { st.ctrl[CTRL_ERROR] = s_err; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = w; st.ctrl[CTRL_N_ACTIVE] = 0; }
+            s_tmp[0] = w;
+        }
     }
     __syncthreads();
     if (s_err) return;
     const int n_left = s_tmp[0];
-    plan_next_iteration(st, n_left, Wn, s_tmp);
+    plan_next_iteration(st, s_newact, s_front, G, n_left, Wn, s_tmp, col_live);
 }
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     const int warps = st.B < 32 ? (st.B < 4 ? 4 : st.B) : 32;
-    greedy_accept_kernel<<<1, warps * 32, ((size_t)st.plan_smem_offset + st.gen_ld) * sizeof(int), s>>>(st);
+    const size_t base_ints = (size_t)4 * st.B + (size_t)warps * 64 + st.gen_ld;
+    const size_t gen_ints = (size_t)st.B * st.gen_ld;
+    const int stage_gen = base_ints + gen_ints <= (size_t)ACCEPT_MAX_SMEM_INTS ? 1 : 0;
+    const size_t smem = (base_ints + (stage_gen ? gen_ints : 0)) * sizeof(int);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaFuncSetAttribute(greedy_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ACCEPT_MAX_SMEM_INTS * sizeof(int)));
+        attr_smem = ACCEPT_MAX_SMEM_INTS * sizeof(int);
+    }
+    greedy_accept_kernel<<<1, warps * 32, smem, s>>>(st, stage_gen);
 }
 
 // ---- KV-cache append ------------------------------------------------------------------------------

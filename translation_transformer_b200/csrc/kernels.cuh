@@ -97,7 +97,6 @@ struct GreedyState {
     int* trace;        // optional [max_len][B][4] = {query id, n_accepted, draft index, width}
     int tie_break;     // 0 = torch-CPU topk(1) emulation, 1 = lowest index
     int* hist;         // [max_len + 2] live queries at the start of every iteration
-    int plan_smem_offset;  // ints of dynamic shared memory used by the accept kernel before the column flags
 };
 void launch_greedy_init(const GreedyState& st, cudaStream_t s);
 // embeds the (D+1) step tokens of every live draft row

@@ -7,9 +7,12 @@ namespace ttb {
 // ---- torch CPU topk(1) tie-break: libstdc++ introselect on (value, index) pairs -------------
 struct VI { int v; int i; };
 __device__ __forceinline__ bool gt(const VI& a, const VI& b) { return a.v > b.v; }
-__device__ __forceinline__ void swp(VI& a, VI& b) { VI t = a; a = b; b = t; }
+// (value << 8 | index) in one word: half the memory operations of VI; for n < 64 and small values
+struct PK { int x; };
+__device__ __forceinline__ bool gt(const PK& a, const PK& b) { return (a.x >> 8) > (b.x >> 8); }
+template <typename VI> __device__ __forceinline__ void swp(VI& a, VI& b) { VI t = a; a = b; b = t; }
 
-__device__ inline void push_heap_(VI* e, int first, int hole, int top, VI val) {
+template <typename VI> __device__ inline void push_heap_(VI* e, int first, int hole, int top, VI val) {
     int parent = (hole - 1) / 2;
     while (hole > top && gt(e[first + parent], val)) {
         e[first + hole] = e[first + parent];
@@ -18,7 +21,7 @@ __device__ inline void push_heap_(VI* e, int first, int hole, int top, VI val) {
     }
     e[first + hole] = val;
 }
-__device__ inline void adjust_heap_(VI* e, int first, int hole, int len, VI val) {
+template <typename VI> __device__ inline void adjust_heap_(VI* e, int first, int hole, int len, VI val) {
     const int top = hole;
     int child = hole;
     while (child < (len - 1) / 2) {
@@ -34,7 +37,7 @@ __device__ inline void adjust_heap_(VI* e, int first, int hole, int len, VI val)
     }
     push_heap_(e, first, hole, top, val);
 }
-__device__ inline void heap_select_(VI* e, int first, int middle, int last) {
+template <typename VI> __device__ inline void heap_select_(VI* e, int first, int middle, int last) {
     const int len = middle - first;
     if (len >= 2) {
         int parent = (len - 2) / 2;
@@ -52,15 +55,9 @@ __device__ inline void heap_select_(VI* e, int first, int middle, int last) {
         }
     }
 }
-// index torch.topk(vals, 1) returns on the CPU backend (n < 64: std::nth_element, else partial_sort)
-__device__ inline int topk1_torch_cpu(const int* vals, int n) {
-    if (n >= 64 || n <= 1) {
-        int best = 0;
-        for (int j = 1; j < n; ++j) if (vals[j] > vals[best]) best = j;
-        return best;
-    }
-    VI e[64];
-    for (int j = 0; j < n; ++j) { e[j].v = vals[j]; e[j].i = j; }
+// libstdc++ std::nth_element(e, e + 0, e + n, gt) (introselect); the winner ends up in e[0]
+template <typename VI>
+__device__ inline void nth_element0_(VI* e, int n) {
     int first = 0, last = n;
     const int nth = 0;
     int depth = 2 * (31 - __clz(n));
@@ -68,7 +65,7 @@ __device__ inline int topk1_torch_cpu(const int* vals, int n) {
         if (depth == 0) {
             heap_select_(e, first, nth + 1, last);
             swp(e[first], e[nth]);
-            return e[nth].i;
+            return;
         }
         --depth;
         const int mid = first + (last - first) / 2;
@@ -104,8 +101,26 @@ __device__ inline int topk1_torch_cpu(const int* vals, int n) {
             e[j] = val;
         }
     }
-    return e[nth].i;
 }
+
+// index torch.topk(vals, 1) returns on the CPU backend (n < 64: std::nth_element, else partial_sort)
+__device__ inline int topk1_torch_cpu(const int* vals, int n) {
+    if (n >= 64 || n <= 1) {
+        int best = 0;
+        for (int j = 1; j < n; ++j) if (vals[j] > vals[best]) best = j;
+        return best;
+    }
+    VI e[64];
+    for (int j = 0; j < n; ++j) { e[j].v = vals[j]; e[j].i = j; }
+    nth_element0_(e, n);
+    return e[0].i;
+}
+// same on a shared-memory array that already holds (value << 8 | index) words, 1 < n < 64 (clobbers it)
+__device__ inline int topk1_torch_cpu_packed(int* packed, int n) {
+    nth_element0_(reinterpret_cast<PK*>(packed), n);
+    return packed[0] & 0xff;
+}
+
 
 
 }  // namespace ttb

@@ -262,6 +262,32 @@ static int linear(ttb_engine* e, int kc, const __nv_bfloat16* A, int lda, const 
     return launch_gemm_bf16_tc<OutT>(A, lda, L.wh, L.b, C, ldc, rows, L.N, L.K, relu, s);
 }
 
+// Sub-layer tail  x <- LN2?(LN1(x + A W^T + b)):  one fused tcgen05 kernel on the bf16 path with E = 256,
+// GEMM (fp32 out) + add_layernorm otherwise.  TTB_NO_FUSED_LN=1 forces the unfused kernels (A/B comparisons).
+static bool fused_ln_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TTB_NO_FUSED_LN"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+static int linear_resid_ln(ttb_engine* e, int kc, const float* A, int lda, const Lin& L, const Norm& n1, const Norm* n2,
+                           float* x, float* /*xh*/, float* y, float* dst, float* dsth, RowCount rows, cudaStream_t s) {
+    if (linear<float>(e, kc, A, lda, L, y, L.N, rows, false, s)) return 1;
+    Scope sc(e, KC_LAYERNORM, s);
+    launch_add_layernorm<float>(x, y, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, dst, dsth, rows, L.N, s);
+    return 0;
+}
+static int linear_resid_ln(ttb_engine* e, int kc, const __nv_bfloat16* A, int lda, const Lin& L, const Norm& n1, const Norm* n2,
+                           float* x, __nv_bfloat16* xh, float* y, float* dst, __nv_bfloat16* dsth, RowCount rows, cudaStream_t s) {
+    if (L.N == 256 && dst == x && dsth == xh && fused_ln_enabled()) {
+        Scope sc(e, kc, s);
+        return launch_gemm_resid_ln(A, lda, L.wh, L.b, x, xh, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, rows, L.K, s);
+    }
+    if (linear<float>(e, kc, A, lda, L, y, L.N, rows, false, s)) return 1;
+    Scope sc(e, KC_LAYERNORM, s);
+    launch_add_layernorm<__nv_bfloat16>(x, y, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, dst, dsth, rows, L.N, s);
+    return 0;
+}
+
 // Attention dispatch: fp32 path -> SIMT kernels (exact), bf16 path -> tensor-core kernels
 // (TTB_ATTN_SIMT=1 forces the SIMT kernels for A/B comparisons).
 static bool attn_simt_forced() {
@@ -343,17 +369,11 @@ static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int 
             attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, nullptr, Ls, Ls, Ls, nullptr,
                                    key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
         }
-        if (linear<float>(e, KC_ENCODER, att, E, L.out_proj, y, E, rows, false, s)) return 1;
-        { Scope sc(e, KC_ENCODER, s); launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear_resid_ln(e, KC_ENCODER, att, E, L.out_proj, L.n1, nullptr, x, xh, y, x, xh, rows, s)) return 1;
         if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
-        if (linear<float>(e, KC_ENCODER, hid, F, L.ff2, y, E, rows, false, s)) return 1;
         float* dst = last ? mem_out : x;
         ActT* dsth = last ? memh_out : xh;
-        {
-            Scope sc(e, KC_ENCODER, s);
-            launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, last ? e->enc_norm.g : nullptr, last ? e->enc_norm.b : nullptr,
-                                       dst, dsth, rows, E, s);
-        }
+        if (linear_resid_ln(e, KC_ENCODER, hid, F, L.ff2, L.n2, last ? &e->enc_norm : nullptr, x, xh, y, dst, dsth, rows, s)) return 1;
     }
     return 0;
 }
@@ -391,19 +411,12 @@ static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long
         ActT* qkv = e->qkv.as<ActT>() + (qkv_layers > 1 ? (long long)l * qkv_layer_stride : 0);
         if (linear<ActT>(e, KC_GEMM_QKV, a_view<ActT>(x, xh), E, L.self_in, qkv, 3 * E, rows, false, s)) return 1;
         { Scope sc(e, KC_SELF_ATTN, s); self_attn(l, qkv, att); }
-        if (linear<float>(e, KC_GEMM_SELF_OUT, att, E, L.self_out, y, E, rows, false, s)) return 1;
-        { Scope sc(e, KC_LAYERNORM, s); launch_add_layernorm<ActT>(x, y, L.n1.g, L.n1.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear_resid_ln(e, KC_GEMM_SELF_OUT, att, E, L.self_out, L.n1, nullptr, x, xh, y, x, xh, rows, s)) return 1;
         if (linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
         { Scope sc(e, KC_CROSS_ATTN, s); cross_attn(l, q2, att); }
-        if (linear<float>(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, y, E, rows, false, s)) return 1;
-        { Scope sc(e, KC_LAYERNORM, s); launch_add_layernorm<ActT>(x, y, L.n2.g, L.n2.b, nullptr, nullptr, x, xh, rows, E, s); }
+        if (linear_resid_ln(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, L.n2, nullptr, x, xh, y, x, xh, rows, s)) return 1;
         if (linear<ActT>(e, KC_GEMM_FFN1, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
-        if (linear<float>(e, KC_GEMM_FFN2, hid, F, L.ff2, y, E, rows, false, s)) return 1;
-        {
-            Scope sc(e, KC_LAYERNORM, s);
-            launch_add_layernorm<ActT>(x, y, L.n3.g, L.n3.b, last ? e->dec_norm.g : nullptr, last ? e->dec_norm.b : nullptr,
-                                       x, xh, rows, E, s);
-        }
+        if (linear_resid_ln(e, KC_GEMM_FFN2, hid, F, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, y, x, xh, rows, s)) return 1;
     }
     return 0;
 }

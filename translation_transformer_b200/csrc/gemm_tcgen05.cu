@@ -466,13 +466,14 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = box_rows x 64, 128-byte swizzle
-static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-    using Key = std::tuple<const void*, int, int, int, int>;
+// 2-D tensor [rows, cols] with row stride ld (elements); box = box_rows x 128 bytes (64 bf16 or 32 fp32
+// elements), 128-byte swizzle
+static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, bool f32 = false) {
+    using Key = std::tuple<const void*, int, int, int, int, bool>;
     static std::map<Key, CUtensorMap> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    Key key{ptr, rows, cols, ld, box_rows};
+    Key key{ptr, rows, cols, ld, box_rows, f32};
     auto it = cache.find(key);
     if (it != cache.end()) {
         *out = it->second;
@@ -484,12 +485,13 @@ static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_r
         return 4;
     }
     CUtensorMap m;
+    const int esz = f32 ? 4 : 2;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows=" + std::to_string(rows) +
@@ -500,6 +502,263 @@ static int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_r
     cache[key] = m;
     *out = m;
     return 0;
+}
+
+// =====================================================================================================
+// GEMM + bias + residual + LayerNorm (+ optional second LayerNorm) for E = 256 rows:
+//     x <- LN2?( LN1( x + A W^T + bias ) ),  written as fp32 (x, in place) and bf16 (xh)
+// One cluster of two CTAs per 128-row tile; CTA r owns output columns [128 r, 128 r + 128):
+//   warp 0      TMA producer: K-blocks of A (128 x 64) and of the CTA's W slice (128 x 64) into a 4-stage ring,
+//               plus the fp32 residual tile (four 128 x 32 boxes, 128-byte swizzle)
+//   warp 1      tcgen05.mma issuer, 128 x 128 fp32 accumulator in TMEM
+//   warps 2..9  epilogue: one thread per (row, 64-column half).  tcgen05.ld -> + bias + residual (swizzled
+//               shared-memory reads are conflict-free for a row-per-lane pattern) -> local mean / M2 ->
+//               the four partial statistics of a row (2 CTAs x 2 halves) are exchanged through
+//               distributed shared memory + one cluster barrier and combined with Chan's formula ->
+//               normalise -> write fp32 / bf16 tiles back into swizzled shared memory -> TMA stores.
+// The LayerNorm kernels, the fp32 GEMM output round trip through HBM/L2 and one launch per
+// sub-layer disappear.
+namespace lnk {
+constexpr int NST = 4;
+constexpr int BNL = 128;                               // output columns per CTA
+constexpr int STAGE = A_BYTES + BNL * BK * 2;          // 32 KB
+constexpr int RESID_BYTES = BM * BNL * 4;              // 64 KB
+constexpr int PART_BYTES = 4 * BM * 8;                 // float2[4][128]
+constexpr int PARAM_FLOATS = 5 * BNL;                  // bias, g1, b1, g2, b2 slices
+constexpr int THREADS = 320;
+constexpr int SMEM = NST * STAGE + RESID_BYTES + 2 * PART_BYTES + PARAM_FLOATS * 4 + 256 + 1024;
+}  // namespace lnk
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer_rank, float a, float b) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer_rank));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(lnk::THREADS, 1)
+gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXh,
+                     const float* __restrict__ bias, const float* __restrict__ g1, const float* __restrict__ b1,
+                     const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int K) {
+    using namespace lnk;
+    const int M = rows.live();
+    const int m0 = (blockIdx.x >> 1) * BM;
+    if (m0 >= M) return;   // uniform per cluster, before any barrier / TMEM allocation
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int n0 = (int)rank * BNL;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    uint8_t* resid_sm = gen_base + NST * STAGE;
+    const uint32_t resid_u32 = base + NST * STAGE;
+    float2* part1 = reinterpret_cast<float2*>(resid_sm + RESID_BYTES);
+    float2* part2 = part1 + 4 * BM;
+    float* prm = reinterpret_cast<float*>(part2 + 4 * BM);
+    const uint32_t bar_base = base + NST * STAGE + RESID_BYTES + 2 * PART_BYTES + PARAM_FLOATS * 4;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * NST);
+    const uint32_t resid_bar = bar_base + 8u * (2 * NST + 1);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (bar_base - base) + 8 * (2 * NST + 2));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXh)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            mbar_init(tfull_bar, 1);
+            mbar_init(resid_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)BNL) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {   // parameter slices of this CTA's columns
+        const int t = threadIdx.x - 64;
+        if (t < BNL) {
+            prm[t] = bias ? __ldg(bias + n0 + t) : 0.f;
+            prm[BNL + t] = __ldg(g1 + n0 + t);
+            prm[2 * BNL + t] = __ldg(b1 + n0 + t);
+            prm[3 * BNL + t] = g2 ? __ldg(g2 + n0 + t) : 1.f;
+            prm[4 * BNL + t] = g2 ? __ldg(b2 + n0 + t) : 0.f;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // phase 0 of the cluster barrier: "this CTA is running" (its shared memory may be written by the peer);
+    // the matching wait sits right before the first remote store
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), STAGE);
+                const uint32_t a_dst = base + s * STAGE, b_dst = a_dst + A_BYTES;
+                tma_load_2d(a_dst, &tmA, kb * BK, m0, full_bar(s));
+                tma_load_2d(b_dst, &tmB, kb * BK, n0, full_bar(s));
+                if (kb == (KB < NST ? KB : NST) - 1) {   // residual tile: queued behind the first ring fill
+                    mbar_expect_tx(resid_bar, RESID_BYTES);
+                    for (int bx = 0; bx < 4; ++bx) tma_load_2d(resid_u32 + bx * (BM * 128), &tmX, n0 + 32 * bx, m0, resid_bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BNL);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t a_src = base + s * STAGE, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(a_src + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(b_src + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tfull_bar);
+        }
+    }
+
+    // ===== epilogue (warps 2..9); warps 0/1 only take part in the cluster barriers =====
+    const bool epi = warp >= 2;
+    const int q = warp & 3;
+    const int h = epi ? ((warp - 2) >> 2) : 0;
+    const int row = q * 32 + lane;
+    const int swz = row & 7;
+    const int pidx = (int)rank * 2 + h;
+    float v[64];
+    auto local_stats = [&](float& mean, float& m2) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s += v[j];
+        mean = s * (1.0f / 64.0f);
+        float qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qq += d * d; }
+        m2 = qq;
+    };
+    auto publish = [&](float2* part, float mean, float m2) {
+        part[pidx * BM + row] = make_float2(mean, m2);
+        st_peer_f32x2(smem_u32(&part[pidx * BM + row]), rank ^ 1u, mean, m2);
+    };
+    auto normalise = [&](const float2* part, const float* gg, const float* bb) {
+        // Chan's combination of four equally sized groups (64 values each)
+        const float2 p0 = part[row], p1 = part[BM + row], p2 = part[2 * BM + row], p3 = part[3 * BM + row];
+        const float mean = 0.25f * (p0.x + p1.x + p2.x + p3.x);
+        const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+        const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+        const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd * gg[h * 64 + j] + bb[h * 64 + j];
+    };
+
+    if (epi) {
+        mbar_wait(tfull_bar, 0);
+        tcgen05_fence_after();
+        mbar_wait(resid_bar, 0);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64 + c0), r);
+            const uint8_t* box = resid_sm + (2 * h + c0 / 32) * (BM * 128) + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
+                const int j = c0 + 4 * c;
+                v[j + 0] = __uint_as_float(r[4 * c + 0]) + prm[h * 64 + j + 0] + rv.x;
+                v[j + 1] = __uint_as_float(r[4 * c + 1]) + prm[h * 64 + j + 1] + rv.y;
+                v[j + 2] = __uint_as_float(r[4 * c + 2]) + prm[h * 64 + j + 2] + rv.z;
+                v[j + 3] = __uint_as_float(r[4 * c + 3]) + prm[h * 64 + j + 3] + rv.w;
+            }
+        }
+        float mean, m2;
+        local_stats(mean, m2);
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // phase 0: the peer is running
+        publish(part1, mean, m2);
+    } else {
+        __syncwarp();
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    __syncwarp();
+    cluster_sync_all();
+    if (epi) normalise(part1, prm + BNL, prm + 2 * BNL);
+    if (g2) {   // final LayerNorm of the stack on top (uniform branch)
+        if (epi) {
+            float mean, m2;
+            local_stats(mean, m2);
+            publish(part2, mean, m2);
+        }
+        __syncwarp();
+        cluster_sync_all();
+        if (epi) normalise(part2, prm + 3 * BNL, prm + 4 * BNL);
+    }
+    if (epi) {
+        // fp32 tile back into the residual boxes (in place), bf16 tile into the idle ring (stage 0)
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint8_t* box = resid_sm + (2 * h + c0 / 32) * (BM * 128) + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = c0 + 4 * c;
+                *reinterpret_cast<float4*>(box + ((c ^ swz) << 4)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        uint8_t* hbox = gen_base + h * (BM * 128) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * c + 0], v[8 * c + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2);
+            u.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(hbox + ((c ^ swz) << 4)) = u;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+            for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, resid_u32 + bx * (BM * 128), n0 + 32 * bx, m0);
+            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + hb * (BM * 128), n0 + 64 * hb, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BNL) : "memory");
+    }
 }
 }  // namespace tc
 
@@ -555,6 +814,34 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     gemm_bf16_tc_kernel<OutT><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
     return 0;
 }
+int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
+                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s) {
+    using namespace tc;
+    if (rows.max_rows <= 0) return 0;
+    if (K % BK != 0 || lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
+        (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(xh) & 15)) {
+        set_last_error("fused GEMM+LayerNorm needs K % 64 == 0, lda % 8 == 0 and 16-byte aligned operands");
+        return 4;
+    }
+    CUtensorMap tmA, tmB, tmX, tmXh;
+    if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
+    if (int rc = get_tensor_map(W, 256, K, K, lnk::BNL, &tmB)) return rc;
+    if (int rc = get_tensor_map(x, rows.max_rows, 256, 256, BM, &tmX, true)) return rc;
+    if (int rc = get_tensor_map(xh, rows.max_rows, 256, 256, BM, &tmXh)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_resid_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lnk::SMEM);
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    const int tiles = (rows.max_rows + BM - 1) / BM;
+    gemm_resid_ln_kernel<<<2 * tiles, lnk::THREADS, lnk::SMEM, s>>>(tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K);
+    return 0;
+}
+
 template int launch_gemm_bf16_tc<float>(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, float*, int, RowCount, int, int, bool, cudaStream_t);
 template int launch_gemm_bf16_tc<__nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, RowCount, int, int, bool, cudaStream_t);
 

@@ -42,6 +42,11 @@ template <typename OutT>
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias,
                         OutT* C, int ldc, RowCount rows, int N, int K, bool relu, cudaStream_t s);
 
+// Fused sub-layer tail for embedding_dim 256 (bf16 path):  x <- LN2?(LN1(x + A W^T + bias)), x fp32 updated in
+// place, xh = bf16 copy.  W is [256, K] bf16; g2/b2 = nullptr without the second LayerNorm.
+int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
+                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s);
+
 // ---- attention.cu ---------------------------------------------------------------------------
 // Generic masked attention over "groups".  Queries of group g are tokens g*Lq .. g*Lq+Lq-1 of
 // `q`; its keys/values are rows kv_row0 .. kv_row0+Lk-1 with kv_row0 = (kvmap ? kvmap[g] : g) *

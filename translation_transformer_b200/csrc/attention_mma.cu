@@ -39,6 +39,17 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                  : "r"(addr));
 }
+__device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: exact 0 for -inf, 1 for 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+struct NoMask { __device__ __forceinline__ bool operator()(int, int) const { return false; } };
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&p);
@@ -110,14 +121,24 @@ __device__ __forceinline__ void process_block(const Tile<HD>& t, int kb, const u
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        // matrices: keys kb+nt*8..+7 x dims {0..7 | 8..15 | 16..23 | 24..31} (+32 per x4): lanes 8m..8m+7 give
+        // the row addresses of matrix m, so one ldmatrix.x4 feeds two k16 steps
+        const int key = kb + nt * 8 + (lane & 7);
+        if constexpr (HD % 32 == 0) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-            uint32_t b0, b1;
-            // matrices: keys kb+nt*8..+7 x dims ks*16+{0..7 | 8..15}; lanes 0-7 / 8-15 give the row addresses
-            const int key = kb + nt * 8 + (lane & 7);
-            const int dim = ks * 16 + ((lane >> 3) & 1) * 8;
-            ldsm_x2(b0, b1, smem_u32(t.k + key * Tile<HD>::PITCH + dim));
-            mma16816(s[nt], qa[ks], b0, b1);
+            for (int kp = 0; kp < HD / 32; ++kp) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(b0, b1, b2, b3, smem_u32(t.k + key * Tile<HD>::PITCH + kp * 32 + (lane >> 3) * 8));
+                mma16816(s[nt], qa[2 * kp], b0, b1);
+                mma16816(s[nt], qa[2 * kp + 1], b2, b3);
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks) {
+                uint32_t b0, b1;
+                ldsm_x2(b0, b1, smem_u32(t.k + key * Tile<HD>::PITCH + ks * 16 + ((lane >> 3) & 1) * 8));
+                mma16816(s[nt], qa[ks], b0, b1);
+            }
         }
     }
     const int c0 = (lane & 3) * 2;
@@ -139,13 +160,13 @@ __device__ __forceinline__ void process_block(const Tile<HD>& t, int kb, const u
     mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
     const float nA = fmaxf(mA, mxA), nB = fmaxf(mB, mxB);
     const float uA = (nA == -INFINITY) ? 0.f : nA, uB = (nB == -INFINITY) ? 0.f : nB;
-    const float cA = exp2f(mA - uA), cB = exp2f(mB - uB);   // m = -inf -> 0
+    const float cA = fast_exp2(mA - uA), cB = fast_exp2(mB - uB);   // m = -inf -> 0
     mA = nA; mB = nB;
     float sumA = 0.f, sumB = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] - uA); s[nt][1] = exp2f(s[nt][1] - uA);
-        s[nt][2] = exp2f(s[nt][2] - uB); s[nt][3] = exp2f(s[nt][3] - uB);
+        s[nt][0] = fast_exp2(s[nt][0] - uA); s[nt][1] = fast_exp2(s[nt][1] - uA);
+        s[nt][2] = fast_exp2(s[nt][2] - uB); s[nt][3] = fast_exp2(s[nt][3] - uB);
         sumA += s[nt][0] + s[nt][1];
         sumB += s[nt][2] + s[nt][3];
     }
@@ -176,6 +197,8 @@ template <int HD>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_mma_kernel(Params p) {
     const int g = blockIdx.y, h = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.n_groups_dev && g >= *p.n_groups_dev) return;
     extern __shared__ __align__(16) uint8_t attn_smem[];
     constexpr int PITCH = Tile<HD>::PITCH;
@@ -207,13 +230,22 @@ attn_mma_kernel(Params p) {
         // ---- staging (asynchronous; the Q fragments are fetched while the copies are in flight) ----
         // phase A window [j0, j0 + KTA): keys shared by the whole group
         const int kA_end = p.causal ? min(Lk, min(p.Lq, blk0 + ROWS_PER_CTA)) : Lk;
+        // keys behind the last unmasked one (source padding) contribute exactly nothing: s_last_key bounds the scan
+        __shared__ int s_last_key;
+        if (threadIdx.x == 0) s_last_key = 0;
+        __syncthreads();
         auto stage_A = [&](int j0) {
             const int nk = min(KTA, kA_end - j0);
             if (nk <= 0) return;
             stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk);
             const int nfill = (nk + 31) & ~31;
-            for (int j = threadIdx.x; j < nfill; j += THREADS)
-                tileA.bias[j] = (j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id)) ? 0.f : -INFINITY;
+            int last = 0;
+            for (int j = threadIdx.x; j < nfill; j += THREADS) {
+                const bool ok = j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id);
+                tileA.bias[j] = ok ? 0.f : -INFINITY;
+                if (ok) last = j0 + j + 1;
+            }
+            if (last) atomicMax(&s_last_key, last);
         };
         // phase B window [u0, u0 + KTB): freshly projected keys of the draft rows this CTA's queries belong to
         const int RL = p.spec ? p.row_len : 1;
@@ -266,18 +298,23 @@ attn_mma_kernel(Params p) {
                 cp_async_wait_all();
                 __syncthreads();
             }
-            const int nk = min(KTA, kA_end - j0);
+            const int nk = min(min(KTA, kA_end - j0), s_last_key - j0);
             if (warp_live) {
 #pragma unroll 1
                 for (int kb = 0; kb < nk; kb += 32) {
-                    if (p.causal && j0 + kb > wrow_last) break;
+                    if (p.causal) {
+                        if (j0 + kb > wrow_last) break;
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const int rowA = wrow0 + mt * 16 + rA;
-                        const int colbase = j0 + kb;
-                        const int causal = p.causal;
-                        process_block<HD>(tileA, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
-                                          [&](int rs, int col) { return causal && (colbase + col > rowA + rs * 8); });
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const int rowA = wrow0 + mt * 16 + rA;
+                            const int colbase = j0 + kb;
+                            process_block<HD>(tileA, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
+                                              [&](int rs, int col) { return colbase + col > rowA + rs * 8; });
+                        }
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            process_block<HD>(tileA, kb, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane, NoMask());
                     }
                 }
             }
@@ -351,9 +388,9 @@ static void launch(const Params& p, int heads, int head_dim, int n_groups_max, c
                cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()) == cudaSuccess;
     }();
     (void)attr_ok;
-    if (head_dim == 16) attn_mma_kernel<16><<<grid, THREADS, smem_bytes<16>(), s>>>(p);
-    else if (head_dim == 32) attn_mma_kernel<32><<<grid, THREADS, smem_bytes<32>(), s>>>(p);
-    else if (head_dim == 64) attn_mma_kernel<64><<<grid, THREADS, smem_bytes<64>(), s>>>(p);
+    if (head_dim == 16) launch_pdl(attn_mma_kernel<16>, grid, dim3(THREADS), smem_bytes<16>(), s, p);
+    else if (head_dim == 32) launch_pdl(attn_mma_kernel<32>, grid, dim3(THREADS), smem_bytes<32>(), s, p);
+    else if (head_dim == 64) launch_pdl(attn_mma_kernel<64>, grid, dim3(THREADS), smem_bytes<64>(), s, p);
 }
 }  // namespace amma
 

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 namespace ttb {
 
@@ -49,6 +50,31 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// Kernels of the decoding iteration are launched with the programmatic-stream-serialization attribute:
+// a kernel may be scheduled while its predecessor drains, runs its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and then blocks in pdl_wait() until the predecessor has completed
+// and its writes are visible.  Rule: no global-memory access that depends on (or could disturb) an
+// earlier kernel before pdl_wait().  Both instructions are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // engine.cu: TTB_NO_PDL=1 switches the attribute off (A/B comparisons)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // Control words of the device-resident decoding loops (int32 each).
 enum Ctrl : int {

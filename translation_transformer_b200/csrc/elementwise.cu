@@ -223,6 +223,8 @@ template void launch_add_layernorm<__nv_bfloat16>(const float*, const float*, co
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int V, int* __restrict__ out, RowCount rows) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= rows.live()) return;
     const float* p = logits + (long long)row * ld;
     float best = -INFINITY;
@@ -241,7 +243,7 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int
 }
 void launch_argmax_rows(const float* logits, int ld, int V, int* out, RowCount rows, cudaStream_t s) {
     if (rows.max_rows <= 0) return;
-    argmax_rows_kernel<<<(rows.max_rows + 7) / 8, 256, 0, s>>>(logits, ld, V, out, rows);
+    launch_pdl(argmax_rows_kernel, dim3((rows.max_rows + 7) / 8), dim3(256), 0, s, logits, ld, V, out, rows);
 }
 
 }  // namespace ttb

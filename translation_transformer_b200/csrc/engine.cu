@@ -17,6 +17,11 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("TTB_NO_PDL"); return !(v && v[0] == '1'); }();
+    return on;
+}
+
 static long long g_alloc_gen = 0;  // bumped whenever a workspace buffer moves (invalidates captured graphs)
 
 struct DevBuf {

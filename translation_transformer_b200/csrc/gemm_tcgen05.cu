@@ -290,11 +290,6 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     constexpr int BN = BN_;                                  // shadows tc::BN inside this kernel
     constexpr int COLS_PER_WARP = BN_ / 2;
     constexpr int STAGE_BYTES = pers::stage_bytes<BN_>();   // shadows tc::STAGE_BYTES
-    const int M = rows.live();
-    const int n_tiles_n = (N + BN - 1) / BN;
-    const int total_tiles = ((M + BM - 1) / BM) * n_tiles_n;
-    if ((int)blockIdx.x >= total_tiles) return;   // uniform per CTA, before any barrier / TMEM allocation
-
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -333,6 +328,12 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above is independent of earlier kernels; from here on their results are needed
+    pdl_launch_dependents();
+    pdl_wait();
+    const int M = rows.live();
+    const int n_tiles_n = (N + BN - 1) / BN;
+    const int total_tiles = ((M + BM - 1) / BM) * n_tiles_n;   // CTAs beyond it skip straight to the teardown
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -549,9 +550,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const float* __restrict__ bias, const float* __restrict__ g1, const float* __restrict__ b1,
                      const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int K) {
     using namespace lnk;
-    const int M = rows.live();
     const int m0 = (blockIdx.x >> 1) * BM;
-    if (m0 >= M) return;   // uniform per cluster, before any barrier / TMEM allocation
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int n0 = (int)rank * BNL;
@@ -609,9 +608,13 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // phase 0 of the cluster barrier: "this CTA is running" (its shared memory may be written by the peer);
     // the matching wait sits right before the first remote store
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // everything above is independent of earlier kernels (weights only); from here on their results are needed
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool live = m0 < rows.live();   // uniform per cluster: dead tiles only take part in the barriers
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
+        if (lane == 0 && live) {  // ===== TMA producer =====
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % NST;
                 const uint32_t ph = (kb / NST) & 1;
@@ -627,7 +630,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
+        if (lane == 0 && live) {  // ===== MMA issuer =====
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BNL);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % NST;
@@ -648,7 +651,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 
     // ===== epilogue (warps 2..9); warps 0/1 only take part in the cluster barriers =====
-    const bool epi = warp >= 2;
+    const bool epi = warp >= 2 && live;
     const int q = warp & 3;
     const int h = epi ? ((warp - 2) >> 2) : 0;
     const int row = q * 32 + lane;
@@ -795,7 +798,7 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
                 }
                 flag = true;
             }
-            kernel<<<grid, pers::THREADS, smem, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
+            launch_pdl(kernel, dim3(grid), dim3(pers::THREADS), (size_t)smem, s, tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
             return 0;
         };
         if (narrow) return launch(gemm_bf16_tc_persistent_kernel<OutT, 64>, pers::smem_bytes<OutT, 64>(), pattr_set[which][0]);
@@ -838,7 +841,7 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
         attr_set = true;
     }
     const int tiles = (rows.max_rows + BM - 1) / BM;
-    gemm_resid_ln_kernel<<<2 * tiles, lnk::THREADS, lnk::SMEM, s>>>(tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K);
+    launch_pdl(gemm_resid_ln_kernel, dim3(2 * tiles), dim3(lnk::THREADS), (size_t)lnk::SMEM, s, tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K);
     return 0;
 }
 

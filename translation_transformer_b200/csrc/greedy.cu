@@ -79,6 +79,8 @@ __global__ void greedy_embed_kernel(GreedyState st, const float* __restrict__ ta
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int per_q = st.N * (st.D + 1);
+    pdl_launch_dependents();
+    pdl_wait();
     if (st.ctrl[CTRL_DONE] || t >= st.ctrl[CTRL_N_ACTIVE] * per_q) return;
     const int g = t / per_q, r = t % per_q, n = r / (st.D + 1), i = r % (st.D + 1);
     const int b = st.active[g];
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
     int* col_live = s_nacc_all + n_warps * 64;   // [gen_ld]
     int* s_gen = col_live + st.gen_ld;           // [B][gen_ld] when stage_gen
     int* s_nacc = s_nacc_all + warp * 64;
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- round 1: independent loads --------------------------------------------------------------
     const int done = st.ctrl[CTRL_DONE];
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
@@ -251,7 +255,7 @@ void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
         cudaFuncSetAttribute(greedy_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ACCEPT_MAX_SMEM_INTS * sizeof(int)));
         attr_smem = ACCEPT_MAX_SMEM_INTS * sizeof(int);
     }
-    greedy_accept_kernel<<<1, warps * 32, smem, s>>>(st, stage_gen);
+    launch_pdl(greedy_accept_kernel, dim3(1), dim3(warps * 32), smem, s, st, stage_gen);
 }
 
 // ---- KV-cache append ------------------------------------------------------------------------------
@@ -260,6 +264,8 @@ __global__ void greedy_cache_append_kernel(GreedyState st, const ActT* __restric
                                            int qkv_ld, int E, ActT* __restrict__ kcache, ActT* __restrict__ vcache,
                                            long long cache_layer_stride, long long cache_query_stride, int cache_ld) {
     const int g = blockIdx.x, l = blockIdx.y;
+    pdl_launch_dependents();
+    pdl_wait();
     if (st.ctrl[CTRL_DONE] || g >= st.ctrl[CTRL_N_SEL]) return;  // after DONE the cache is never read again
     const int b = st.sel[g * 4 + 0], f = st.sel[g * 4 + 1], pick = st.sel[g * 4 + 2], a = st.sel[g * 4 + 3];
     const ActT* src = qkv_all + (long long)l * qkv_layer_stride + ((long long)g * st.N + pick) * (st.D + 1) * qkv_ld;
@@ -277,8 +283,8 @@ void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long
                                 long long cache_layer_stride, long long cache_query_stride, int cache_ld,
                                 cudaStream_t s) {
     dim3 grid(st.B, n_layers);
-    greedy_cache_append_kernel<ActT><<<grid, 256, 0, s>>>(st, qkv_all, qkv_layer_stride, qkv_ld, E, kcache, vcache,
-                                                          cache_layer_stride, cache_query_stride, cache_ld);
+    launch_pdl(greedy_cache_append_kernel<ActT>, grid, dim3(256), 0, s, st, qkv_all, qkv_layer_stride, qkv_ld, E, kcache, vcache,
+               cache_layer_stride, cache_query_stride, cache_ld);
 }
 template void launch_greedy_cache_append<float>(const GreedyState&, const float*, long long, int, int, int, float*, float*, long long, long long, int, cudaStream_t);
 template void launch_greedy_cache_append<__nv_bfloat16>(const GreedyState&, const __nv_bfloat16*, long long, int, int, int, __nv_bfloat16*, __nv_bfloat16*, long long, long long, int, cudaStream_t);

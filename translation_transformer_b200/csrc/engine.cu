@@ -293,6 +293,28 @@ static int linear_resid_ln(ttb_engine* e, int kc, const __nv_bfloat16* A, int ld
     return 0;
 }
 
+// Feed-forward sub-layer  x <- LN2?(LN1(x + relu(x W1^T + b1) W2^T + b2)):  one fused kernel (hidden activations stay
+// on the SM) on the bf16 path with E = 256, FFN1 GEMM + (FFN2 GEMM + LN) otherwise.  TTB_NO_FUSED_FFN=1 disables it.
+static bool fused_ffn_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TTB_NO_FUSED_FFN"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+static int ffn_block(ttb_engine* e, int kc1, int kc2, const Lin& L1, const Lin& L2, const Norm& n1, const Norm* n2, float* x, float* xh,
+                     float* hid, float* y, float* dst, float* dsth, RowCount rows, cudaStream_t s) {
+    if (linear<float>(e, kc1, x, L1.K, L1, hid, L1.N, rows, true, s)) return 1;
+    return linear_resid_ln(e, kc2, hid, L1.N, L2, n1, n2, x, xh, y, dst, dsth, rows, s);
+}
+static int ffn_block(ttb_engine* e, int kc1, int kc2, const Lin& L1, const Lin& L2, const Norm& n1, const Norm* n2, float* x,
+                     __nv_bfloat16* xh, __nv_bfloat16* hid, float* y, float* dst, __nv_bfloat16* dsth, RowCount rows, cudaStream_t s) {
+    if (L2.N == 256 && L1.K == 256 && L1.N % 256 == 0 && L1.N <= 4096 && dst == x && dsth == xh && fused_ffn_enabled() && fused_ln_enabled()) {
+        Scope sc(e, kc1, s);
+        return launch_ffn_fused(xh, L1.wh, L1.b, L2.wh, L2.b, x, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, rows, L1.N, s);
+    }
+    if (linear<__nv_bfloat16>(e, kc1, xh, L1.K, L1, hid, L1.N, rows, true, s)) return 1;
+    return linear_resid_ln(e, kc2, hid, L1.N, L2, n1, n2, x, xh, y, dst, dsth, rows, s);
+}
+
 // Attention dispatch: fp32 path -> SIMT kernels (exact), bf16 path -> tensor-core kernels
 // (TTB_ATTN_SIMT=1 forces the SIMT kernels for A/B comparisons).
 static bool attn_simt_forced() {
@@ -352,7 +374,7 @@ static int ensure_work(ttb_engine* e, long long T, int qkv_layers) {
 // Encoder stack on tokens src32 (B, Ls); writes memory (fp32) and, on the bf16 path, memh.
 template <typename ActT>
 static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int B, int Ls, float* mem_out, ActT* memh_out, cudaStream_t s) {
-    const int E = e->E(), F = e->d.feedforward_dim, T = B * Ls, H = e->d.num_heads, HD = e->HD();
+    const int E = e->E(), T = B * Ls, H = e->d.num_heads, HD = e->HD();
     if (ensure_work<ActT>(e, T, 1)) return 1;
     float* x = e->x.as<float>();
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
@@ -375,10 +397,9 @@ static int encode_impl(ttb_engine* e, const int* src32, const int* key_tok, int 
                                    key_tok, Ls, e->d.src_pad_token_idx, false, H, HD, s);
         }
         if (linear_resid_ln(e, KC_ENCODER, att, E, L.out_proj, L.n1, nullptr, x, xh, y, x, xh, rows, s)) return 1;
-        if (linear<ActT>(e, KC_ENCODER, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
         float* dst = last ? mem_out : x;
         ActT* dsth = last ? memh_out : xh;
-        if (linear_resid_ln(e, KC_ENCODER, hid, F, L.ff2, L.n2, last ? &e->enc_norm : nullptr, x, xh, y, dst, dsth, rows, s)) return 1;
+        if (ffn_block(e, KC_ENCODER, KC_ENCODER, L.ff1, L.ff2, L.n2, last ? &e->enc_norm : nullptr, x, xh, hid, y, dst, dsth, rows, s)) return 1;
     }
     return 0;
 }
@@ -402,7 +423,7 @@ static int cross_kv_impl(ttb_engine* e, const float* mem, const ActT* memh, int 
 template <typename ActT, typename SelfAttn, typename CrossAttn>
 static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long qkv_layer_stride,
                          SelfAttn self_attn, CrossAttn cross_attn, cudaStream_t s) {
-    const int E = e->E(), F = e->d.feedforward_dim;
+    const int E = e->E();
     float* x = e->x.as<float>();
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
     float* y = e->y.as<float>();
@@ -420,8 +441,7 @@ static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long
         if (linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
         { Scope sc(e, KC_CROSS_ATTN, s); cross_attn(l, q2, att); }
         if (linear_resid_ln(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, L.n2, nullptr, x, xh, y, x, xh, rows, s)) return 1;
-        if (linear<ActT>(e, KC_GEMM_FFN1, a_view<ActT>(x, xh), E, L.ff1, hid, F, rows, true, s)) return 1;
-        if (linear_resid_ln(e, KC_GEMM_FFN2, hid, F, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, y, x, xh, rows, s)) return 1;
+        if (ffn_block(e, KC_GEMM_FFN1, KC_GEMM_FFN2, L.ff1, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, hid, y, x, xh, rows, s)) return 1;
     }
     return 0;
 }

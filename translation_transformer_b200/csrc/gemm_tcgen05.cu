@@ -544,6 +544,60 @@ __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 
+// ---- LayerNorm tail shared by the fused kernels: one thread = (row, 64-column half h of the CTA's 128 columns) ----
+__device__ __forceinline__ void ln_local_stats(const float (&v)[64], float& mean, float& m2) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) s += v[j];
+    mean = s * (1.0f / 64.0f);
+    float qq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qq += d * d; }
+    m2 = qq;
+}
+// partial statistics of group pidx = 2 * rank + h into both CTAs' tables (float2[4][128])
+__device__ __forceinline__ void ln_publish(float2* part, int pidx, int row, uint32_t rank, float mean, float m2) {
+    part[pidx * BM + row] = make_float2(mean, m2);
+    st_peer_f32x2(smem_u32(&part[pidx * BM + row]), rank ^ 1u, mean, m2);
+}
+// Chan's combination of the four equally sized groups (64 values each) of a 256-wide row, then scale/shift
+__device__ __forceinline__ void ln_normalise(float (&v)[64], const float2* part, int row, const float* gg, const float* bb) {
+    const float2 p0 = part[row], p1 = part[BM + row], p2 = part[2 * BM + row], p3 = part[3 * BM + row];
+    const float mean = 0.25f * (p0.x + p1.x + p2.x + p3.x);
+    const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+    const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+    const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+}
+// fp32 values into two [128 x 32] boxes and bf16 values into one [128 x 64] box (128-byte swizzle, TMA-store layout)
+__device__ __forceinline__ void ln_store_tiles(const float (&v)[64], uint8_t* f32_box0, uint8_t* bf16_box, int row) {
+    const int swz = row & 7;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint8_t* box = f32_box0 + (c0 / 32) * (BM * 128) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = c0 + 4 * c;
+            *reinterpret_cast<float4*>(box + ((c ^ swz) << 4)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    }
+    uint8_t* hbox = bf16_box + row * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * c + 0], v[8 * c + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        u.z = *reinterpret_cast<uint32_t*>(&p2);
+        u.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(hbox + ((c ^ swz) << 4)) = u;
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(lnk::THREADS, 1)
 gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXh,
@@ -658,31 +712,6 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int swz = row & 7;
     const int pidx = (int)rank * 2 + h;
     float v[64];
-    auto local_stats = [&](float& mean, float& m2) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) s += v[j];
-        mean = s * (1.0f / 64.0f);
-        float qq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qq += d * d; }
-        m2 = qq;
-    };
-    auto publish = [&](float2* part, float mean, float m2) {
-        part[pidx * BM + row] = make_float2(mean, m2);
-        st_peer_f32x2(smem_u32(&part[pidx * BM + row]), rank ^ 1u, mean, m2);
-    };
-    auto normalise = [&](const float2* part, const float* gg, const float* bb) {
-        // Chan's combination of four equally sized groups (64 values each)
-        const float2 p0 = part[row], p1 = part[BM + row], p2 = part[2 * BM + row], p3 = part[3 * BM + row];
-        const float mean = 0.25f * (p0.x + p1.x + p2.x + p3.x);
-        const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
-        const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
-        const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd * gg[h * 64 + j] + bb[h * 64 + j];
-    };
-
     if (epi) {
         mbar_wait(tfull_bar, 0);
         tcgen05_fence_after();
@@ -703,51 +732,29 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
         float mean, m2;
-        local_stats(mean, m2);
+        ln_local_stats(v, mean, m2);
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // phase 0: the peer is running
-        publish(part1, mean, m2);
+        ln_publish(part1, pidx, row, rank, mean, m2);
     } else {
         __syncwarp();
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     __syncwarp();
     cluster_sync_all();
-    if (epi) normalise(part1, prm + BNL, prm + 2 * BNL);
+    if (epi) ln_normalise(v, part1, row, prm + BNL + h * 64, prm + 2 * BNL + h * 64);
     if (g2) {   // final LayerNorm of the stack on top (uniform branch)
         if (epi) {
             float mean, m2;
-            local_stats(mean, m2);
-            publish(part2, mean, m2);
+            ln_local_stats(v, mean, m2);
+            ln_publish(part2, pidx, row, rank, mean, m2);
         }
         __syncwarp();
         cluster_sync_all();
-        if (epi) normalise(part2, prm + 3 * BNL, prm + 4 * BNL);
+        if (epi) ln_normalise(v, part2, row, prm + 3 * BNL + h * 64, prm + 4 * BNL + h * 64);
     }
     if (epi) {
         // fp32 tile back into the residual boxes (in place), bf16 tile into the idle ring (stage 0)
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint8_t* box = resid_sm + (2 * h + c0 / 32) * (BM * 128) + row * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int j = c0 + 4 * c;
-                *reinterpret_cast<float4*>(box + ((c ^ swz) << 4)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-        }
-        uint8_t* hbox = gen_base + h * (BM * 128) + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 u;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * c + 0], v[8 * c + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2);
-            u.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(hbox + ((c ^ swz) << 4)) = u;
-        }
+        ln_store_tiles(v, resid_sm + 2 * h * (BM * 128), gen_base + h * (BM * 128), row);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {
@@ -761,6 +768,335 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BNL) : "memory");
+    }
+}
+
+// =====================================================================================================
+// Fused feed-forward sub-layer for E = 256:
+//     x <- LN2?( LN1( x + relu(xh W1^T + b1) W2^T + b2 ) ),  x fp32 in place, xh = bf16 copy (in place)
+// The hidden activations never leave the SM.  One cluster of two CTAs per 128-row tile; CTA r owns the
+// hidden units [r F/2, (r+1) F/2) in chunks of 128:
+//   GEMM1(c)  acc1[c&1] (128 x 128, TMEM) = X (128 x 256, resident in smem) . W1[chunk]^T
+//   epilogue  acc1 -> + b1 -> ReLU -> bf16 -> H (128 x 128, two swizzled K-blocks in smem)
+//   GEMM2(c)  acc2 (128 x 256, TMEM) += H . W2[:, chunk]^T
+// issued as G1(0) G1(1) G2(0) G1(2) G2(1) ... so that the tensor pipe works on the next chunk while the
+// epilogue warps convert the current one.  W1/W2 stream through a ring of three 32 KB slots (TMA).  At the
+// end each CTA holds a partial sum over its half of the hidden units: the half of it that belongs to the
+// peer's output columns is pushed through distributed shared memory, the own half is combined with the
+// peer's push, bias and residual, and the LayerNorm tail is the one of gemm_resid_ln_kernel.
+namespace ffn {
+constexpr int NSLOT = 3, SLOT = 32768;
+constexpr int X_BYTES = 65536, H_BYTES = 32768;
+constexpr int THREADS = 320;
+constexpr int OFF_H = X_BYTES, OFF_RING = X_BYTES + H_BYTES, OFF_PART = OFF_RING + NSLOT * SLOT;
+constexpr int PART_BYTES = 4 * BM * 8;
+constexpr int OFF_PRM = OFF_PART + 2 * PART_BYTES;           // b2, g1, b1, g2, b2' slices: 5 * 128 floats
+constexpr int OFF_B1 = OFF_PRM + 5 * 128 * 4;                // this CTA's half of linear1.bias (<= 2048 floats)
+constexpr int MAX_HALF = 2048;
+constexpr int OFF_BAR = OFF_B1 + MAX_HALF * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+}  // namespace ffn
+
+__device__ __forceinline__ void st_peer_f32x4(uint32_t local_addr, uint32_t peer_rank, float a, float b, float c, float d) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer_rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                 const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ g1,
+                 const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F) {
+    using namespace ffn;
+    const int m0 = (blockIdx.x >> 1) * BM;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int half = F / 2;                 // hidden units of this CTA
+    const int n_chunks = half / 128;
+    const int j_base = (int)rank * half;    // first hidden unit of this CTA
+    const int n0 = (int)rank * 128;         // output columns owned by this CTA
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    float2* part1 = reinterpret_cast<float2*>(gen + OFF_PART);
+    float2* part2 = part1 + 4 * BM;
+    float* prm = reinterpret_cast<float*>(gen + OFF_PRM);
+    float* b1s = reinterpret_cast<float*>(gen + OFF_B1);
+    const uint32_t bar_base = base + OFF_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSLOT + s); };
+    const uint32_t x_full = bar_base + 8u * (2 * NSLOT);
+    auto acc1_full = [&](int b) { return bar_base + 8u * (2 * NSLOT + 1 + b); };
+    auto acc1_empty = [&](int b) { return bar_base + 8u * (2 * NSLOT + 3 + b); };
+    const uint32_t h_full = bar_base + 8u * (2 * NSLOT + 5);
+    const uint32_t h_empty = bar_base + 8u * (2 * NSLOT + 6);
+    const uint32_t acc2_full = bar_base + 8u * (2 * NSLOT + 7);
+    const uint32_t resid_bar = bar_base + 8u * (2 * NSLOT + 8);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 9));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            mbar_init(x_full, 1);
+            for (int b = 0; b < 2; ++b) { mbar_init(acc1_full(b), 1); mbar_init(acc1_empty(b), 8); }
+            mbar_init(h_full, 8);
+            mbar_init(h_empty, 1);
+            mbar_init(acc2_full, 1);
+            mbar_init(resid_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {   // parameter slices (weights only: independent of earlier kernels)
+        const int t = threadIdx.x - 64;
+        if (t < 128) {
+            prm[t] = bias2 ? __ldg(bias2 + n0 + t) : 0.f;
+            prm[128 + t] = __ldg(g1 + n0 + t);
+            prm[256 + t] = __ldg(b1 + n0 + t);
+            prm[384 + t] = g2 ? __ldg(g2 + n0 + t) : 1.f;
+            prm[512 + t] = g2 ? __ldg(b2 + n0 + t) : 0.f;
+        }
+        for (int i = t; i < half; i += 256) b1s[i] = bias1 ? __ldg(bias1 + j_base + i) : 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_acc2 = tmem_base, tm_acc1 = tmem_base + 256u;
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // phase 0: "this CTA is running"
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool live = m0 < rows.live();   // uniform per cluster: dead tiles only take part in the barriers
+
+    if (warp == 0) {
+        if (lane == 0 && live) {  // ===== TMA producer =====
+            mbar_expect_tx(x_full, X_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d(base + kb * 16384, &tmXh, kb * BK, m0, x_full);
+            int it = 0;
+            auto take_slot = [&]() -> uint32_t {
+                const int s = it % NSLOT;
+                const uint32_t ph = (it / NSLOT) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), SLOT);
+                ++it;
+                return (uint32_t)s;
+            };
+            auto load_w1 = [&](int c) {    // two slots, each two K-blocks [128 x 64] of the chunk's W1 rows
+                const int j0 = j_base + c * 128;
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t sl = take_slot();
+                    const uint32_t dst = base + OFF_RING + sl * SLOT;
+                    tma_load_2d(dst, &tmW1, (2 * j) * BK, j0, full_bar(sl));
+                    tma_load_2d(dst + 16384, &tmW1, (2 * j + 1) * BK, j0, full_bar(sl));
+                }
+            };
+            auto load_w2 = [&](int c) {    // two slots, each one K-block [256 x 64] of W2 (two boxes of 128 rows)
+                const int j0 = j_base + c * 128;
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint32_t sl = take_slot();
+                    const uint32_t dst = base + OFF_RING + sl * SLOT;
+                    tma_load_2d(dst, &tmW2, j0 + kk * BK, 0, full_bar(sl));
+                    tma_load_2d(dst + 16384, &tmW2, j0 + kk * BK, 128, full_bar(sl));
+                }
+            };
+            load_w1(0);
+            for (int c = 0; c < n_chunks; ++c) {
+                if (c + 1 < n_chunks) load_w1(c + 1);
+                load_w2(c);
+            }
+            // residual tile into the (now idle) X region once every MMA has completed
+            mbar_wait(acc2_full, 0);
+            mbar_expect_tx(resid_bar, 65536);
+            for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && live) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc1 = umma_idesc_bf16(BM, 128);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 256);
+            int it = 0;
+            mbar_wait(x_full, 0);
+            tcgen05_fence_after();
+            auto gemm1 = [&](int c) {
+                const int b = c & 1;
+                mbar_wait(acc1_empty(b), ((c >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
+                for (int j = 0; j < 2; ++j, ++it) {
+                    const int s = it % NSLOT;
+                    mbar_wait(full_bar(s), (it / NSLOT) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+                    for (int kq = 0; kq < 2; ++kq) {
+                        const int kb = 2 * j + kq;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
+                            const uint64_t bdesc = umma_desc_sw128(slot + kq * 16384 + k * UMMA_K * 2);
+                            umma_bf16(d, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc1_full(b));
+            };
+            auto gemm2 = [&](int c) {
+                mbar_wait(h_full, c & 1);
+                tcgen05_fence_after();
+                for (int kk = 0; kk < 2; ++kk, ++it) {
+                    const int s = it % NSLOT;
+                    mbar_wait(full_bar(s), (it / NSLOT) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(base + OFF_H + kk * 16384 + k * UMMA_K * 2);
+                        const uint64_t bdesc = umma_desc_sw128(slot + k * UMMA_K * 2);
+                        umma_bf16(tm_acc2, adesc, bdesc, idesc2, (c | kk | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(h_empty);
+            };
+            gemm1(0);
+            for (int c = 0; c < n_chunks; ++c) {
+                if (c + 1 < n_chunks) gemm1(c + 1);
+                gemm2(c);
+            }
+            umma_commit(acc2_full);
+        }
+    }
+
+    // ===== epilogue warps 2..9: thread = (row, 64-column half hh) =====
+    const bool epi = warp >= 2 && live;
+    const int q = warp & 3;
+    const int hh = warp >= 2 ? ((warp - 2) >> 2) : 0;
+    const int row = q * 32 + lane;
+    const int swz = row & 7;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (epi) {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b = c & 1;
+            mbar_wait(acc1_full(b), (c >> 1) & 1);
+            tcgen05_fence_after();
+            uint32_t pk[32];   // 64 bf16 values
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 * b + hh * 64 + c0), r);
+                const float* bb = b1s + c * 128 + hh * 64 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float v0 = fmaxf(__uint_as_float(r[j]) + bb[j], 0.f);
+                    const float v1 = fmaxf(__uint_as_float(r[j + 1]) + bb[j + 1], 0.f);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v0, v1);
+                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p2);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc1_empty(b));        // accumulator buffer may be overwritten
+            mbar_wait(h_empty, (c & 1) ^ 1);                  // GEMM2 of the previous chunk has read H
+            uint8_t* hrow = gen + OFF_H + hh * 16384 + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(hrow + ((ch ^ swz) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_full);
+        }
+        mbar_wait(acc2_full, 0);
+        tcgen05_fence_after();
+    }
+    // ---- cross-CTA reduction of the two partial sums -------------------------------------------------
+    // barrier A: both CTAs have finished their main loops, so the H / ring regions are free to receive
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // phase 0
+    cluster_sync_all();                                                         // barrier A
+    uint8_t* recv = gen + OFF_H;    // [128 rows][32 chunks of 16 B], chunk index XOR (row & 31)
+    if (epi) {
+        const int pcol = (int)(rank ^ 1u) * 128 + hh * 64;   // the peer's output columns handled by this thread
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_acc2 + lane_base + (uint32_t)(pcol + c0), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int chunk = hh * 16 + (c0 >> 2) + i;
+                st_peer_f32x4(smem_u32(recv + row * 512 + ((chunk ^ (row & 31)) << 4)), rank ^ 1u, __uint_as_float(r[4 * i]),
+                              __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+        }
+    }
+    __syncwarp();
+    cluster_sync_all();                                                         // barrier B: pushes are visible
+    float v[64];
+    const int pidx = (int)rank * 2 + hh;
+    if (epi) {
+        mbar_wait(resid_bar, 0);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_acc2 + lane_base + (uint32_t)(n0 + hh * 64 + c0), r);
+            const uint8_t* box = gen + (2 * hh + c0 / 32) * 16384 + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
+                const int chunk = hh * 16 + (c0 >> 2) + c;
+                const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
+                const int j = c0 + 4 * c;
+                v[j + 0] = __uint_as_float(r[4 * c + 0]) + pv.x + prm[hh * 64 + j + 0] + rv.x;
+                v[j + 1] = __uint_as_float(r[4 * c + 1]) + pv.y + prm[hh * 64 + j + 1] + rv.y;
+                v[j + 2] = __uint_as_float(r[4 * c + 2]) + pv.z + prm[hh * 64 + j + 2] + rv.z;
+                v[j + 3] = __uint_as_float(r[4 * c + 3]) + pv.w + prm[hh * 64 + j + 3] + rv.w;
+            }
+        }
+        float mean, m2;
+        ln_local_stats(v, mean, m2);
+        ln_publish(part1, pidx, row, rank, mean, m2);
+    }
+    __syncwarp();
+    cluster_sync_all();                                                         // barrier C
+    if (epi) ln_normalise(v, part1, row, prm + 128 + hh * 64, prm + 256 + hh * 64);
+    if (g2) {
+        if (epi) {
+            float mean, m2;
+            ln_local_stats(v, mean, m2);
+            ln_publish(part2, pidx, row, rank, mean, m2);
+        }
+        __syncwarp();
+        cluster_sync_all();
+        if (epi) ln_normalise(v, part2, row, prm + 384 + hh * 64, prm + 512 + hh * 64);
+    }
+    if (epi) {
+        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (idle, not part of recv)
+        ln_store_tiles(v, gen + 2 * hh * 16384, gen + OFF_RING + SLOT + hh * 16384, row);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+            for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + bx * 16384, n0 + 32 * bx, m0);
+            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + OFF_RING + SLOT + hb * 16384, n0 + 64 * hb, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 }  // namespace tc
@@ -817,6 +1153,34 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     gemm_bf16_tc_kernel<OutT><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
     return 0;
 }
+int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,
+                     float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s) {
+    using namespace tc;
+    if (rows.max_rows <= 0) return 0;
+    if (F % 256 != 0 || F / 2 > ffn::MAX_HALF || (reinterpret_cast<uintptr_t>(W1) & 15) || (reinterpret_cast<uintptr_t>(W2) & 15) ||
+        (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(xh) & 15)) {
+        set_last_error("fused FFN needs feedforward_dim % 256 == 0, <= 4096 and 16-byte aligned operands");
+        return 4;
+    }
+    CUtensorMap tmXh, tmW1, tmW2, tmX;
+    if (int rc = get_tensor_map(xh, rows.max_rows, 256, 256, BM, &tmXh)) return rc;
+    if (int rc = get_tensor_map(W1, F, 256, 256, 128, &tmW1)) return rc;
+    if (int rc = get_tensor_map(W2, 256, F, F, 128, &tmW2)) return rc;
+    if (int rc = get_tensor_map(x, rows.max_rows, 256, 256, BM, &tmX, true)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn::SMEM);
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    const int tiles = (rows.max_rows + BM - 1) / BM;
+    launch_pdl(ffn_fused_kernel, dim3(2 * tiles), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F);
+    return 0;
+}
+
 int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
                          const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s) {
     using namespace tc;

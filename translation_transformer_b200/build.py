@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     out_dir.mkdir(exist_ok=True)
     for src in SOURCES:
         obj = out_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("TTB_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

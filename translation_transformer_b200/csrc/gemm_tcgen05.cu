@@ -567,8 +567,16 @@ __device__ __forceinline__ void ln_normalise(float (&v)[64], const float2* part,
     const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
     const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
     const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(gg);   // 16-byte aligned parameter slices: 32 broadcast
+    const float4* b4 = reinterpret_cast<const float4*>(bb);   // LDS.128 per thread instead of 128 LDS.32
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+    for (int j = 0; j < 16; ++j) {
+        const float4 g = g4[j], b = b4[j];
+        v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
+        v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+        v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
+        v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+    }
 }
 // fp32 values into two [128 x 32] boxes and bf16 values into one [128 x 64] box (128-byte swizzle, TMA-store layout)
 __device__ __forceinline__ void ln_store_tiles(const float (&v)[64], uint8_t* f32_box0, uint8_t* bf16_box, int row) {
@@ -725,10 +733,11 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int c = 0; c < 8; ++c) {
                 const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
                 const int j = c0 + 4 * c;
-                v[j + 0] = __uint_as_float(r[4 * c + 0]) + prm[h * 64 + j + 0] + rv.x;
-                v[j + 1] = __uint_as_float(r[4 * c + 1]) + prm[h * 64 + j + 1] + rv.y;
-                v[j + 2] = __uint_as_float(r[4 * c + 2]) + prm[h * 64 + j + 2] + rv.z;
-                v[j + 3] = __uint_as_float(r[4 * c + 3]) + prm[h * 64 + j + 3] + rv.w;
+                const float4 bv = *reinterpret_cast<const float4*>(prm + h * 64 + j);
+                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
+                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
+                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
+                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
             }
         }
         float mean, m2;
@@ -784,6 +793,21 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // end each CTA holds a partial sum over its half of the hidden units: the half of it that belongs to the
 // peer's output columns is pushed through distributed shared memory, the own half is combined with the
 // peer's push, bias and residual, and the LayerNorm tail is the one of gemm_resid_ln_kernel.
+#ifdef TTB_FFN_TIMELINE
+// Debug build only: (event id, clock64) pairs of CTA 0 per role -> g_ffn_ts[role][256][2]
+__device__ long long g_ffn_ts[3][256][2];
+#define FFN_TS(role, cnt, id)                                                   \
+    do {                                                                        \
+        if (blockIdx.x == 0 && (cnt) < 256) {                                   \
+            g_ffn_ts[role][cnt][0] = (id);                                      \
+            g_ffn_ts[role][cnt][1] = clock64();                                 \
+            ++(cnt);                                                            \
+        }                                                                       \
+    } while (0)
+#else
+#define FFN_TS(role, cnt, id) do { } while (0)
+#endif
+
 namespace ffn {
 constexpr int NSLOT = 3, SLOT = 32768;
 constexpr int X_BYTES = 65536, H_BYTES = 32768;
@@ -807,7 +831,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                  const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ g1,
-                 const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F) {
+                 const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F, int dbg) {
     using namespace ffn;
     const int m0 = (blockIdx.x >> 1) * BM;
     uint32_t rank;
@@ -835,7 +859,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     const uint32_t h_empty = bar_base + 8u * (2 * NSLOT + 6);
     const uint32_t acc2_full = bar_base + 8u * (2 * NSLOT + 7);
     const uint32_t resid_bar = bar_base + 8u * (2 * NSLOT + 8);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 9));
+    const uint32_t recv_bar = bar_base + 8u * (2 * NSLOT + 9);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 10));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -854,6 +879,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             mbar_init(h_empty, 1);
             mbar_init(acc2_full, 1);
             mbar_init(resid_bar, 1);
+            mbar_init(recv_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -879,10 +905,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // phase 0: "this CTA is running"
     pdl_launch_dependents();
     pdl_wait();
+#ifdef TTB_FFN_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
+#endif
     const bool live = m0 < rows.live();   // uniform per cluster: dead tiles only take part in the barriers
 
     if (warp == 0) {
         if (lane == 0 && live) {  // ===== TMA producer =====
+            [[maybe_unused]] int tsn = 0;
+            FFN_TS(0, tsn, 1);
             mbar_expect_tx(x_full, X_BYTES);
             for (int kb = 0; kb < 4; ++kb) tma_load_2d(base + kb * 16384, &tmXh, kb * BK, m0, x_full);
             int it = 0;
@@ -890,6 +921,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 const int s = it % NSLOT;
                 const uint32_t ph = (it / NSLOT) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
+                FFN_TS(0, tsn, 100 + it);
+                if ((dbg & 1) && it >= NSLOT) { mbar_expect_tx(full_bar(s), 0); ++it; return 0xffffffffu; }   // timing experiment: no reload
                 mbar_expect_tx(full_bar(s), SLOT);
                 ++it;
                 return (uint32_t)s;
@@ -898,6 +931,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 const int j0 = j_base + c * 128;
                 for (int j = 0; j < 2; ++j) {
                     const uint32_t sl = take_slot();
+                    if (sl == 0xffffffffu) continue;
                     const uint32_t dst = base + OFF_RING + sl * SLOT;
                     tma_load_2d(dst, &tmW1, (2 * j) * BK, j0, full_bar(sl));
                     tma_load_2d(dst + 16384, &tmW1, (2 * j + 1) * BK, j0, full_bar(sl));
@@ -907,6 +941,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 const int j0 = j_base + c * 128;
                 for (int kk = 0; kk < 2; ++kk) {
                     const uint32_t sl = take_slot();
+                    if (sl == 0xffffffffu) continue;
                     const uint32_t dst = base + OFF_RING + sl * SLOT;
                     tma_load_2d(dst, &tmW2, j0 + kk * BK, 0, full_bar(sl));
                     tma_load_2d(dst + 16384, &tmW2, j0 + kk * BK, 128, full_bar(sl));
@@ -927,17 +962,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             constexpr uint32_t idesc1 = umma_idesc_bf16(BM, 128);
             constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 256);
             int it = 0;
+            [[maybe_unused]] int tsn = 0;
+            FFN_TS(1, tsn, 1);
             mbar_wait(x_full, 0);
             tcgen05_fence_after();
+            FFN_TS(1, tsn, 2);
             auto gemm1 = [&](int c) {
                 const int b = c & 1;
                 mbar_wait(acc1_empty(b), ((c >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                FFN_TS(1, tsn, 1000 + c);
                 const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
                 for (int j = 0; j < 2; ++j, ++it) {
                     const int s = it % NSLOT;
                     mbar_wait(full_bar(s), (it / NSLOT) & 1);
                     tcgen05_fence_after();
+                    FFN_TS(1, tsn, 2000 + it);
                     const uint32_t slot = base + OFF_RING + s * SLOT;
 #pragma unroll
                     for (int kq = 0; kq < 2; ++kq) {
@@ -956,10 +996,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             auto gemm2 = [&](int c) {
                 mbar_wait(h_full, c & 1);
                 tcgen05_fence_after();
+                FFN_TS(1, tsn, 3000 + c);
                 for (int kk = 0; kk < 2; ++kk, ++it) {
                     const int s = it % NSLOT;
                     mbar_wait(full_bar(s), (it / NSLOT) & 1);
                     tcgen05_fence_after();
+                    FFN_TS(1, tsn, 2000 + it);
                     const uint32_t slot = base + OFF_RING + s * SLOT;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -977,10 +1019,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 gemm2(c);
             }
             umma_commit(acc2_full);
+            FFN_TS(1, tsn, 9);
         }
     }
 
     // ===== epilogue warps 2..9: thread = (row, 64-column half hh) =====
+    [[maybe_unused]] int tse = 0;
+    [[maybe_unused]] const bool ts_on = threadIdx.x == 64;
     const bool epi = warp >= 2 && live;
     const int q = warp & 3;
     const int hh = warp >= 2 ? ((warp - 2) >> 2) : 0;
@@ -990,26 +1035,34 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     if (epi) {
         for (int c = 0; c < n_chunks; ++c) {
             const int b = c & 1;
+            if (ts_on) FFN_TS(2, tse, 100 + c);
             mbar_wait(acc1_full(b), (c >> 1) & 1);
             tcgen05_fence_after();
+            if (ts_on) FFN_TS(2, tse, 200 + c);
             uint32_t pk[32];   // 64 bf16 values
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 * b + hh * 64 + c0), r);
-                const float* bb = b1s + c * 128 + hh * 64 + c0;
+                const float4* bb = reinterpret_cast<const float4*>(b1s + c * 128 + hh * 64 + c0);
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float v0 = fmaxf(__uint_as_float(r[j]) + bb[j], 0.f);
-                    const float v1 = fmaxf(__uint_as_float(r[j + 1]) + bb[j + 1], 0.f);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v0, v1);
-                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p2);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = bb[j >> 2];
+                    const float v0 = fmaxf(__uint_as_float(r[j]) + bv.x, 0.f);
+                    const float v1 = fmaxf(__uint_as_float(r[j + 1]) + bv.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(r[j + 2]) + bv.z, 0.f);
+                    const float v3 = fmaxf(__uint_as_float(r[j + 3]) + bv.w, 0.f);
+                    __nv_bfloat162 p01 = __floats2bfloat162_rn(v0, v1), p23 = __floats2bfloat162_rn(v2, v3);
+                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p01);
+                    pk[((c0 + j) >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p23);
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc1_empty(b));        // accumulator buffer may be overwritten
+            if (ts_on) FFN_TS(2, tse, 300 + c);
             mbar_wait(h_empty, (c & 1) ^ 1);                  // GEMM2 of the previous chunk has read H
+            if (ts_on) FFN_TS(2, tse, 400 + c);
             uint8_t* hrow = gen + OFF_H + hh * 16384 + row * 128;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
@@ -1017,16 +1070,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full);
+            if (ts_on) FFN_TS(2, tse, 500 + c);
         }
         mbar_wait(acc2_full, 0);
         tcgen05_fence_after();
+        if (ts_on) FFN_TS(2, tse, 600);
     }
     // ---- cross-CTA reduction of the two partial sums -------------------------------------------------
-    // barrier A: both CTAs have finished their main loops, so the H / ring regions are free to receive
+    // Each CTA stages the half of its partial sum that belongs to the peer's output columns in its own shared
+    // memory (idle ring slots 1-2) and ships it with one asynchronous bulk copy per 16 KB into the peer's
+    // receive buffer (idle H + ring slot 0); the copy signals the peer's recv_bar.  Cluster barrier A ("my main
+    // loop is over, my buffers may be written") is split into arrive / wait around the staging.
+    uint8_t* recv = gen + OFF_H;             // [128 rows][32 chunks of 16 B], chunk index XOR (row & 31)
+    uint8_t* send = gen + OFF_RING + SLOT;   // same layout
+    if (threadIdx.x == 64 && live) mbar_expect_tx(recv_bar, 65536);
     __syncwarp();
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // phase 0
-    cluster_sync_all();                                                         // barrier A
-    uint8_t* recv = gen + OFF_H;    // [128 rows][32 chunks of 16 B], chunk index XOR (row & 31)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // barrier A (arrive)
     if (epi) {
         const int pcol = (int)(rank ^ 1u) * 128 + hh * 64;   // the peer's output columns handled by this thread
 #pragma unroll
@@ -1036,13 +1096,25 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int chunk = hh * 16 + (c0 >> 2) + i;
-                st_peer_f32x4(smem_u32(recv + row * 512 + ((chunk ^ (row & 31)) << 4)), rank ^ 1u, __uint_as_float(r[4 * i]),
-                              __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                *reinterpret_cast<uint4*>(send + row * 512 + ((chunk ^ (row & 31)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     __syncwarp();
-    cluster_sync_all();                                                         // barrier B: pushes are visible
+    if (ts_on) FFN_TS(2, tse, 700);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // barrier A (wait): the peer's buffers are free
+    if (ts_on) FFN_TS(2, tse, 701);
+    if (threadIdx.x == 64 && live) {
+        uint32_t r_recv, r_bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_recv) : "r"(base + OFF_H), "r"(rank ^ 1u));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar) : "r"(recv_bar), "r"(rank ^ 1u));
+        for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(r_recv + i * 16384),
+                         "r"(base + OFF_RING + SLOT + i * 16384), "r"(16384), "r"(r_bar)
+                         : "memory");
+    }
     float v[64];
     const int pidx = (int)rank * 2 + hh;
     if (epi) {
@@ -1055,22 +1127,35 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
-                const int chunk = hh * 16 + (c0 >> 2) + c;
-                const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
                 const int j = c0 + 4 * c;
-                v[j + 0] = __uint_as_float(r[4 * c + 0]) + pv.x + prm[hh * 64 + j + 0] + rv.x;
-                v[j + 1] = __uint_as_float(r[4 * c + 1]) + pv.y + prm[hh * 64 + j + 1] + rv.y;
-                v[j + 2] = __uint_as_float(r[4 * c + 2]) + pv.z + prm[hh * 64 + j + 2] + rv.z;
-                v[j + 3] = __uint_as_float(r[4 * c + 3]) + pv.w + prm[hh * 64 + j + 3] + rv.w;
+                const float4 bv = *reinterpret_cast<const float4*>(prm + hh * 64 + j);
+                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
+                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
+                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
+                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
             }
+        }
+        mbar_wait(recv_bar, 0);   // the peer's partial sum has landed (its flight overlapped the loads above)
+        if (ts_on) FFN_TS(2, tse, 702);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int chunk = hh * 16 + c;
+            const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
+            v[4 * c + 0] += pv.x;
+            v[4 * c + 1] += pv.y;
+            v[4 * c + 2] += pv.z;
+            v[4 * c + 3] += pv.w;
         }
         float mean, m2;
         ln_local_stats(v, mean, m2);
         ln_publish(part1, pidx, row, rank, mean, m2);
     }
     __syncwarp();
+    if (ts_on) FFN_TS(2, tse, 800);
     cluster_sync_all();                                                         // barrier C
+    if (ts_on) FFN_TS(2, tse, 801);
     if (epi) ln_normalise(v, part1, row, prm + 128 + hh * 64, prm + 256 + hh * 64);
+    if (ts_on) FFN_TS(2, tse, 810);
     if (g2) {
         if (epi) {
             float mean, m2;
@@ -1081,16 +1166,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         cluster_sync_all();
         if (epi) ln_normalise(v, part2, row, prm + 384 + hh * 64, prm + 512 + hh * 64);
     }
+    if (ts_on) FFN_TS(2, tse, 811);
     if (epi) {
-        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (idle, not part of recv)
+        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (the send buffer:
+        // the peer has consumed it before it arrived at barrier C)
         ln_store_tiles(v, gen + 2 * hh * 16384, gen + OFF_RING + SLOT + hh * 16384, row);
+        if (ts_on) FFN_TS(2, tse, 820);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (ts_on) FFN_TS(2, tse, 830);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {
+            if (ts_on) FFN_TS(2, tse, 850);
             for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + bx * 16384, n0 + 32 * bx, m0);
             for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + OFF_RING + SLOT + hb * 16384, n0 + 64 * hb, m0);
+            if (ts_on) FFN_TS(2, tse, 860);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (ts_on) FFN_TS(2, tse, 900);
         }
     }
     tcgen05_fence_before();
@@ -1177,7 +1269,25 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
         attr_set = true;
     }
     const int tiles = (rows.max_rows + BM - 1) / BM;
-    launch_pdl(ffn_fused_kernel, dim3(2 * tiles), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F);
+    static const int ffn_dbg = [] { const char* v = getenv("TTB_FFN_DBG"); return v ? atoi(v) : 0; }();
+#ifdef TTB_FFN_TIMELINE
+    {
+        static int n_launch = 0;
+        if (++n_launch == 400) {   // dump the timeline of launch #399 (steady state)
+            cudaStreamSynchronize(s);
+            static long long h[3][256][2];
+            cudaMemcpyFromSymbol(h, g_ffn_ts, sizeof(h));
+            FILE* f = fopen("gpurun_out/ffn_timeline.txt", "w");
+            if (f) {
+                for (int r = 0; r < 3; ++r)
+                    for (int i = 0; i < 256; ++i)
+                        if (h[r][i][1]) fprintf(f, "%d %lld %lld\n", r, h[r][i][0], h[r][i][1]);
+                fclose(f);
+            }
+        }
+    }
+#endif
+    launch_pdl(ffn_fused_kernel, dim3(2 * tiles), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F, ffn_dbg);
     return 0;
 }
 

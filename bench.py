@@ -29,6 +29,10 @@ sys.path.insert(0, str(REPO))
 from translation_transformer_b200.synthetic import synthetic_sources  # noqa: E402
 from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, random_init_state_dict  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+# (kernel class -> bytes); classes without a capture report null
+NCU_TRAFFIC = {"gemm_ffn1": 14.6e6}
+
 PAD, BOS, EOS, REPLACE = 0, 1, 2, 7   # REPLACE plays the role of the "c" token (lightning_model.py:117)
 METRIC = "SMILES/sec (greedy speculative, product prediction)"
 
@@ -130,20 +134,31 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def class_work(name, args, cfg, hist, src_lens_mean):
+def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=True):
     """Algorithmic (flops, bytes) of ALL launches of a kernel class over the iterations in `hist`
-    (live queries per iteration); per-unit figures are in DESIGN.md §4."""
+    (live queries per iteration); per-unit figures are in DESIGN.md §4.  With the fused kernels the
+    sub-layer tails (bias + residual + LayerNorm, fp32 and bf16 copies of the residual stream) are part
+    of the GEMM classes and the whole feed-forward block is the class `gemm_ffn1`."""
     E, F, V, L = cfg.embedding_dim, cfg.feedforward_dim, cfg.tgt_vocab_size, cfg.num_decoder_layers
     per_q = args.n_drafts * (args.draft_len + 1)
     rows = sum(h * per_q for h in hist)           # token rows summed over iterations
     ab = 2 if args.precision == "bf16" else 4      # activation bytes
+    n_it = len(hist)
+    ln_flops = 8.0 * rows * E
+    stream_bytes = rows * E * (4 + 4 + ab)          # residual in, residual out (fp32), low-precision copy out
+    if name == "gemm_ffn1" and fused_ffn:
+        return (4.0 * rows * E * F + ln_flops) * L, (rows * E * ab + stream_bytes) * L + 2 * E * F * ab * L * n_it
+    if name in ("gemm_self_out", "gemm_cross_out") and fused_ln:
+        return (2.0 * rows * E * E + ln_flops) * L, (rows * E * ab + stream_bytes) * L + E * E * ab * L * n_it
+    if name == "gemm_ffn2" and fused_ln:
+        return (2.0 * rows * E * F + ln_flops) * L, (rows * F * ab + stream_bytes) * L + E * F * ab * L * n_it
     gemm = {"gemm_qkv": (E, 3 * E, ab), "gemm_self_out": (E, E, 4), "gemm_cross_q": (E, E, ab), "gemm_cross_out": (E, E, 4),
             "gemm_ffn1": (E, F, ab), "gemm_ffn2": (F, E, 4)}
     if name in gemm:
         K, N, ob = gemm[name]
-        return 2.0 * rows * K * N * L, (rows * K * ab + rows * N * ob) * L + K * N * ab * L * len(hist)
+        return 2.0 * rows * K * N * L, (rows * K * ab + rows * N * ob) * L + K * N * ab * L * n_it
     if name == "gemm_classifier":
-        return 2.0 * rows * E * V, rows * E * ab + rows * V * 4 + E * V * ab * len(hist)
+        return 2.0 * rows * E * V, rows * E * ab + rows * V * 4 + E * V * ab * n_it
     if name == "cross_attn":
         lk = src_lens_mean
         return 4.0 * rows * lk * E * L, (rows * E * ab * 2 + sum(hist) * lk * 2 * E * ab) * L
@@ -208,6 +223,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd = build_weights(args)
     eng = B200Transformer(cfg, sd, precision=args.precision, device=local_rank)
@@ -304,8 +321,10 @@ def main():
         peaks = measured_peaks()
         src_lens_mean = float((host[args.warmup + args.steps] != PAD).sum().item()) / args.batch_size
         flops = byts = 0.0
+        fused_ln = "add_layernorm" not in shares
+        fused_ffn = "gemm_ffn2" not in shares
         for h in hists:
-            f, b = class_work(dominant, args, cfg, h, src_lens_mean)
+            f, b = class_work(dominant, args, cfg, h, src_lens_mean, fused_ln, fused_ffn)
             flops += f
             byts += b
         intensity = flops / max(byts, 1.0)
@@ -315,7 +334,12 @@ def main():
             roof = {"bound": "tensor", "achieved": flops / dom_s / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
         else:
             roof = {"bound": "hbm", "achieved": byts / dom_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-        roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": None, "kernel": dominant,
+        label = {"gemm_ffn1": "ffn_fused_kernel (FFN1+ReLU+FFN2+residual+LayerNorm)" if fused_ffn else "gemm_ffn1",
+                 "gemm_self_out": "gemm_resid_ln_kernel (self out-proj)" if fused_ln else "gemm_self_out",
+                 "gemm_cross_out": "gemm_resid_ln_kernel (cross out-proj)" if fused_ln else "gemm_cross_out"}.get(dominant, dominant)
+        overhead_us = 1000.0 * shares["misc"]["ms"] / shares["misc"]["launches"] if "misc" in shares else None
+        roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": NCU_TRAFFIC.get(dominant), "kernel": label, "kernel_class": dominant,
+                     "event_bracket_us_of_a_trivial_kernel": overhead_us,
                      "launches": dom_launches, "avg_launch_us": 1000.0 * dom_ms / max(dom_launches, 1),
                      "algorithmic_flops_per_launch": flops / max(dom_launches, 1), "algorithmic_bytes_per_launch": byts / max(dom_launches, 1),
                      "peak_source": peaks["source"], "share_of_step": shares[dominant]["share"],

@@ -66,6 +66,7 @@ struct Params {
     const int* key_tok; int key_tok_stride; int pad_id;
     int causal;
     const int* lk_dev;                           // when set: Lk = kv_group_stride = key_tok_stride = *lk_dev (graph replay)
+    const int* lk_group;                         // optional [kv group]: keys behind it are padding (never unmasked)
     float scale_log2e;
     // speculative self-attention
     int spec;
@@ -92,11 +93,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Stage rows [0, nk) of a K/V source into a tile (asynchronously) and zero rows [nk, round-up-32(nk)).
+// Stage rows [0, nk) of a K/V source into a tile (asynchronously) and zero rows [nk, nfill).
 template <int HD>
-__device__ __forceinline__ void stage_rows(const Tile<HD>& t, const __nv_bfloat16* ksrc, const __nv_bfloat16* vsrc, int ld, int nk) {
+__device__ __forceinline__ void stage_rows(const Tile<HD>& t, const __nv_bfloat16* ksrc, const __nv_bfloat16* vsrc, int ld, int nk, int nfill) {
     constexpr int CH = HD / 8, PITCH = Tile<HD>::PITCH;
-    const int nfill = (nk + 31) & ~31;
     for (int idx = threadIdx.x; idx < nfill * CH; idx += THREADS) {
         const int j = idx / CH, c = idx % CH;
         __nv_bfloat16* kd = t.k + j * PITCH + c * 8;
@@ -212,7 +212,8 @@ attn_mma_kernel(Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kvg = p.spec ? p.active[g] : (p.kvmap ? p.kvmap[g] : g);
     const int dynLk = p.lk_dev ? *p.lk_dev : 0;
-    const int Lk = p.spec ? p.front[kvg] : (p.lk_dev ? dynLk : p.Lk);
+    const int Lk_all = p.spec ? p.front[kvg] : (p.lk_dev ? dynLk : p.Lk);
+    const int Lk = (!p.spec && p.lk_group) ? min(Lk_all, p.lk_group[kvg]) : Lk_all;
     const long long kv_group_stride = p.lk_dev ? dynLk : p.kv_group_stride;
     const int key_tok_stride = p.lk_dev ? dynLk : p.key_tok_stride;
     const int* key_tok = p.spec ? p.gen + (long long)kvg * p.gen_ld : (p.key_tok ? p.key_tok + (long long)kvg * key_tok_stride : nullptr);
@@ -237,8 +238,8 @@ attn_mma_kernel(Params p) {
         auto stage_A = [&](int j0) {
             const int nk = min(KTA, kA_end - j0);
             if (nk <= 0) return;
-            stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk);
             const int nfill = (nk + 31) & ~31;
+            stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk, nfill);
             int last = 0;
             for (int j = threadIdx.x; j < nfill; j += THREADS) {
                 const bool ok = j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id);
@@ -253,11 +254,14 @@ attn_mma_kernel(Params p) {
         const int firstB = (blk0 / RL) * RL;   // start of the draft row that contains the CTA's first query
         const __nv_bfloat16* nkb = p.spec ? p.newk + (long long)g * p.Lq * p.new_ld + h * HD : nullptr;
         const __nv_bfloat16* nvb = p.spec ? p.newv + (long long)g * p.Lq * p.new_ld + h * HD : nullptr;
+        // short draft rows (<= 17 tokens): the keys an m16 query tile can see span at most 32 consecutive rows, so
+        // each tile runs ONE 32-key block that starts at its first draft row instead of walking aligned blocks
+        const bool fastB = p.spec && RL <= 17 && endB - firstB <= KTB;
         auto stage_B = [&](int u0) {
             const int nk = min(KTB, endB - u0);
             if (nk <= 0) return;
-            stage_rows<HD>(tileB, nkb + (long long)u0 * p.new_ld, nvb + (long long)u0 * p.new_ld, p.new_ld, nk);
-            const int nfill = (nk + 31) & ~31;
+            const int nfill = fastB ? KTB : ((nk + 31) & ~31);
+            stage_rows<HD>(tileB, nkb + (long long)u0 * p.new_ld, nvb + (long long)u0 * p.new_ld, p.new_ld, nk, nfill);
             for (int j = threadIdx.x; j < nfill; j += THREADS) {
                 const bool bad = j >= nk || (first_new_masked && ((u0 + j) % RL) == 0);
                 tileB.bias[j] = bad ? -INFINITY : 0.f;
@@ -321,7 +325,23 @@ attn_mma_kernel(Params p) {
         }
 
         // ---- phase B ------------------------------------------------------------------------------
-        if (p.spec) {
+        if (fastB) {
+            if (warp_live) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int row0 = wrow0 + mt * 16;
+                    if (row0 >= p.Lq) continue;
+                    const int kstart = (row0 / RL) * RL;      // first key row the tile can see
+                    const int rowA = row0 + rA;
+                    const int startA = (rowA / RL) * RL, startB = ((rowA + 8) / RL) * RL;
+                    process_block<HD>(tileB, kstart - firstB, qa[mt], o[mt], m[mt][0], m[mt][1], l[mt][0], l[mt][1], p.scale_log2e, lane,
+                                      [&](int rs, int col) {
+                                          const int qr = rowA + rs * 8, kr = kstart + col;
+                                          return kr < (rs ? startB : startA) || kr > qr;
+                                      });
+                }
+            }
+        } else if (p.spec) {
             const int lo = warp_live ? (wrow0 / RL) * RL : 0;
             const int hi = warp_live ? min(p.Lq, (wrow_last / RL + 1) * RL) : 0;
             for (int u0 = firstB; u0 < endB; u0 += KTB) {
@@ -398,10 +418,11 @@ void launch_attention_mma(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16*
                           __nv_bfloat16* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                           int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                           const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                          int heads, int head_dim, cudaStream_t s, const int* lk_dev) {
+                          int heads, int head_dim, cudaStream_t s, const int* lk_dev, const int* lk_group) {
     if (n_groups_max <= 0 || Lq <= 0) return;
     amma::Params p{};
     p.lk_dev = lk_dev;
+    p.lk_group = lk_group;
     p.q = q; p.q_ld = q_ld; p.k = k; p.v = v; p.kv_ld = kv_ld; p.out = out; p.out_ld = out_ld;
     p.n_groups_dev = n_groups_dev; p.Lq = Lq; p.Lk = Lk; p.kv_group_stride = kv_group_stride; p.kvmap = kvmap;
     p.key_tok = key_tok; p.key_tok_stride = key_tok_stride; p.pad_id = pad_id; p.causal = causal ? 1 : 0;

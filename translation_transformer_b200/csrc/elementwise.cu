@@ -219,6 +219,21 @@ void launch_add_layernorm(const float* resid, const float* y, const float* g, co
 template void launch_add_layernorm<float>(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, RowCount, int, cudaStream_t);
 template void launch_add_layernorm<__nv_bfloat16>(const float*, const float*, const float*, const float*, const float*, const float*, float*, __nv_bfloat16*, RowCount, int, cudaStream_t);
 
+__global__ void row_lengths_kernel(const int* __restrict__ tok, int L, int pad_id, int* __restrict__ out) {
+    __shared__ int s_len;
+    if (threadIdx.x == 0) s_len = 0;
+    __syncthreads();
+    int last = 0;
+    for (int j = threadIdx.x; j < L; j += blockDim.x)
+        if (tok[(long long)blockIdx.x * L + j] != pad_id) last = j + 1;
+    if (last) atomicMax(&s_len, last);
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = s_len;
+}
+void launch_row_lengths(const int* tok, int B, int L, int pad_id, int* out, cudaStream_t s) {
+    if (B > 0) row_lengths_kernel<<<B, 128, 0, s>>>(tok, L, pad_id, out);
+}
+
 // ---- argmax over the vocabulary (first maximal index, like torch.argmax) ----------------------
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int V, int* __restrict__ out, RowCount rows) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

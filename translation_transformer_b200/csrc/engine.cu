@@ -124,7 +124,7 @@ struct ttb_engine {
     // forward workspace (typed by the precision's activation type at use)
     DevBuf x, xh, y, qkv, att, q2, hid, logits, tok32, keytok32, pred;
     // encoder products / decoding state
-    DevBuf src32, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
+    DevBuf src32, srclen, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
     int* h_ctrl = nullptr;  // pinned snapshots of ctrl for lagged polling
     cudaEvent_t poll_ev[4]{};
     cudaEvent_t t0{}, t1{};
@@ -324,16 +324,16 @@ static bool attn_simt_forced() {
 }
 static void attn(const float* q, int q_ld, const float* k, const float* v, int kv_ld, float* out, int out_ld, int ng, const int* ng_dev,
                  int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad, bool causal, int H, int HD, cudaStream_t s,
-                 const int* lk_dev = nullptr) {
+                 const int* lk_dev = nullptr, const int* = nullptr) {
     launch_attention<float>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
 }
 static void attn(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* k, const __nv_bfloat16* v, int kv_ld, __nv_bfloat16* out, int out_ld,
                  int ng, const int* ng_dev, int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad,
-                 bool causal, int H, int HD, cudaStream_t s, const int* lk_dev = nullptr) {
+                 bool causal, int H, int HD, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr) {
     if (attn_simt_forced())
         launch_attention<__nv_bfloat16>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
     else
-        launch_attention_mma(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
+        launch_attention_mma(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev, lk_group);
 }
 static void spec_attn(const float* qkv, int ld, const float* kc, const float* vc, long long cqs, int cld, float* out, int old, int B,
                       const int* na, const int* active, const int* front, const int* gen, int gen_ld, int pad, int N, int D, int H,
@@ -531,7 +531,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     const int max_iters = max_len + 1;
 
     // encoder + cross-attention K/V (computed once per query, not once per draft row and iteration)
-    if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float))) return 1;
+    if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float)) || e->srclen.ensure((size_t)B * sizeof(int))) return 1;
     if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
     if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
     if (e->kcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT)) || e->vcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT))) return 1;
@@ -544,6 +544,8 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     TTB_CUDA_OK(cudaEventRecord(e->t0, s));
     int* src32 = e->src32.as<int>();
     { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s); }
+    // per-query source length: the cross-attention kernels skip the padding behind it
+    { Scope sc(e, KC_MISC, s); launch_row_lengths(src32, B, Ls, e->d.src_pad_token_idx, e->srclen.as<int>(), s); }
     float* mem = e->memory.as<float>();
     ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
@@ -576,7 +578,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
         const ActT* kv = crosskv + (long long)l * TS_cap * 2 * E;
         attn(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
-             src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS);
+             src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS, e->srclen.as<int>());
     };
 
     auto enqueue_iteration = [&]() -> int {

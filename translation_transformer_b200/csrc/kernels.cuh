@@ -20,6 +20,8 @@ struct RowCount {
 void launch_i64_to_i32(const long long* in, int* out, long long n, cudaStream_t s);
 void launch_i32_to_i64(const int* in, long long* out, long long n, cudaStream_t s);
 void launch_mask_to_tokens(const unsigned char* mask, int* out, long long n, int pad_id, cudaStream_t s);
+// out[b] = 1 + index of the last token of row b that differs from pad_id (0 for an all-pad row)
+void launch_row_lengths(const int* tok, int B, int L, int pad_id, int* out, cudaStream_t s);
 // x[t] = table[tok[t]] + pe[(t % L) + 1]; also writes the low-precision copy when xh != nullptr
 template <typename ActT>
 void launch_embed_seq(const int* tok, int T, int L, const float* table, const float* pe, int E,
@@ -80,7 +82,7 @@ void launch_attention_mma(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16*
                           __nv_bfloat16* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                           int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                           const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                          int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr);
+                          int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr);
 void launch_spec_self_attention_mma(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                                     long long cache_query_stride, int cache_ld, __nv_bfloat16* out, int out_ld,
                                     int B_max, const int* n_active_dev, const int* active, const int* front,

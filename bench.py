@@ -31,7 +31,8 @@ from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
 # (kernel class -> bytes); classes without a capture report null
-NCU_TRAFFIC = {"gemm_ffn1": 14.6e6}
+NCU_TRAFFIC = {"gemm_ffn1": 14.6e6, "gemm_self_out": 12.6e6, "gemm_cross_out": 12.6e6, "self_attn": 13.2e6, "cross_attn": 7.0e6,
+               "gemm_qkv": 4.6e6, "gemm_cross_q": 4.3e6}   # profiles/r1e_top_kernels_ncu_full.txt
 
 PAD, BOS, EOS, REPLACE = 0, 1, 2, 7   # REPLACE plays the role of the "c" token (lightning_model.py:117)
 METRIC = "SMILES/sec (greedy speculative, product prediction)"

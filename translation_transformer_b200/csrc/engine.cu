@@ -584,8 +584,21 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     auto enqueue_iteration = [&]() -> int {
         { Scope sc(e, KC_EMBED, s); launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s); }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
-        if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
-        { Scope sc(e, KC_ARGMAX, s); launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s); }
+        bool fused_cls = false;
+        if constexpr (Prec<ActT>::lowp) {
+            static const bool off = [] { const char* v = getenv("TTB_NO_FUSED_ARGMAX"); return v && v[0] == '1'; }();
+            if (!off) {
+                Scope sc(e, KC_GEMM_CLASSIFIER, s);
+                const int rc = launch_classifier_argmax(xh, E, e->classifier.wh, e->classifier.b, st.pred, rows, V, E, s);
+                if (rc > 0) return 1;
+                fused_cls = rc == 0;
+                if (!fused_cls) e->launches--;
+            }
+        }
+        if (!fused_cls) {
+            if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
+            { Scope sc(e, KC_ARGMAX, s); launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s); }
+        }
         { Scope sc(e, KC_ACCEPT, s); launch_greedy_accept(st, s); }
         {
             Scope sc(e, KC_CACHE_APPEND, s);

@@ -1191,6 +1191,126 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
+
+// =====================================================================================================
+// Vocabulary projection + arg-max for the greedy loop:  pred[row] = argmax_v (xh[row] . Wc[v] + bc[v])
+// (first maximal index, like torch.argmax).  The logits never leave the SM: one CTA per 128 rows keeps
+// the whole [V x K] classifier weight and its A tile in shared memory (K = 256: 64 KB + 144 KB for V = 288),
+// accumulates all V_pad <= 512 columns in TMEM (one N <= 256 MMA group plus a tail group), and each row's
+// maximum is found by two threads scanning disjoint column ranges straight out of TMEM.
+namespace cls {
+constexpr int THREADS = 320;
+}
+__global__ void __launch_bounds__(cls::THREADS, 1)
+classifier_argmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                         const __grid_constant__ CUtensorMap tmWtail, const float* __restrict__ bias, int* __restrict__ pred,
+                         RowCount rows, int V, int V_pad, int KB) {
+    const int m0 = blockIdx.x * BM;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    const int w_kb_bytes = V_pad * 128;                       // one K-block of the weight: V_pad rows x 64 bf16
+    const uint32_t w_base = base + KB * A_BYTES;
+    float* bias_sm = reinterpret_cast<float*>(gen + KB * A_BYTES + KB * w_kb_bytes);
+    float2* half_best = reinterpret_cast<float2*>(bias_sm + V_pad);
+    const uint32_t bar_base = base + KB * A_BYTES + KB * w_kb_bytes + V_pad * 4 + BM * 8;
+    auto full_bar = [&](int kb) { return bar_base + 8u * kb; };
+    const uint32_t tfull_bar = bar_base + 8u * 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar_base - base) + 8 * 17);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_main = V_pad < 256 ? V_pad : 256, n_tail = V_pad - n_main;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWtail)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) mbar_init(full_bar(kb), 1);
+            mbar_init(tfull_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2)
+        for (int c = threadIdx.x - 64; c < V_pad; c += 256) bias_sm[c] = (bias && c < V) ? __ldg(bias + c) : 0.f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int M = rows.live();
+    const bool live = m0 < M;
+
+    if (warp == 0) {
+        if (lane == 0 && live) {  // ===== TMA producer: everything at once, one barrier per K-block =====
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_expect_tx(full_bar(kb), A_BYTES + w_kb_bytes);
+                tma_load_2d(base + kb * A_BYTES, &tmA, kb * BK, m0, full_bar(kb));
+                const uint32_t wdst = w_base + kb * w_kb_bytes;
+                int r0 = 0;
+                for (; r0 + 128 <= V_pad; r0 += 128) tma_load_2d(wdst + r0 * 128, &tmW, kb * BK, r0, full_bar(kb));
+                if (r0 < V_pad) tma_load_2d(wdst + r0 * 128, &tmWtail, kb * BK, r0, full_bar(kb));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && live) {  // ===== MMA issuer =====
+            const uint32_t idesc_main = umma_idesc_bf16(BM, n_main);
+            const uint32_t idesc_tail = umma_idesc_bf16(BM, n_tail > 0 ? n_tail : 16);
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(full_bar(kb), 0);
+                tcgen05_fence_after();
+                const uint32_t a_src = base + kb * A_BYTES, b_src = w_base + kb * w_kb_bytes;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(a_src + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, adesc, umma_desc_sw128(b_src + k * UMMA_K * 2), idesc_main, (kb | k) != 0 ? 1u : 0u);
+                    if (n_tail > 0)
+                        umma_bf16(tmem_base + 256u, adesc, umma_desc_sw128(b_src + 256 * 128 + k * UMMA_K * 2), idesc_tail, (kb | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else if (live) {  // ===== arg-max: thread = (row, column range) =====
+        const int q = warp & 3, hh = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int n32 = V_pad / 32, c_half = (n32 + 1) / 2;
+        const int c_begin = hh == 0 ? 0 : c_half, c_end = hh == 0 ? c_half : n32;
+        float best = -INFINITY;
+        int bi = c_begin * 32;
+        mbar_wait(tfull_bar, 0);
+        tcgen05_fence_after();
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                const float v = __uint_as_float(r[j]) + bias_sm[col];
+                if (col < V && v > best) { best = v; bi = col; }
+            }
+        }
+        if (hh == 1) half_best[row] = make_float2(best, __int_as_float(bi));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (hh == 0) {
+            if (c_end < n32) {   // columns of the upper half exist: a strictly larger value there wins
+                const float2 o = half_best[row];
+                if (o.x > best) { best = o.x; bi = __float_as_int(o.y); }
+            }
+            if (m0 + row < M) pred[m0 + row] = bi;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
 }  // namespace tc
 
 template <typename OutT>
@@ -1245,6 +1365,35 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     gemm_bf16_tc_kernel<OutT><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
     return 0;
 }
+// returns 0 on success, -1 when the shape does not fit the fused kernel (caller falls back to GEMM + argmax)
+int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int* pred, RowCount rows,
+                             int V, int K, cudaStream_t s) {
+    using namespace tc;
+    if (rows.max_rows <= 0) return 0;
+    const int V_pad = (V + 31) / 32 * 32, KB = K / BK;
+    const int smem = KB * A_BYTES + KB * V_pad * 128 + V_pad * 4 + BM * 8 + 8 * 18 + 64 + 1024;
+    if (K % BK != 0 || KB > 16 || V_pad > 512 || smem > 227 * 1024 || lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) ||
+        (reinterpret_cast<uintptr_t>(W) & 15))
+        return -1;
+    CUtensorMap tmA, tmW, tmWtail;
+    if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
+    const int tail_rows = V_pad % 128 ? V_pad % 128 : 128;
+    if (int rc = get_tensor_map(W, V, K, K, V_pad >= 128 ? 128 : tail_rows, &tmW)) return rc;
+    if (int rc = get_tensor_map(W, V, K, K, tail_rows, &tmWtail)) return rc;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(classifier_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        attr_smem = smem;
+    }
+    const int tiles = (rows.max_rows + BM - 1) / BM;
+    launch_pdl(classifier_argmax_kernel, dim3(tiles), dim3(cls::THREADS), (size_t)smem, s, tmA, tmW, tmWtail, bias, pred, rows, V, V_pad, KB);
+    return 0;
+}
+
 int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,
                      float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s) {
     using namespace tc;

@@ -49,6 +49,11 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
 int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
                          const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s);
 
+// Vocabulary projection fused with arg-max (greedy loop, bf16 path): pred[row] = argmax_v(A[row] . W[v] + bias[v]).
+// Returns -1 when the shape does not fit the kernel (K % 64, V <= 512, shared memory) so the caller can fall back.
+int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int* pred, RowCount rows,
+                             int V, int K, cudaStream_t s);
+
 // Fused feed-forward sub-layer for embedding_dim 256 (bf16 path):
 //   x <- LN2?(LN1(x + relu(xh W1^T + b1) W2^T + b2)), x fp32 and its bf16 copy xh both updated in place.
 int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,

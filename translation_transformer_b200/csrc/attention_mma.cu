@@ -67,6 +67,7 @@ struct Params {
     int causal;
     const int* lk_dev;                           // when set: Lk = kv_group_stride = key_tok_stride = *lk_dev (graph replay)
     const int* lk_group;                         // optional [kv group]: keys behind it are padding (never unmasked)
+    const int4* desc;                            // optional per-slot descriptor {kv group, front, token at front, key bound}
     float scale_log2e;
     // speculative self-attention
     int spec;
@@ -210,14 +211,16 @@ attn_mma_kernel(Params p) {
     tileA.bias = reinterpret_cast<float*>(tileB.v + KTB * PITCH);
     tileB.bias = tileA.bias + KTA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kvg = p.spec ? p.active[g] : (p.kvmap ? p.kvmap[g] : g);
+    int4 dsc = make_int4(0, 0, 0, 0x7fffffff);
+    if (p.desc) dsc = p.desc[g];
+    const int kvg = p.desc ? dsc.x : (p.spec ? p.active[g] : (p.kvmap ? p.kvmap[g] : g));
     const int dynLk = p.lk_dev ? *p.lk_dev : 0;
-    const int Lk_all = p.spec ? p.front[kvg] : (p.lk_dev ? dynLk : p.Lk);
-    const int Lk = (!p.spec && p.lk_group) ? min(Lk_all, p.lk_group[kvg]) : Lk_all;
+    const int Lk_all = p.spec ? (p.desc ? dsc.y : p.front[kvg]) : (p.lk_dev ? dynLk : p.Lk);
+    const int Lk = p.spec ? Lk_all : (p.desc ? min(Lk_all, dsc.w) : (p.lk_group ? min(Lk_all, p.lk_group[kvg]) : Lk_all));
     const long long kv_group_stride = p.lk_dev ? dynLk : p.kv_group_stride;
     const int key_tok_stride = p.lk_dev ? dynLk : p.key_tok_stride;
     const int* key_tok = p.spec ? p.gen + (long long)kvg * p.gen_ld : (p.key_tok ? p.key_tok + (long long)kvg * key_tok_stride : nullptr);
-    const bool first_new_masked = p.spec ? (p.gen[(long long)kvg * p.gen_ld + Lk] == p.pad_id) : false;
+    const bool first_new_masked = p.spec ? ((p.desc ? dsc.z : p.gen[(long long)kvg * p.gen_ld + Lk]) == p.pad_id) : false;
     const __nv_bfloat16* kbase = p.k + (long long)kvg * kv_group_stride * p.kv_ld + h * HD;
     const __nv_bfloat16* vbase = p.v + (long long)kvg * kv_group_stride * p.kv_ld + h * HD;
     const int rA = lane >> 2, c0 = (lane & 3) * 2;
@@ -418,11 +421,12 @@ void launch_attention_mma(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16*
                           __nv_bfloat16* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                           int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                           const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                          int heads, int head_dim, cudaStream_t s, const int* lk_dev, const int* lk_group) {
+                          int heads, int head_dim, cudaStream_t s, const int* lk_dev, const int* lk_group, const int4* desc) {
     if (n_groups_max <= 0 || Lq <= 0) return;
     amma::Params p{};
     p.lk_dev = lk_dev;
     p.lk_group = lk_group;
+    p.desc = desc;
     p.q = q; p.q_ld = q_ld; p.k = k; p.v = v; p.kv_ld = kv_ld; p.out = out; p.out_ld = out_ld;
     p.n_groups_dev = n_groups_dev; p.Lq = Lq; p.Lk = Lk; p.kv_group_stride = kv_group_stride; p.kvmap = kvmap;
     p.key_tok = key_tok; p.key_tok_stride = key_tok_stride; p.pad_id = pad_id; p.causal = causal ? 1 : 0;
@@ -435,10 +439,11 @@ void launch_spec_self_attention_mma(const __nv_bfloat16* qkv, int qkv_ld, const 
                                     long long cache_query_stride, int cache_ld, __nv_bfloat16* out, int out_ld,
                                     int B_max, const int* n_active_dev, const int* active, const int* front,
                                     const int* gen, int gen_ld, int pad_id, int N, int D,
-                                    int heads, int head_dim, cudaStream_t s) {
+                                    int heads, int head_dim, cudaStream_t s, const int4* desc) {
     if (B_max <= 0) return;
     const int E = heads * head_dim;
     amma::Params p{};
+    p.desc = desc;
     p.q = qkv; p.q_ld = qkv_ld; p.k = kcache; p.v = vcache; p.kv_ld = cache_ld; p.out = out; p.out_ld = out_ld;
     p.n_groups_dev = n_active_dev; p.Lq = N * (D + 1); p.Lk = 0;
     p.kv_group_stride = cache_query_stride / cache_ld;   // rows per query in the cache

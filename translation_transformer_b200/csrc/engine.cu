@@ -124,7 +124,7 @@ struct ttb_engine {
     // forward workspace (typed by the precision's activation type at use)
     DevBuf x, xh, y, qkv, att, q2, hid, logits, tok32, keytok32, pred;
     // encoder products / decoding state
-    DevBuf src32, srclen, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
+    DevBuf src32, srclen, desc, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
     int* h_ctrl = nullptr;  // pinned snapshots of ctrl for lagged polling
     cudaEvent_t poll_ev[4]{};
     cudaEvent_t t0{}, t1{};
@@ -324,29 +324,30 @@ static bool attn_simt_forced() {
 }
 static void attn(const float* q, int q_ld, const float* k, const float* v, int kv_ld, float* out, int out_ld, int ng, const int* ng_dev,
                  int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad, bool causal, int H, int HD, cudaStream_t s,
-                 const int* lk_dev = nullptr, const int* = nullptr) {
+                 const int* lk_dev = nullptr, const int* = nullptr, const int4* = nullptr) {
     launch_attention<float>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
 }
 static void attn(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* k, const __nv_bfloat16* v, int kv_ld, __nv_bfloat16* out, int out_ld,
                  int ng, const int* ng_dev, int Lq, int Lk, long long kvs, const int* kvmap, const int* key_tok, int kts, int pad,
-                 bool causal, int H, int HD, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr) {
+                 bool causal, int H, int HD, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr,
+                 const int4* desc = nullptr) {
     if (attn_simt_forced())
         launch_attention<__nv_bfloat16>(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev);
     else
-        launch_attention_mma(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev, lk_group);
+        launch_attention_mma(q, q_ld, k, v, kv_ld, out, out_ld, ng, ng_dev, Lq, Lk, kvs, kvmap, key_tok, kts, pad, causal, H, HD, s, lk_dev, lk_group, desc);
 }
 static void spec_attn(const float* qkv, int ld, const float* kc, const float* vc, long long cqs, int cld, float* out, int old, int B,
                       const int* na, const int* active, const int* front, const int* gen, int gen_ld, int pad, int N, int D, int H,
-                      int HD, int P, cudaStream_t s) {
+                      int HD, int P, cudaStream_t s, const int4* = nullptr) {
     launch_spec_self_attention<float>(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, P, s);
 }
 static void spec_attn(const __nv_bfloat16* qkv, int ld, const __nv_bfloat16* kc, const __nv_bfloat16* vc, long long cqs, int cld,
                       __nv_bfloat16* out, int old, int B, const int* na, const int* active, const int* front, const int* gen,
-                      int gen_ld, int pad, int N, int D, int H, int HD, int P, cudaStream_t s) {
+                      int gen_ld, int pad, int N, int D, int H, int HD, int P, cudaStream_t s, const int4* desc = nullptr) {
     if (attn_simt_forced())
         launch_spec_self_attention<__nv_bfloat16>(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, P, s);
     else
-        launch_spec_self_attention_mma(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, s);
+        launch_spec_self_attention_mma(qkv, ld, kc, vc, cqs, cld, out, old, B, na, active, front, gen, gen_ld, pad, N, D, H, HD, s, desc);
 }
 
 // GEMM A-operand view of the residual stream: fp32 path reads x itself, bf16 path its bf16 copy
@@ -538,6 +539,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     if (e->drafts.ensure((size_t)B * N * D * sizeof(int)) || e->gen.ensure((size_t)B * gen_ld * sizeof(int))) return 1;
     if (e->front.ensure(B * sizeof(int)) || e->active.ensure(B * sizeof(int)) || e->ctrl.ensure(CTRL_COUNT * sizeof(int))) return 1;
     if (e->sel.ensure((size_t)B * 4 * sizeof(int)) || e->out64.ensure((size_t)B * max_len * sizeof(long long))) return 1;
+    if (e->desc.ensure((size_t)B * sizeof(int4))) return 1;
     if (e->hist.ensure((size_t)(max_iters + 1) * sizeof(int))) return 1;
     if (ensure_work<ActT>(e, std::max(T, TS_cap), n_dec)) return 1;
 
@@ -559,6 +561,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     st.gen = e->gen.as<int>(); st.front = e->front.as<int>(); st.active = e->active.as<int>(); st.ctrl = e->ctrl.as<int>();
     st.drafts = e->drafts.as<int>(); st.pred = e->pred.as<int>(); st.out = e->out64.as<long long>();
     st.sel = e->sel.as<int>(); st.trace = trace_dev; st.tie_break = tie_break; st.hist = e->hist.as<int>();
+    st.desc = e->desc.as<int4>(); st.src_len = e->srclen.as<int>();
     { Scope sc(e, KC_MISC, s); launch_greedy_init(st, s); }
 
     float* x = e->x.as<float>();
@@ -573,16 +576,20 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     auto self_attn = [&](int l, ActT* qkv, ActT* att) {
         spec_attn(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
                                          att, E, B, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
-                                         N, D, H, HD, P, s);
+                                         N, D, H, HD, P, s, st.desc);
     };
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
         const ActT* kv = crosskv + (long long)l * TS_cap * 2 * E;
         attn(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
-             src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS, e->srclen.as<int>());
+             src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS, e->srclen.as<int>(), st.desc);
     };
 
     auto enqueue_iteration = [&]() -> int {
-        { Scope sc(e, KC_EMBED, s); launch_greedy_embed<ActT>(st, e->tgt_emb, e->pe, E, x, xh, s); }
+        {   // KV-cache append of the previous iteration's accepted tokens + embedding of this iteration's step tokens
+            Scope sc(e, KC_EMBED, s);
+            launch_greedy_advance<ActT>(st, e->tgt_emb, e->pe, E, x, xh, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, kc, vc,
+                                        cache_l_stride, cache_q_stride, E, s);
+        }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
         bool fused_cls = false;
         if constexpr (Prec<ActT>::lowp) {
@@ -600,11 +607,6 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
             { Scope sc(e, KC_ARGMAX, s); launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s); }
         }
         { Scope sc(e, KC_ACCEPT, s); launch_greedy_accept(st, s); }
-        {
-            Scope sc(e, KC_CACHE_APPEND, s);
-            launch_greedy_cache_append<ActT>(st, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, E, kc, vc, cache_l_stride,
-                                             cache_q_stride, E, s);
-        }
         return 0;
     };
 

@@ -62,7 +62,11 @@ __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     for (long long idx = threadIdx.x; idx < (long long)st.B * st.gen_ld; idx += blockDim.x)
         st.gen[idx] = (idx % st.gen_ld == 0) ? st.bos : st.pad;
     for (long long idx = threadIdx.x; idx < (long long)st.B * st.max_len; idx += blockDim.x) st.out[idx] = st.pad;
-    for (int b = threadIdx.x; b < st.B; b += blockDim.x) { st.front[b] = 0; st.active[b] = b; }
+    for (int b = threadIdx.x; b < st.B; b += blockDim.x) {
+        st.front[b] = 0;
+        st.active[b] = b;
+        st.desc[b] = make_int4(b, 0, st.bos, st.src_len ? st.src_len[b] : 0x7fffffff);
+    }
     if (threadIdx.x < CTRL_COUNT) st.ctrl[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) { st.ctrl[CTRL_N_ACTIVE] = st.B; st.ctrl[CTRL_LS] = st.Ls; }
@@ -72,20 +76,40 @@ void launch_greedy_init(const GreedyState& st, cudaStream_t s) {
     greedy_init_kernel<<<1, 256, (size_t)st.gen_ld * sizeof(int), s>>>(st);
 }
 
-// ---- step-token embedding ---------------------------------------------------------------------
+// ---- first kernel of an iteration: KV-cache append of the previous iteration + step-token embedding ----------
 template <typename ActT>
-__global__ void greedy_embed_kernel(GreedyState st, const float* __restrict__ table, const float* __restrict__ pe,
-                                    int E, float* __restrict__ x, ActT* __restrict__ xh) {
+__global__ void greedy_advance_kernel(GreedyState st, const float* __restrict__ table, const float* __restrict__ pe,
+                                      int E, float* __restrict__ x, ActT* __restrict__ xh, int n_embed_blocks,
+                                      const ActT* __restrict__ qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld,
+                                      ActT* __restrict__ kcache, ActT* __restrict__ vcache, long long cache_layer_stride,
+                                      long long cache_query_stride, int cache_ld) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (st.ctrl[CTRL_DONE]) return;   // after DONE neither the cache nor the embeddings are read again
+    if ((int)blockIdx.x >= n_embed_blocks) {
+        // K/V of the accepted positions of the chosen draft (recorded in st.sel by the accept kernel) -> cache
+        const int idx = blockIdx.x - n_embed_blocks;
+        const int g = idx / n_layers, l = idx % n_layers;
+        if (g >= st.ctrl[CTRL_N_SEL]) return;
+        const int b = st.sel[g * 4 + 0], f = st.sel[g * 4 + 1], pick = st.sel[g * 4 + 2], a = st.sel[g * 4 + 3];
+        const ActT* src = qkv_all + (long long)l * qkv_layer_stride + ((long long)g * st.N + pick) * (st.D + 1) * qkv_ld;
+        ActT* kd = kcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
+        ActT* vd = vcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
+        for (int i2 = threadIdx.x; i2 < (a + 1) * E; i2 += blockDim.x) {
+            const int i = i2 / E, c = i2 % E;
+            kd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + E + c];
+            vd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + 2 * E + c];
+        }
+        return;
+    }
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int per_q = st.N * (st.D + 1);
-    pdl_launch_dependents();
-    pdl_wait();
-    if (st.ctrl[CTRL_DONE] || t >= st.ctrl[CTRL_N_ACTIVE] * per_q) return;
+    if (t >= st.ctrl[CTRL_N_ACTIVE] * per_q) return;
     const int g = t / per_q, r = t % per_q, n = r / (st.D + 1), i = r % (st.D + 1);
-    const int b = st.active[g];
-    const int f = st.front[b];
-    const int tok = (i == 0) ? st.gen[(long long)b * st.gen_ld + f] : st.drafts[((long long)b * st.N + n) * st.D + i - 1];
+    const int4 d = st.desc[g];
+    const int b = d.x, f = d.y;
+    const int tok = (i == 0) ? d.z : st.drafts[((long long)b * st.N + n) * st.D + i - 1];
     const float* e = table + (long long)tok * E;
     const float* p = pe + (long long)(f + i + 1) * E;
     for (int c = lane; c < E; c += 32) {
@@ -95,13 +119,21 @@ __global__ void greedy_embed_kernel(GreedyState st, const float* __restrict__ ta
     }
 }
 template <typename ActT>
-void launch_greedy_embed(const GreedyState& st, const float* table, const float* pe, int E,
-                         float* x, ActT* xh, cudaStream_t s) {
+void launch_greedy_advance(const GreedyState& st, const float* table, const float* pe, int E, float* x, ActT* xh,
+                           const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld, ActT* kcache, ActT* vcache,
+                           long long cache_layer_stride, long long cache_query_stride, int cache_ld, cudaStream_t s) {
     const int T = st.B * st.N * (st.D + 1);
-    greedy_embed_kernel<ActT><<<(T + 7) / 8, 256, 0, s>>>(st, table, pe, E, x, xh);
+    const int n_embed_blocks = (T + 7) / 8;
+    // first kernel of the captured iteration: plain launch (its predecessor is the previous graph launch)
+    greedy_advance_kernel<ActT><<<n_embed_blocks + st.B * n_layers, 256, 0, s>>>(st, table, pe, E, x, xh, n_embed_blocks, qkv_all,
+                                                                              qkv_layer_stride, n_layers, qkv_ld, kcache, vcache,
+                                                                              cache_layer_stride, cache_query_stride, cache_ld);
 }
-template void launch_greedy_embed<float>(const GreedyState&, const float*, const float*, int, float*, float*, cudaStream_t);
-template void launch_greedy_embed<__nv_bfloat16>(const GreedyState&, const float*, const float*, int, float*, __nv_bfloat16*, cudaStream_t);
+template void launch_greedy_advance<float>(const GreedyState&, const float*, const float*, int, float*, float*, const float*, long long, int, int,
+                                           float*, float*, long long, long long, int, cudaStream_t);
+template void launch_greedy_advance<__nv_bfloat16>(const GreedyState&, const float*, const float*, int, float*, __nv_bfloat16*,
+                                                   const __nv_bfloat16*, long long, int, int, __nv_bfloat16*, __nv_bfloat16*, long long,
+                                                   long long, int, cudaStream_t);
 
 // ---- accept / retire / plan ---------------------------------------------------------------------
 // One CTA, one warp per live query: lanes score the drafts in parallel (accepted length = leading
@@ -226,6 +258,8 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
                 const int b = s_active[g];
                 s_newact[pos] = b;
                 st.active[pos] = b;
+                const int fb = s_front[b];
+                st.desc[pos] = make_int4(b, fb, G[(long long)b * st.gen_ld + fb], st.src_len ? st.src_len[b] : 0x7fffffff);
             }
             w += __popc(m);
         }
@@ -257,36 +291,5 @@ void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     }
     launch_pdl(greedy_accept_kernel, dim3(1), dim3(warps * 32), smem, s, st, stage_gen);
 }
-
-// ---- KV-cache append ------------------------------------------------------------------------------
-template <typename ActT>
-__global__ void greedy_cache_append_kernel(GreedyState st, const ActT* __restrict__ qkv_all, long long qkv_layer_stride,
-                                           int qkv_ld, int E, ActT* __restrict__ kcache, ActT* __restrict__ vcache,
-                                           long long cache_layer_stride, long long cache_query_stride, int cache_ld) {
-    const int g = blockIdx.x, l = blockIdx.y;
-    pdl_launch_dependents();
-    pdl_wait();
-    if (st.ctrl[CTRL_DONE] || g >= st.ctrl[CTRL_N_SEL]) return;  // after DONE the cache is never read again
-    const int b = st.sel[g * 4 + 0], f = st.sel[g * 4 + 1], pick = st.sel[g * 4 + 2], a = st.sel[g * 4 + 3];
-    const ActT* src = qkv_all + (long long)l * qkv_layer_stride + ((long long)g * st.N + pick) * (st.D + 1) * qkv_ld;
-    ActT* kd = kcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
-    ActT* vd = vcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
-    for (int idx = threadIdx.x; idx < (a + 1) * E; idx += blockDim.x) {
-        const int i = idx / E, c = idx % E;
-        kd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + E + c];
-        vd[(long long)i * cache_ld + c] = src[(long long)i * qkv_ld + 2 * E + c];
-    }
-}
-template <typename ActT>
-void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long long qkv_layer_stride,
-                                int n_layers, int qkv_ld, int E, ActT* kcache, ActT* vcache,
-                                long long cache_layer_stride, long long cache_query_stride, int cache_ld,
-                                cudaStream_t s) {
-    dim3 grid(st.B, n_layers);
-    launch_pdl(greedy_cache_append_kernel<ActT>, grid, dim3(256), 0, s, st, qkv_all, qkv_layer_stride, qkv_ld, E, kcache, vcache,
-               cache_layer_stride, cache_query_stride, cache_ld);
-}
-template void launch_greedy_cache_append<float>(const GreedyState&, const float*, long long, int, int, int, float*, float*, long long, long long, int, cudaStream_t);
-template void launch_greedy_cache_append<__nv_bfloat16>(const GreedyState&, const __nv_bfloat16*, long long, int, int, int, __nv_bfloat16*, __nv_bfloat16*, long long, long long, int, cudaStream_t);
 
 }  // namespace ttb

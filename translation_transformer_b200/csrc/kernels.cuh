@@ -87,12 +87,13 @@ void launch_attention_mma(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16*
                           __nv_bfloat16* out, int out_ld, int n_groups_max, const int* n_groups_dev,
                           int Lq, int Lk, long long kv_group_stride, const int* kvmap,
                           const int* key_tok, int key_tok_stride, int pad_id, bool causal,
-                          int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr);
+                          int heads, int head_dim, cudaStream_t s, const int* lk_dev = nullptr, const int* lk_group = nullptr,
+                          const int4* desc = nullptr);
 void launch_spec_self_attention_mma(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                                     long long cache_query_stride, int cache_ld, __nv_bfloat16* out, int out_ld,
                                     int B_max, const int* n_active_dev, const int* active, const int* front,
                                     const int* gen, int gen_ld, int pad_id, int N, int D,
-                                    int heads, int head_dim, cudaStream_t s);
+                                    int heads, int head_dim, cudaStream_t s, const int4* desc = nullptr);
 
 // ---- drafting.cu ------------------------------------------------------------------------------
 // Mirrors utils/drafting.py::make_drafts on device; src is (B, L) int32 with row stride src_ld (the
@@ -114,21 +115,21 @@ struct GreedyState {
     int* trace;        // optional [max_len][B][4] = {query id, n_accepted, draft index, width}
     int tie_break;     // 0 = torch-CPU topk(1) emulation, 1 = lowest index
     int* hist;         // [max_len + 2] live queries at the start of every iteration
+    int4* desc;        // [B] per live slot of the COMING iteration: {query id, front, token at front, source length};
+                       // written by the init / accept kernels so that the kernels of an iteration need one load
+                       // instead of the chain active[g] -> front[b] -> gen[b][front]
+    const int* src_len;  // [B] source length per query (cross-attention key bound), may be nullptr
 };
 void launch_greedy_init(const GreedyState& st, cudaStream_t s);
-// embeds the (D+1) step tokens of every live draft row
+// First kernel of an iteration: appends the K/V rows of the tokens accepted in the previous iteration (chosen
+// draft recorded in st.sel) to the self-attention cache of every layer, and embeds the (D+1) step tokens of
+// every live draft row.
 template <typename ActT>
-void launch_greedy_embed(const GreedyState& st, const float* table, const float* pe, int E,
-                         float* x, ActT* xh, cudaStream_t s);
+void launch_greedy_advance(const GreedyState& st, const float* table, const float* pe, int E, float* x, ActT* xh,
+                           const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld, ActT* kcache, ActT* vcache,
+                           long long cache_layer_stride, long long cache_query_stride, int cache_ld, cudaStream_t s);
 // picks the best draft per live query, appends tokens, retires finished queries, plans next width
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s);
-// copies K/V of the accepted positions of the chosen draft (recorded in st.sel by the accept
-// kernel) into the self-attention cache, for all layers at once
-template <typename ActT>
-void launch_greedy_cache_append(const GreedyState& st, const ActT* qkv_all, long long qkv_layer_stride,
-                                int n_layers, int qkv_ld, int E, ActT* kcache, ActT* vcache,
-                                long long cache_layer_stride, long long cache_query_stride, int cache_ld,
-                                cudaStream_t s);
 
 // ---- beam.cu --------------------------------------------------------------------------------------
 struct BeamState {

@@ -91,6 +91,7 @@ enum Ctrl : int {
                          // row-counted kernel of an already-enqueued iteration exits immediately)
     CTRL_LS = 10,        // source length of the batch (read by the cross-attention kernels so that the
                          // captured decoding graph does not depend on it)
+    CTRL_ALLEQ_PICK = 11,  // draft index torch-CPU topk(1) returns when all n_drafts accepted lengths are equal
     CTRL_COUNT = 16
 };
 

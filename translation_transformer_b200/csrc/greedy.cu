@@ -69,11 +69,21 @@ __global__ void __launch_bounds__(256) greedy_init_kernel(GreedyState st) {
     }
     if (threadIdx.x < CTRL_COUNT) st.ctrl[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) { st.ctrl[CTRL_N_ACTIVE] = st.B; st.ctrl[CTRL_LS] = st.Ls; }
+    if (threadIdx.x == 0) {
+        st.ctrl[CTRL_N_ACTIVE] = st.B;
+        st.ctrl[CTRL_LS] = st.Ls;
+        // the most frequent tie (no draft accepted at all: every length is 0) has a fixed answer per n_drafts
+        int pick = 0;
+        if (st.tie_break == 0 && st.N > 1 && st.N < 64) {
+            for (int n = 0; n < st.N; ++n) s_init_dyn[n] = n;   // value 0, index n
+            pick = topk1_torch_cpu_packed(s_init_dyn, st.N);
+        }
+        st.ctrl[CTRL_ALLEQ_PICK] = pick;
+    }
     plan_next_iteration(st, st.active, st.front, st.gen, st.B, 1, s_tmp, s_init_dyn);
 }
 void launch_greedy_init(const GreedyState& st, cudaStream_t s) {
-    greedy_init_kernel<<<1, 256, (size_t)st.gen_ld * sizeof(int), s>>>(st);
+    greedy_init_kernel<<<1, 256, (size_t)(st.gen_ld > 64 ? st.gen_ld : 64) * sizeof(int), s>>>(st);
 }
 
 // ---- first kernel of an iteration: KV-cache append of the previous iteration + step-token embedding ----------
@@ -154,7 +164,8 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
     int* s_front = s_active + B;                 // [B]
     int* s_fin = s_front + B;                    // [B]
     int* s_newact = s_fin + B;                   // [B]
-    int* s_nacc_all = s_newact + B;              // [warps][64]
+    int* s_srclen = s_newact + B;                // [B]
+    int* s_nacc_all = s_srclen + B;              // [warps][64]
     int* col_live = s_nacc_all + n_warps * 64;   // [gen_ld]
     int* s_gen = col_live + st.gen_ld;           // [B][gen_ld] when stage_gen
     int* s_nacc = s_nacc_all + warp * 64;
@@ -165,7 +176,12 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
     const int Wn = st.ctrl[CTRL_WIDTH];
     const int iter = st.ctrl[CTRL_ITERS];
-    for (int b = threadIdx.x; b < B; b += blockDim.x) { s_active[b] = st.active[b]; s_front[b] = st.front[b]; }
+    const int alleq_pick = st.ctrl[CTRL_ALLEQ_PICK];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        s_active[b] = st.active[b];
+        s_front[b] = st.front[b];
+        s_srclen[b] = st.src_len ? st.src_len[b] : 0x7fffffff;
+    }
     if (stage_gen)
         for (int idx = threadIdx.x; idx < B * st.gen_ld; idx += blockDim.x) s_gen[idx] = st.gen[idx];
     if (done) return;
@@ -209,7 +225,9 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
             for (int n = lane; n < N; n += 32) ties += ((s_nacc[n] >> 8) == best_val) ? 1 : 0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
-            if (ties > 1) {
+            if (ties == N) {
+                pick = alleq_pick;            // all lengths equal: answer precomputed by the init kernel
+            } else if (ties > 1) {
                 if (lane == 0) pick = topk1_torch_cpu_packed(s_nacc, N);
                 pick = __shfl_sync(0xffffffffu, pick, 0);
             }
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
                 s_newact[pos] = b;
                 st.active[pos] = b;
                 const int fb = s_front[b];
-                st.desc[pos] = make_int4(b, fb, G[(long long)b * st.gen_ld + fb], st.src_len ? st.src_len[b] : 0x7fffffff);
+                st.desc[pos] = make_int4(b, fb, G[(long long)b * st.gen_ld + fb], s_srclen[b]);
             }
             w += __popc(m);
         }
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
 }
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     const int warps = st.B < 32 ? (st.B < 4 ? 4 : st.B) : 32;
-    const size_t base_ints = (size_t)4 * st.B + (size_t)warps * 64 + st.gen_ld;
+    const size_t base_ints = (size_t)5 * st.B + (size_t)warps * 64 + st.gen_ld;
     const size_t gen_ints = (size_t)st.B * st.gen_ld;
     const int stage_gen = base_ints + gen_ints <= (size_t)ACCEPT_MAX_SMEM_INTS ? 1 : 0;
     const size_t smem = (base_ints + (stage_gen ? gen_ints : 0)) * sizeof(int);

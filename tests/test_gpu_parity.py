@@ -279,6 +279,61 @@ def test_greedy_speculative_bf16_tokens_are_reference_argmax(dev):
     assert total > 200
 
 
+def _ragged_sources(B, lo, hi, vocab, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(lo, hi, (B,), generator=g)
+    src = torch.zeros(B, int(lens.max()) + 2, dtype=torch.int64)
+    for b in range(B):
+        n = int(lens[b])
+        src[b, 0] = 1
+        src[b, 1:n + 1] = torch.randint(4, vocab, (n,), generator=g)
+        src[b, n + 1] = 2
+    return src
+
+
+@pytest.mark.parametrize("D,N,lo,hi", [(10, 23, 10, 60), (20, 7, 20, 50), (6, 30, 200, 236)],
+                         ids=["bench-shape", "long-drafts", "long-sources"])
+def test_greedy_speculative_bf16_full_size_fused_kernels(dev, D, N, lo, hi):
+    """The benchmark model shape (E=256, F=2048: fused GEMM+LayerNorm, fused FFN, fused classifier+argmax, tensor-core
+    attention with KV cache) through the whole decoding loop, against the fp32 path of the same engine code (which is
+    bit-exact with the reference, see the fp32 tests).  A random-init model of this size never emits EOS at a useful
+    length, so the comparison is on the per-iteration trace (accepted length and chosen draft of every query): bf16
+    may only leave the fp32 trajectory through a near-tie of two logits, i.e. late or never."""
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    from helpers import FULL
+    vocab, B, max_len = 120, 5, 72
+    cfg = ModelConfig(src_vocab_size=vocab, tgt_vocab_size=vocab, **FULL)
+    sd = {k: v.clone() for k, v in random_init_state_dict(cfg, 4242).items()}
+    sd["tgt_token_featurizer.embedding.weight"] = sd["src_token_featurizer.embedding.weight"]
+    src = _ragged_sources(B, lo, hi, vocab, seed=77 + D)
+    traces, calls, outs = {}, {}, {}
+    for prec in ("fp32", "bf16"):
+        eng = _engine(cfg, sd, prec)
+        gen = TranslationInferenceGreedySpeculative(eng, max_len, D, N, 0, 1, 2, 7, keep_trace=True)
+        try:
+            outs[prec] = gen.generate(src.to(dev)).cpu()
+        except RuntimeError:
+            outs[prec] = None
+        traces[prec] = [(t["rows"], t["n_accepted"], t["draft_index"]) for t in gen.trace]
+        calls[prec] = gen.model_calls_num
+        if prec == "bf16" and outs[prec] is not None:
+            # the graph-replayed loop (no trace) must give the same tokens as the traced, eagerly launched one
+            gen2 = TranslationInferenceGreedySpeculative(eng, max_len, D, N, 0, 1, 2, 7)
+            out2 = gen2.generate(src.to(dev)).cpu()
+            assert np.array_equal(outs[prec].numpy(), out2.numpy())
+            assert gen2.model_calls_num == calls[prec]
+        eng.close()
+    n = min(len(traces["fp32"]), len(traces["bf16"]))
+    first_diff = next((i for i in range(n) if traces["fp32"][i] != traces["bf16"][i]), None)
+    assert n >= 5
+    assert first_diff is None or first_diff >= 8, (first_diff, traces["fp32"][first_diff], traces["bf16"][first_diff])
+    if first_diff is None:
+        assert calls["fp32"] == calls["bf16"]
+        if outs["fp32"] is not None and outs["bf16"] is not None:
+            assert np.array_equal(outs["fp32"].numpy(), outs["bf16"].numpy())
+    print(f"bf16 trace identical to fp32 for {n if first_diff is None else first_diff} of {n} iterations")
+
+
 # ---------------------------------------------------------------------------------------------
 # speculative beam search (configs[2], configs[3] of BASELINE.json at test size)
 def _beam_cases():

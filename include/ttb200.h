@@ -95,6 +95,13 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                     int32_t tie_break, int64_t* out_dev, int32_t* trace_dev,
                                     ttb_generate_stats* stats, void* stream);
 
+/* ---- standard_decoding.py:29 TranslationInferenceGreedy.generate(src)
+ * Plain greedy decoding, one token per row and step, on the same KV-cached device loop (no drafts).  Like the
+ * reference, rows keep decoding after their EOS until every row predicts EOS or PAD in the same step.
+ * out_dev is (B, max_len) int64, PAD behind the last generated column. */
+int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t pad_token,
+                        int32_t bos_token, int32_t eos_token, int64_t* out_dev, ttb_generate_stats* stats, void* stream);
+
 /* ---- speculative_decoding.py:422 TranslationInferenceBeamSearchSpeculative.generate(src),
  * smart_drafts_mode=False ("try all the drafts", :428-598).  out_dev must hold
  * B * n_best * (max_len + clamp(draft_len,5,200) + 4) int64; the hypotheses are written densely as

@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py [--only model,drafts,greedy,beam]
+    python tests/golden/make_golden.py [--only model,drafts,greedy,beam,standard]
 
 What it does
   * stubs `pytorch_lightning` (not installed here; only class bases are needed to import
@@ -297,3 +297,6 @@ if __name__ == "__main__":
     if "beam" in todo:
         from make_golden_beam import gen_beam
         gen_beam(ref)
+    if "standard" in todo:
+        from make_golden_standard import gen_standard
+        gen_standard(ref)

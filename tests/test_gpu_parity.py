@@ -383,3 +383,43 @@ def test_beam_speculative_bf16_runs_and_is_consistent(dev):
     w = min(a.shape[2], b.shape[2])
     same_top1 = sum(bool(torch.equal(a[i, 0, :w], b[i, 0, :w])) for i in range(case["B"]))
     assert same_top1 >= case["B"] // 2
+
+
+# ---------------------------------------------------------------------------------------------
+# standard (non-speculative) decoding, standard_decoding.py
+def _standard_cases(kind):
+    return [c for c in load_json("standard_decoding.json") if c["kind"] == kind]
+
+
+@pytest.mark.parametrize("case", _standard_cases("greedy"), ids=lambda c: c["id"])
+def test_standard_greedy_fp32_matches_reference_golden(dev, case):
+    from translation_transformer_b200.decoding import TranslationInferenceGreedy
+    z = load_npz("standard_decoding.npz")
+    cfg, sd = case_weights(case)
+    eng = _engine(cfg, sd, "fp32")
+    gen = TranslationInferenceGreedy(eng, case["max_len"], 0, 1, 2)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+    out = gen.generate(src.to(dev)).cpu()
+    assert np.array_equal(out.numpy(), z[case["id"] + "_out"].astype(np.int64))
+    assert gen.model_calls_num == case["model_calls"] and gen.given_tokens == case["given_tokens"]
+    # second call on the same engine (graph replay, buffers reused)
+    out2 = gen.generate(src.to(dev)).cpu()
+    assert np.array_equal(out.numpy(), out2.numpy())
+    eng.close()
+
+
+def test_standard_greedy_bf16_tokens_are_reference_argmax(dev):
+    from oracle.transformer import OracleTransformer
+    from translation_transformer_b200.decoding import TranslationInferenceGreedy
+    z = load_npz("standard_decoding.npz")
+    total = 0
+    for case in _standard_cases("greedy"):
+        if "eos_bias" not in case:
+            continue
+        cfg, sd = case_weights(case)
+        eng = _engine(cfg, sd, "bf16")
+        src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+        out = TranslationInferenceGreedy(eng, case["max_len"], 0, 1, 2).generate(src.to(dev)).cpu()
+        total += _check_tokens_near_argmax(OracleTransformer(sd, cfg.num_heads), src, out, 0, 2, margin=3e-2)
+        eng.close()
+    assert total > 100

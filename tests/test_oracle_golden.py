@@ -152,3 +152,28 @@ def test_beam_speculative_oracle_matches_reference(case):
     pick = np.concatenate([t["pick"] for t in gen.trace])
     assert np.array_equal(nacc, z[case["id"] + "_nacc"].astype(np.int64))               # accepted lengths of every draft
     assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))               # chosen draft indices
+
+
+# ---------------------------------------------------------------------------------------------
+# standard (non-speculative) decoding, standard_decoding.py
+def _standard_cases():
+    return load_json("standard_decoding.json")
+
+
+@pytest.mark.parametrize("case", _standard_cases(), ids=lambda c: c["id"])
+def test_standard_decoding_oracle_matches_reference_golden(case):
+    from oracle.standard_decoding import BeamSearchOracle, GreedyOracle
+    z = load_npz("standard_decoding.npz")
+    cfg, sd = case_weights(case)
+    model = OracleTransformer(sd, cfg.num_heads)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+    if case["kind"] == "greedy":
+        o = GreedyOracle(model, case["max_len"], 0, 1, 2)
+    else:
+        o = BeamSearchOracle(model, case["beam_size"], case["max_len"], 0, 1, 2)
+    out = o.generate(src)
+    assert np.array_equal(out.numpy(), z[case["id"] + "_out"].astype(np.int64))
+    assert o.model_calls_num == case["model_calls"] and o.given_tokens == case["given_tokens"]
+    shas = [sha_tokens(t.numpy()) for t in o.decoder_inputs]
+    # the reference's first beam-search step goes through model.forward, which the recording hook does not see
+    assert (shas if case["kind"] == "greedy" else shas[1:]) == case["decoder_input_sha1"]

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ttb_greedy_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
+    "ttb_greedy_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_beam_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 11 +
                                       [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_kernel_class_count": (C.c_int, []),

@@ -510,7 +510,7 @@ static int decode_api(ttb_engine* e, const int64_t* tgt_dev, int B, int Lt, cons
 template <typename ActT>
 static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int draft_len, int N,
                       int pad, int bos, int eos, int replace, int tie_break, int64_t* out_dev, int32_t* trace_dev,
-                      ttb_generate_stats* stats, cudaStream_t user_stream) {
+                      ttb_generate_stats* stats, cudaStream_t user_stream, bool standard = false) {
     const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
     const int n_dec = (int)e->dec.size();
     // the loop runs on the engine's own stream (graph capture is not allowed on the legacy default
@@ -518,7 +518,10 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     cudaStream_t s = e->stream;
     TTB_CUDA_OK(cudaEventRecord(e->join_ev, user_stream));
     TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
-    const int D = std::min(std::max(1, draft_len), max_len);  // make_drafts(min_draft_len=1, max_draft_len=max_len)
+    // speculative: make_drafts(min_draft_len=1, max_draft_len=max_len); standard greedy decoding (standard_decoding.py)
+    // is the same KV-cached loop with one row per query and no draft tokens
+    const int D = standard ? 0 : std::min(std::max(1, draft_len), max_len);
+    if (standard) N = 1;
     const long long TS = (long long)B * Ls;
     // buffers that depend on the source length are sized for a rounded-up capacity so that batches of
     // different length neither reallocate nor invalidate the captured graph
@@ -554,7 +557,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     ActT* crosskv = e->crosskv.as<ActT>();
     if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s, TS_cap * 2 * E)) return 1;
     // drafts from the source without its BOS column (speculative_decoding.py:64-73)
-    { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s); }
+    if (!standard) { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s); }
 
     GreedyState st{};
     st.B = B; st.N = N; st.D = D; st.max_len = max_len; st.gen_ld = gen_ld; st.pad = pad; st.bos = bos; st.eos = eos; st.Ls = Ls;
@@ -606,7 +609,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
             if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, e->logits.as<float>(), V, rows, false, s)) return 1;
             { Scope sc(e, KC_ARGMAX, s); launch_argmax_rows(e->logits.as<float>(), V, V, st.pred, rows, s); }
         }
-        { Scope sc(e, KC_ACCEPT, s); launch_greedy_accept(st, s); }
+        { Scope sc(e, KC_ACCEPT, s); if (standard) launch_greedy_std_step(st, s); else launch_greedy_accept(st, s); }
         return 0;
     };
 
@@ -615,7 +618,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     static const bool no_graph = [] { const char* v = getenv("TTB_NO_GRAPH"); return v && v[0] == '1'; }();
     const bool use_graph = !no_graph && !trace_dev && e->prof.mask == 0;
     if (use_graph) {
-        const long long key[12] = {B, N, D, 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT), replace};
+        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT), replace};
         if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
             const long long l0 = e->launches;
@@ -888,7 +891,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     }
     DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
                       &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
-                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam};
+                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam, &e->srclen, &e->desc};
     for (DevBuf* b : bufs) b->release();
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
@@ -1039,6 +1042,17 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
                                              replace_token, tie_break, out_dev, trace_dev, stats, s),
                         greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
                                                   replace_token, tie_break, out_dev, trace_dev, stats, s));
+}
+
+int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t pad_token,
+                        int32_t bos_token, int32_t eos_token, int64_t* out_dev, ttb_generate_stats* stats, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(src_dev && out_dev && B > 0 && Ls > 0 && max_len > 1, "bad arguments");
+    TTB_CHECK(Ls <= e->d.max_positions && max_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true),
+                        greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true));
 }
 
 int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,

@@ -310,4 +310,43 @@ void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     launch_pdl(greedy_accept_kernel, dim3(1), dim3(warps * 32), smem, s, st, stage_gen);
 }
 
+// ---- standard greedy decoding (standard_decoding.py:29-56): one token per row and iteration ------------------
+// Runs in place of the accept kernel when the loop is used without drafts (N = 1, D = 0).  Every row stays live
+// until the first step in which ALL rows predict EOS or PAD (rows that already emitted EOS keep decoding, like in
+// the reference), or until the token matrix is full.
+__global__ void __launch_bounds__(1024) greedy_std_step_kernel(GreedyState st) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (st.ctrl[CTRL_DONE]) return;
+    const int iter = st.ctrl[CTRL_ITERS];
+    const int f = iter;                     // every row holds iter + 1 tokens
+    int stop = 1;
+    for (int b = threadIdx.x; b < st.B; b += blockDim.x) {
+        const int tok = st.pred[b];
+        st.gen[(long long)b * st.gen_ld + f + 1] = tok;
+        st.front[b] = f + 1;
+        st.desc[b] = make_int4(b, f + 1, tok, st.src_len ? st.src_len[b] : 0x7fffffff);
+        st.sel[b * 4 + 0] = b; st.sel[b * 4 + 1] = f; st.sel[b * 4 + 2] = 0; st.sel[b * 4 + 3] = 0;
+        if (tok != st.eos && tok != st.pad) stop = 0;
+    }
+    const int all_stop = __syncthreads_and(stop);
+    const bool done = all_stop || f + 2 >= st.max_len;
+    if (done) {   // export: tokens 0 .. f+1, PAD behind them (the reference's pre-filled token matrix)
+        for (long long idx = threadIdx.x; idx < (long long)st.B * st.max_len; idx += blockDim.x) {
+            const int b = (int)(idx / st.max_len), c = (int)(idx % st.max_len);
+            st.out[idx] = c <= f + 1 ? st.gen[(long long)b * st.gen_ld + c] : st.pad;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (st.hist) st.hist[iter] = st.B;
+        st.ctrl[CTRL_N_SEL] = st.B;
+        st.ctrl[CTRL_ITERS] = iter + 1;
+        st.ctrl[CTRL_TOKENS] += st.B;
+        if (done) { st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = 0; st.ctrl[CTRL_N_ACTIVE] = 0; }
+    }
+}
+void launch_greedy_std_step(const GreedyState& st, cudaStream_t s) {
+    launch_pdl(greedy_std_step_kernel, dim3(1), dim3(st.B < 1024 ? ((st.B + 31) / 32 * 32) : 1024), 0, s, st);
+}
+
 }  // namespace ttb

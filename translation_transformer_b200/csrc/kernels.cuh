@@ -130,6 +130,8 @@ void launch_greedy_advance(const GreedyState& st, const float* table, const floa
                            long long cache_layer_stride, long long cache_query_stride, int cache_ld, cudaStream_t s);
 // picks the best draft per live query, appends tokens, retires finished queries, plans next width
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s);
+// standard greedy decoding (no drafts: N = 1, D = 0): appends the predicted token of every row, stop test
+void launch_greedy_std_step(const GreedyState& st, cudaStream_t s);
 
 // ---- beam.cu --------------------------------------------------------------------------------------
 struct BeamState {

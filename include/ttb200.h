@@ -102,6 +102,15 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
 int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t pad_token,
                         int32_t bos_token, int32_t eos_token, int64_t* out_dev, ttb_generate_stats* stats, void* stream);
 
+/* ---- standard_decoding.py:90 TranslationInferenceBeamSearch.generate(src)
+ * Standard beam search: one decoder call per generated column on the hypotheses without EOS; scores are
+ * log(softmax(logits)) sums, finished hypotheses continue with PAD (artificial logits), the beam_size best of the
+ * beam x vocabulary continuations survive (sorted).  out_dev must hold B * beam_size * max_len int64; the
+ * hypotheses are written densely as (B, beam_size, *out_width). */
+int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t beam_size,
+                             int32_t pad_token, int32_t bos_token, int32_t eos_token, int64_t* out_dev, int32_t* out_width,
+                             ttb_generate_stats* stats, void* stream);
+
 /* ---- speculative_decoding.py:422 TranslationInferenceBeamSearchSpeculative.generate(src),
  * smart_drafts_mode=False ("try all the drafts", :428-598).  out_dev must hold
  * B * n_best * (max_len + clamp(draft_len,5,200) + 4) int64; the hypotheses are written densely as

@@ -47,6 +47,8 @@ SIGNATURES = {
                                                   C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_greedy_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
+    "ttb_beam_search_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 +
+                                 [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_beam_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 11 +
                                       [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_kernel_class_count": (C.c_int, []),

@@ -839,6 +839,115 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     return 0;
 }
 
+// ---- standard beam search (standard_decoding.py:90-174), host loop + device kernels -----------------------------
+// One decoder call per generated column on the hypotheses that have not produced EOS (full prefix, no KV cache yet);
+// tokens, scores and logits stay on the device, the host reads two control words per step for the stop test.
+template <typename ActT>
+static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int K, int pad, int bos, int eos,
+                        int64_t* out_dev, int32_t* out_width, ttb_generate_stats* stats, cudaStream_t user_stream) {
+    const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
+    const int n_dec = (int)e->dec.size();
+    cudaStream_t s = e->stream;
+    TTB_CUDA_OK(cudaEventRecord(e->join_ev, user_stream));
+    TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
+    const long long launches0 = e->launches;
+    const long long TS = (long long)B * Ls;
+    const int Cmax = B * K, ldw = max_len;
+    const long long Tmax = (long long)Cmax * max_len;
+
+    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (ensure_work<ActT>(e, std::max(Tmax, TS), 1)) return 1;
+    DevBuf& bb = e->beam;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_y0 = take((size_t)Cmax * ldw * 4), o_y1 = take((size_t)Cmax * ldw * 4);
+    const size_t o_s0 = take(Cmax * 4), o_s1 = take(Cmax * 4), o_fin = take(Cmax * 4), o_cr = take(Cmax * 4), o_rc = take(Cmax * 4),
+                 o_rq = take(Cmax * 4), o_rows = take((size_t)Cmax * ldw * 4), o_tot = take((size_t)Cmax * V * 4), o_ctrl = take(64),
+                 o_xg = take((size_t)Cmax * E * 4), o_xgh = take((size_t)Cmax * E * 2), o_lg = take((size_t)Cmax * V * 4);
+    if (bb.ensure(off)) return 1;
+    char* base = bb.as<char>();
+
+    TTB_CUDA_OK(cudaEventRecord(e->t0, s));
+    int* src32 = e->src32.as<int>();
+    { Scope sc(e, KC_MISC, s); launch_i64_to_i32(reinterpret_cast<const long long*>(src_dev), src32, TS, s); }
+    float* mem = e->memory.as<float>();
+    ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
+    if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
+    ActT* crosskv = e->crosskv.as<ActT>();
+    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
+
+    StdBeamState st{};
+    st.B = B; st.K = K; st.V = V; st.pad = pad; st.bos = bos; st.eos = eos; st.ldw = ldw;
+    st.y_cur = (int*)(base + o_y0); st.y_next = (int*)(base + o_y1);
+    st.score_cur = (float*)(base + o_s0); st.score_next = (float*)(base + o_s1);
+    st.fin = (int*)(base + o_fin); st.cand_row = (int*)(base + o_cr); st.row_cand = (int*)(base + o_rc); st.row_query = (int*)(base + o_rq);
+    st.rows_tok = (int*)(base + o_rows); st.total = (float*)(base + o_tot); st.ctrl = (int*)(base + o_ctrl);
+    float* xg = (float*)(base + o_xg);
+    ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
+    float* logits = (float*)(base + o_lg);
+    { Scope sc(e, KC_MISC, s); launch_sbeam_init(st, s); }
+
+    float* x = e->x.as<float>();
+    ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
+    const int* n_live = st.ctrl;
+    int* hc = e->h_ctrl;
+    int W = 1, beam = 1, calls = 0;
+    // step 0 on the BOS column (:106), then at most max_len - 2 further columns (:127)
+    for (int step = 0; step < max_len - 1; ++step) {
+        const int C = B * beam;
+        { Scope sc(e, KC_MISC, s); launch_sbeam_prepare(st, C, beam, W, s); }
+        RowCount rows(C * W, n_live, W);
+        { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
+        auto self_attn = [&](int, ActT* qkv, ActT* att) {
+            attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, C, n_live, W, W, W, nullptr,
+                 st.rows_tok, W, e->d.tgt_pad_token_idx, true, H, HD, s);
+        };
+        auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+            const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+            attn(q2, E, kv, kv + E, 2 * E, att, E, C, n_live, W, Ls, Ls, st.row_query,
+                 src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+        };
+        if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
+        { Scope sc(e, KC_MISC, s); launch_sbeam_gather_last<ActT>(st, x, xh, C, W, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
+        RowCount last_rows(C, n_live, 1);
+        if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, last_rows, false, s)) return 1;
+        { Scope sc(e, KC_ARGMAX, s); launch_sbeam_scores(st, C, logits, s); }
+        {
+            Scope sc(e, KC_ACCEPT, s);
+            TTB_CHECK(launch_sbeam_select(st, beam, W, s) == 0, "beam_size * vocabulary too large for the selection kernel");
+        }
+        TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TTB_CUDA_OK(cudaStreamSynchronize(s));
+        ++calls;
+        std::swap(st.y_cur, st.y_next);
+        std::swap(st.score_cur, st.score_next);
+        beam = K;
+        W += 1;
+        if (step > 0 && hc[1] == B * K) break;   // every hypothesis contains EOS (:169); the first step never breaks (:106-125)
+    }
+    launch_beam_export(st.y_cur, ldw, B * K, W, reinterpret_cast<long long*>(out_dev), s);
+    e->launches++;
+    TTB_CUDA_OK(cudaEventRecord(e->t1, s));
+    TTB_CUDA_OK(cudaStreamSynchronize(s));
+    TTB_CUDA_OK(cudaGetLastError());
+    prof_collect(e);
+    if (out_width) *out_width = W;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->t0, e->t1);
+    if (stats) {
+        stats->model_calls = calls;
+        stats->accepted_tokens = 0;
+        stats->produced_tokens = 0;
+        stats->unfinished = 0;
+        stats->error = 0;
+        stats->gpu_launches = (int32_t)(e->launches - launches0);
+        stats->gpu_ms = ms;
+    }
+    return 0;
+}
+
 }  // namespace ttb
 
 // =================================================================================================
@@ -1053,6 +1162,20 @@ int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     return TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true),
                         greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true));
+}
+
+int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t beam_size,
+                             int32_t pad_token, int32_t bos_token, int32_t eos_token, int64_t* out_dev, int32_t* out_width,
+                             ttb_generate_stats* stats, void* stream) {
+    TTB_CHECK(e && e->finalized, "engine not finalized");
+    TTB_CHECK(src_dev && out_dev && B > 0 && Ls > 0, "bad arguments");
+    TTB_CHECK(max_len > 1 && beam_size > 0, "max_len must be greater than 1 and beam_size greater than 0");
+    TTB_CHECK(beam_size <= e->d.tgt_vocab_size, "beam_size larger than the vocabulary (the reference's first topk fails as well)");
+    TTB_CHECK(Ls <= e->d.max_positions && max_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
+    TTB_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return TTB_DISPATCH(e, std_beam_api<float>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s),
+                        std_beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s));
 }
 
 int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,

@@ -155,6 +155,25 @@ void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, 
 void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s);
 void launch_beam_control(const BeamState& st, int W, cudaStream_t s);
 void launch_beam_export(const int* cand, int ldw, int R, int W, long long* out, cudaStream_t s);
+// ---- std_beam.cu : standard beam search (standard_decoding.py:90-174) -------------------------------------------
+struct StdBeamState {
+    int B, K, V, pad, bos, eos, ldw;
+    int* y_cur; int* y_next;              // [B*K][ldw] hypotheses (query-major), ping-pong
+    float* score_cur; float* score_next;  // [B*K]
+    int* fin; int* cand_row;              // [B*K] contains EOS / live-row index or -1
+    int* row_cand; int* row_query;        // [live rows]
+    int* rows_tok;                        // [live rows][W] decoder input
+    float* total;                         // [B*K][V] score + log-softmax
+    int* ctrl;                            // [0] live rows, [1] hypotheses with EOS after the selection
+};
+void launch_sbeam_init(const StdBeamState& st, cudaStream_t s);
+void launch_sbeam_prepare(const StdBeamState& st, int C, int beam, int W, cudaStream_t s);
+template <typename ActT>
+void launch_sbeam_gather_last(const StdBeamState& st, const float* x, const ActT* xh, int max_rows, int W, int E, float* xg, ActT* xgh,
+                              cudaStream_t s);
+void launch_sbeam_scores(const StdBeamState& st, int C, const float* logits, cudaStream_t s);
+int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s);
+
 // embedding of (rows, L) token matrices whose live row count is on the device
 template <typename ActT>
 void launch_embed_seq_rows(const int* tok, RowCount rows, int L, const float* table, const float* pe, int E,

@@ -1,0 +1,149 @@
+// Device side of the standard beam search.
+// Reference: /root/reference/src/decoding/standard_decoding.py:90-174 (TranslationInferenceBeamSearch.generate).
+//
+// Per step the engine runs
+//   sbeam_prepare -> finished flag of every hypothesis (contains EOS), compact list of live hypotheses, their
+//                    token rows as the decoder input, row -> query map for the cross-attention
+//   decoder stack on the live rows (full prefix, causal), gather of the last position, classifier GEMM
+//   sbeam_scores  -> log(softmax(logits)) per hypothesis (artificial logits for finished ones: 35 on the PAD
+//                    column, 0 elsewhere, :132-135) added to the hypothesis score
+//   sbeam_select  -> per query: the beam_size best of the (beam x vocab) continuations, sorted, and the new
+//                    token rows (parent prefix + chosen token); counts hypotheses that contain EOS
+#include "kernels.cuh"
+#include "topk_emul.cuh"
+
+namespace ttb {
+
+__global__ void __launch_bounds__(1024) sbeam_prepare_kernel(StdBeamState st, int C, int beam, int W) {
+    __shared__ int s_run;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int* row = st.y_cur + (long long)c * st.ldw;
+        int fin = 0;
+        for (int j = 0; j < W; ++j) fin |= (row[j] == st.eos) ? 1 : 0;
+        st.fin[c] = fin;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // order-preserving compaction (boolean indexing in the reference)
+        int run = 0;
+        for (int c = 0; c < C; ++c) {
+            if (st.fin[c]) { st.cand_row[c] = -1; continue; }
+            st.cand_row[c] = run;
+            st.row_cand[run] = c;
+            st.row_query[run] = c / beam;
+            ++run;
+        }
+        st.ctrl[0] = run;
+        st.ctrl[1] = 0;       // hypotheses with EOS after the coming selection (sbeam_select counts them)
+        s_run = run;
+    }
+    __syncthreads();
+    const int R = s_run;
+    for (long long idx = threadIdx.x; idx < (long long)R * W; idx += blockDim.x) {
+        const int r = (int)(idx / W), j = (int)(idx % W);
+        st.rows_tok[idx] = st.y_cur[(long long)st.row_cand[r] * st.ldw + j];
+    }
+}
+void launch_sbeam_prepare(const StdBeamState& st, int C, int beam, int W, cudaStream_t s) {
+    sbeam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, beam, W);
+}
+
+// last position of every live row of the residual stream -> dense (rows, E) classifier input
+template <typename ActT>
+__global__ void sbeam_gather_last_kernel(StdBeamState st, const float* __restrict__ x, const ActT* __restrict__ xh, int W, int E,
+                                         float* __restrict__ xg, ActT* __restrict__ xgh) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= st.ctrl[0]) return;
+    const long long src = ((long long)r * W + W - 1) * E, dst = (long long)r * E;
+    for (int c = lane; c < E; c += 32) {
+        if (xg) xg[dst + c] = x[src + c];
+        if (xgh) xgh[dst + c] = xh[src + c];
+    }
+}
+template <typename ActT>
+void launch_sbeam_gather_last(const StdBeamState& st, const float* x, const ActT* xh, int max_rows, int W, int E, float* xg, ActT* xgh,
+                              cudaStream_t s) {
+    if (max_rows <= 0) return;
+    sbeam_gather_last_kernel<ActT><<<(max_rows + 7) / 8, 256, 0, s>>>(st, x, xh, W, E, xg, xgh);
+}
+template void launch_sbeam_gather_last<float>(const StdBeamState&, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+template void launch_sbeam_gather_last<__nv_bfloat16>(const StdBeamState&, const float*, const __nv_bfloat16*, int, int, int, float*,
+                                                      __nv_bfloat16*, cudaStream_t);
+
+// One warp per hypothesis: total[c][v] = score[c] + log(softmax(logits_c)[v])   (softmax first, then log, like
+// `torch.log(torch.softmax(x, -1))` at :111 / :150)
+__global__ void __launch_bounds__(256) sbeam_scores_kernel(StdBeamState st, int C, const float* __restrict__ logits) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    const int V = st.V, r = st.cand_row[c];
+    const float* p = r >= 0 ? logits + (long long)r * V : nullptr;
+    auto val = [&](int v) { return p ? p[v] : (v == st.pad ? 35.0f : 0.0f); };
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, val(v));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int v = lane; v < V; v += 32) sum += expf(val(v) - mx);
+    sum = warp_sum(sum);
+    const float base = st.score_cur[c];
+    float* out = st.total + (long long)c * V;
+    for (int v = lane; v < V; v += 32) out[v] = base + logf(expf(val(v) - mx) / sum);
+}
+void launch_sbeam_scores(const StdBeamState& st, int C, const float* logits, cudaStream_t s) {
+    sbeam_scores_kernel<<<(C + 7) / 8, 256, 0, s>>>(st, C, logits);
+}
+
+// One CTA per query: the beam_size best of the beam * V continuation scores in the order torch.topk(sorted=True)
+// returns them on the CPU backend (ties between exactly equal scores — the "-35" continuations of finished
+// hypotheses — are decided by libstdc++'s partial_sort / nth_element, emulated in topk_emul.cuh), then the new
+// token rows.
+__global__ void __launch_bounds__(256) sbeam_select_kernel(StdBeamState st, int beam, int W) {
+    extern __shared__ __align__(8) unsigned char s_sel_raw[];
+    VF* s_e = reinterpret_cast<VF*>(s_sel_raw);      // [beam * V] (score, flat index)
+    const int b = blockIdx.x, V = st.V, K = st.K, n = beam * V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* tot = st.total + (long long)b * beam * V;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { s_e[i].v = tot[i]; s_e[i].i = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) topk_sorted_torch_cpu_(s_e, n, K);
+    __syncthreads();
+    int n_fin = 0;
+    for (int j = warp; j < K; j += 8) {
+        const int idx = s_e[j].i;
+        const int parent = idx / V, ch = idx % V;
+        const int* src = st.y_cur + (long long)(b * beam + parent) * st.ldw;
+        int* dst = st.y_next + (long long)(b * K + j) * st.ldw;
+        int fin = (ch == st.eos) ? 1 : 0;
+        for (int c = lane; c < W; c += 32) {
+            const int t = src[c];
+            dst[c] = t;
+            fin |= (t == st.eos) ? 1 : 0;
+        }
+        if (lane == 0) { dst[W] = ch; st.score_next[b * K + j] = s_e[j].v; }
+        fin = __any_sync(0xffffffffu, fin);
+        if (lane == 0 && fin) ++n_fin;
+    }
+    if (lane == 0 && n_fin) atomicAdd(&st.ctrl[1], n_fin);
+}
+int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s) {
+    const size_t smem = (size_t)beam * st.V * sizeof(VF);
+    if (smem > 200 * 1024) return -1;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(sbeam_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = 200 * 1024;
+    }
+    sbeam_select_kernel<<<st.B, 256, smem, s>>>(st, beam, W);
+    return 0;
+}
+
+__global__ void sbeam_init_kernel(StdBeamState st) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < st.B; b += gridDim.x * blockDim.x) {
+        st.y_cur[(long long)b * st.ldw] = st.bos;
+        st.score_cur[b] = 0.f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) st.ctrl[threadIdx.x] = 0;
+}
+void launch_sbeam_init(const StdBeamState& st, cudaStream_t s) { sbeam_init_kernel<<<8, 256, 0, s>>>(st); }
+
+}  // namespace ttb

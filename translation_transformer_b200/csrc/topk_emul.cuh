@@ -55,11 +55,11 @@ template <typename VI> __device__ inline void heap_select_(VI* e, int first, int
         }
     }
 }
-// libstdc++ std::nth_element(e, e + 0, e + n, gt) (introselect); the winner ends up in e[0]
+// libstdc++ std::nth_element(e, e + nth, e + n, gt) (introselect)
 template <typename VI>
-__device__ inline void nth_element0_(VI* e, int n) {
+__device__ inline void nth_element_(VI* e, int n, int nth) {
     int first = 0, last = n;
-    const int nth = 0;
+    if (n == 0 || nth == n) return;
     int depth = 2 * (31 - __clz(n));
     while (last - first > 3) {
         if (depth == 0) {
@@ -100,6 +100,72 @@ __device__ inline void nth_element0_(VI* e, int n) {
             while (gt(val, e[j - 1])) { e[j] = e[j - 1]; --j; }
             e[j] = val;
         }
+    }
+}
+
+template <typename VI> __device__ inline void nth_element0_(VI* e, int n) { nth_element_(e, n, 0); }
+
+// (float value, index) pairs for torch.topk over scores
+struct VF { float v; int i; };
+__device__ __forceinline__ bool gt(const VF& a, const VF& b) { return a.v > b.v; }
+
+template <typename VI> __device__ inline void insertion_sort_(VI* e, int first, int last) {
+    for (int i = first + 1; i < last; ++i) {
+        VI val = e[i];
+        if (gt(val, e[first])) {
+            for (int j = i; j > first; --j) e[j] = e[j - 1];
+            e[first] = val;
+        } else {
+            int j = i;
+            while (gt(val, e[j - 1])) { e[j] = e[j - 1]; --j; }
+            e[j] = val;
+        }
+    }
+}
+// std::partial_sort(e, e + k, e + n, gt): __heap_select + __sort_heap.  The scan over [k, n) skips runs of eight
+// entries that cannot enter the heap with independent loads (the heap top only changes when one does).
+template <typename VI> __device__ inline void partial_sort_(VI* e, int n, int k) {
+    if (k >= 2) {
+        int parent = (k - 2) / 2;
+        while (true) {
+            adjust_heap_(e, 0, parent, k, e[parent]);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int i = k;
+    while (i < n) {
+        if (i + 8 <= n) {
+            const VI top = e[0];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) any |= gt(e[i + u], top);
+            if (!any) { i += 8; continue; }
+        }
+        if (gt(e[i], e[0])) {
+            VI val = e[i];
+            e[i] = e[0];
+            adjust_heap_(e, 0, 0, k, val);
+        }
+        ++i;
+    }
+    int last = k;
+    while (last > 1) {   // __sort_heap
+        --last;
+        VI val = e[last];
+        e[last] = e[0];
+        adjust_heap_(e, 0, 0, last, val);
+    }
+}
+// The first k entries of e become what torch.topk(values, k, largest=True, sorted=True) returns on the CPU backend
+// (ATen/native/cpu/TopKImpl.h: partial_sort when k * 64 <= n, else nth_element + sort of the first k - 1 entries;
+// the sort is an insertion sort up to 16 entries, which is also used (inexact among ties) beyond that).
+template <typename VI> __device__ inline void topk_sorted_torch_cpu_(VI* e, int n, int k) {
+    if ((long long)k * 64 <= n) {
+        partial_sort_(e, n, k);
+    } else {
+        nth_element_(e, n, k - 1);
+        if (k - 1 > 1) insertion_sort_(e, 0, k - 1);
     }
 }
 

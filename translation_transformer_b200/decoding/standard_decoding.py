@@ -50,3 +50,45 @@ class TranslationInferenceGreedy:
         self.gpu_ms += stats.gpu_ms
         out = out.unsqueeze(1)
         return out if src.is_cuda else out.to(src.device)
+
+
+class TranslationInferenceBeamSearch:
+    """Mirror of standard_decoding.py:59-174 (same arguments, counters and output): `generate(src)` returns the
+    (B, beam_size, width) hypotheses best-first; width is the number of generated columns."""
+
+    def __init__(self, model: B200Transformer, beam_size: int, max_len: int, pad_token: int, bos_token: int, eos_token: int):
+        assert max_len > 1
+        assert beam_size > 0
+        self.model = model
+        self.beam_size, self.max_len = beam_size, max_len
+        self.pad_token, self.bos_token, self.eos_token = pad_token, bos_token, eos_token
+        self.model_calls_num = 0
+        self.given_tokens = 0
+        self.b_sz = 0
+        self.gpu_launches = 0
+        self.gpu_ms = 0.0
+        self.last_stats = None
+
+    def __str__(self):
+        return f"Beam search decoding (beam_size={self.beam_size}, max_len={self.max_len})"
+
+    def generate(self, src: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        src_d = src.to(device=m.device, dtype=torch.int64, non_blocking=True).contiguous()
+        B, Ls = src_d.shape
+        out = torch.empty(B * self.beam_size * self.max_len, dtype=torch.int64, device=m.device)
+        stats = _lib.GenerateStats()
+        width = C.c_int32(0)
+        with torch.cuda.device(m.device):
+            rc = m.lib.ttb_beam_search_generate(m._h, src_d.data_ptr(), B, Ls, self.max_len, self.beam_size, self.pad_token,
+                                                self.bos_token, self.eos_token, out.data_ptr(), C.byref(width), C.byref(stats),
+                                                torch.cuda.current_stream(m.device).cuda_stream)
+        _lib.check(rc, "ttb_beam_search_generate")
+        self.last_stats = stats
+        self.model_calls_num += stats.model_calls
+        self.given_tokens += int((src_d != m.src_pad_token_i).sum().item())
+        self.gpu_launches += stats.gpu_launches
+        self.gpu_ms += stats.gpu_ms
+        W = width.value
+        res = out[:B * self.beam_size * W].view(B, self.beam_size, W)
+        return res if src.is_cuda else res.to(src.device)

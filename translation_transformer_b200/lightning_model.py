@@ -12,6 +12,7 @@ from timeit import default_timer as timer
 from typing import Any
 
 from .decoding.speculative_decoding import TranslationInferenceBeamSearchSpeculative, TranslationInferenceGreedySpeculative
+from .decoding.standard_decoding import TranslationInferenceBeamSearch, TranslationInferenceGreedy
 from .model import B200Transformer
 from .weights import ModelConfig, random_init_state_dict
 
@@ -55,6 +56,13 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         self.model.load_state_dict({k: v for k, v in state_dict.items() if "positional_encoding" not in k})
 
     def _create_generator(self):
+        if self.generation == "greedy":
+            return TranslationInferenceGreedy(self.model, max_len=self.max_len, pad_token=self.tgt_pad_token_i,
+                                              bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i)
+        if self.generation == "beam_search":
+            return TranslationInferenceBeamSearch(self.model, beam_size=self.beam_size, max_len=self.max_len,
+                                                  pad_token=self.tgt_pad_token_i, bos_token=self.tgt_bos_token_i,
+                                                  eos_token=self.tgt_eos_token_i)
         if self.generation == "greedy_speculative":
             assert self.draft_len > 0, "Number of speculative tokens must be a positive integer."
             return TranslationInferenceGreedySpeculative(
@@ -68,8 +76,6 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
                 bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
                 C_token=self.tgt_tokenizer.encoder_dict["c"], smart_drafts_mode=self.smart_drafts_mode)
         options = ", ".join(["beam_search", "greedy", "greedy_speculative", "beam_search_speculative"])
-        if self.generation in ("beam_search", "greedy"):
-            raise NotImplementedError(f"generation={self.generation} is not on the B200 hot path yet (DESIGN.md §0 row f)")
         raise ValueError(f"Unknown generation option {self.generation}. Options are {options}.")
 
     def predict_step(self, batch: Any, batch_idx: int, dataloader_idx: int = 0) -> Any:

@@ -275,17 +275,31 @@ static bool fused_ln_enabled() {
     return v == 1;
 }
 static int linear_resid_ln(ttb_engine* e, int kc, const float* A, int lda, const Lin& L, const Norm& n1, const Norm* n2,
-                           float* x, float* /*xh*/, float* y, float* dst, float* dsth, RowCount rows, cudaStream_t s) {
+                           float* x, float* /*xh*/, float* y, float* dst, float* dsth, RowCount rows, cudaStream_t s,
+                           const Lin* = nullptr, float* = nullptr, bool* chained = nullptr) {
+    if (chained) *chained = false;
     if (linear<float>(e, kc, A, lda, L, y, L.N, rows, false, s)) return 1;
     Scope sc(e, KC_LAYERNORM, s);
     launch_add_layernorm<float>(x, y, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, dst, dsth, rows, L.N, s);
     return 0;
 }
+// `chain` (optional): a projection of the normalised result that the same kernel computes on the way out
+// (the cross-attention query); *chained tells the caller whether it was taken.
+static bool chain_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TTB_NO_CHAIN"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 static int linear_resid_ln(ttb_engine* e, int kc, const __nv_bfloat16* A, int lda, const Lin& L, const Norm& n1, const Norm* n2,
-                           float* x, __nv_bfloat16* xh, float* y, float* dst, __nv_bfloat16* dsth, RowCount rows, cudaStream_t s) {
+                           float* x, __nv_bfloat16* xh, float* y, float* dst, __nv_bfloat16* dsth, RowCount rows, cudaStream_t s,
+                           const Lin* chain = nullptr, __nv_bfloat16* q2 = nullptr, bool* chained = nullptr) {
+    if (chained) *chained = false;
     if (L.N == 256 && dst == x && dsth == xh && fused_ln_enabled()) {
         Scope sc(e, kc, s);
-        return launch_gemm_resid_ln(A, lda, L.wh, L.b, x, xh, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, rows, L.K, s);
+        const bool do_chain = chain && q2 && L.K == 256 && chain->N == 256 && chain->K == 256 && chain_enabled();
+        if (chained) *chained = do_chain;
+        return launch_gemm_resid_ln(A, lda, L.wh, L.b, x, xh, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, rows, L.K, s,
+                                    do_chain ? chain->wh : nullptr, do_chain ? chain->b : nullptr, do_chain ? q2 : nullptr);
     }
     if (linear<float>(e, kc, A, lda, L, y, L.N, rows, false, s)) return 1;
     Scope sc(e, KC_LAYERNORM, s);
@@ -438,8 +452,10 @@ static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long
         ActT* qkv = e->qkv.as<ActT>() + (qkv_layers > 1 ? (long long)l * qkv_layer_stride : 0);
         if (linear<ActT>(e, KC_GEMM_QKV, a_view<ActT>(x, xh), E, L.self_in, qkv, 3 * E, rows, false, s)) return 1;
         { Scope sc(e, KC_SELF_ATTN, s); self_attn(l, qkv, att); }
-        if (linear_resid_ln(e, KC_GEMM_SELF_OUT, att, E, L.self_out, L.n1, nullptr, x, xh, y, x, xh, rows, s)) return 1;
-        if (linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, L.cross_in.rows(0, E), q2, E, rows, false, s)) return 1;
+        const Lin cross_q = L.cross_in.rows(0, E);
+        bool chained = false;
+        if (linear_resid_ln(e, KC_GEMM_SELF_OUT, att, E, L.self_out, L.n1, nullptr, x, xh, y, x, xh, rows, s, &cross_q, q2, &chained)) return 1;
+        if (!chained && linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, cross_q, q2, E, rows, false, s)) return 1;
         { Scope sc(e, KC_CROSS_ATTN, s); cross_attn(l, q2, att); }
         if (linear_resid_ln(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, L.n2, nullptr, x, xh, y, x, xh, rows, s)) return 1;
         if (ffn_block(e, KC_GEMM_FFN1, KC_GEMM_FFN2, L.ff1, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, hid, y, x, xh, rows, s)) return 1;

@@ -525,7 +525,7 @@ constexpr int BNL = 128;                               // output columns per CTA
 constexpr int STAGE = A_BYTES + BNL * BK * 2;          // 32 KB
 constexpr int RESID_BYTES = BM * BNL * 4;              // 64 KB
 constexpr int PART_BYTES = 4 * BM * 8;                 // float2[4][128]
-constexpr int PARAM_FLOATS = 5 * BNL;                  // bias, g1, b1, g2, b2 slices
+constexpr int PARAM_FLOATS = 6 * BNL;                  // bias, g1, b1, g2, b2 slices, bias of the chained GEMM
 constexpr int THREADS = 320;
 constexpr int SMEM = NST * STAGE + RESID_BYTES + 2 * PART_BYTES + PARAM_FLOATS * 4 + 256 + 1024;
 }  // namespace lnk
@@ -610,7 +610,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(lnk::THREADS, 1)
 gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXh,
                      const float* __restrict__ bias, const float* __restrict__ g1, const float* __restrict__ b1,
-                     const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int K) {
+                     const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int K,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmQ,
+                     const float* __restrict__ bias2, int chain) {
     using namespace lnk;
     const int m0 = (blockIdx.x >> 1) * BM;
     uint32_t rank;
@@ -631,7 +633,11 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
     const uint32_t tfull_bar = bar_base + 8u * (2 * NST);
     const uint32_t resid_bar = bar_base + 8u * (2 * NST + 1);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (bar_base - base) + 8 * (2 * NST + 2));
+    const uint32_t w2_bar = bar_base + 8u * (2 * NST + 2);        // chained GEMM: its weight slice has landed
+    const uint32_t a2_peer_bar = bar_base + 8u * (2 * NST + 3);   //   the peer's half of the LayerNorm output has landed
+    const uint32_t a2_own_bar = bar_base + 8u * (2 * NST + 4);    //   this CTA's half is written
+    const uint32_t acc2_bar = bar_base + 8u * (2 * NST + 5);      //   its accumulator is complete
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (bar_base - base) + 8 * (2 * NST + 6));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = K / BK;
@@ -647,10 +653,14 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
             mbar_init(tfull_bar, 1);
             mbar_init(resid_bar, 1);
+            mbar_init(w2_bar, 1);
+            mbar_init(a2_peer_bar, 1);
+            mbar_init(a2_own_bar, 1);
+            mbar_init(acc2_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)BNL) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(2 * BNL)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {   // parameter slices of this CTA's columns
@@ -661,6 +671,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             prm[2 * BNL + t] = __ldg(b1 + n0 + t);
             prm[3 * BNL + t] = g2 ? __ldg(g2 + n0 + t) : 1.f;
             prm[4 * BNL + t] = g2 ? __ldg(b2 + n0 + t) : 0.f;
+            prm[5 * BNL + t] = (chain && bias2) ? __ldg(bias2 + n0 + t) : 0.f;
         }
     }
     tcgen05_fence_before();
@@ -689,6 +700,11 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     mbar_expect_tx(resid_bar, RESID_BYTES);
                     for (int bx = 0; bx < 4; ++bx) tma_load_2d(resid_u32 + bx * (BM * 128), &tmX, n0 + 32 * bx, m0, resid_bar);
                 }
+            }
+            if (chain) {   // weight slice of the chained GEMM into ring stages 2-3 once GEMM1 has released the ring
+                mbar_wait(tfull_bar, 0);
+                mbar_expect_tx(w2_bar, 4 * 16384);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(base + 2 * STAGE + kb * 16384, &tmW2, kb * BK, n0, w2_bar);
             }
         }
     } else if (warp == 1) {
@@ -744,6 +760,8 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         ln_local_stats(v, mean, m2);
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // phase 0: the peer is running
         ln_publish(part1, pidx, row, rank, mean, m2);
+        // chained GEMM: expect the peer's half of the normalised tile (it is sent after the barrier below)
+        if (chain && threadIdx.x == 64) mbar_expect_tx(a2_peer_bar, 2 * 16384);
     } else {
         __syncwarp();
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -761,22 +779,84 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         cluster_sync_all();
         if (epi) ln_normalise(v, part2, row, prm + 3 * BNL + h * 64, prm + 4 * BNL + h * 64);
     }
+    if (chain && live && warp == 1 && lane == 0) {
+        // chained GEMM, issued here (behind the statistics barriers every thread of the cluster takes part in):
+        // q2 = LN(x) . W2^T with A = the full 128 x 256 bf16 tile (own + peer halves) in ring stages 0-1
+        constexpr uint32_t idesc2 = umma_idesc_bf16(BM, BNL);
+        mbar_wait(w2_bar, 0);
+        mbar_wait(a2_own_bar, 0);
+        mbar_wait(a2_peer_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(tmem_base + (uint32_t)BNL, umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2),
+                          umma_desc_sw128(base + 2 * STAGE + kb * 16384 + k * UMMA_K * 2), idesc2, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(acc2_bar);
+    }
     if (epi) {
-        // fp32 tile back into the residual boxes (in place), bf16 tile into the idle ring (stage 0)
-        ln_store_tiles(v, resid_sm + 2 * h * (BM * 128), gen_base + h * (BM * 128), row);
+        // fp32 tile back into the residual boxes (in place), bf16 tile into the idle ring: K-block slots 2*rank + h of
+        // the 128 x 256 tile that the chained GEMM reads as its A operand (slots 0, 1 without a chained GEMM)
+        const int slot0 = chain ? 2 * (int)rank : 0;
+        ln_store_tiles(v, resid_sm + 2 * h * (BM * 128), gen_base + (slot0 + h) * (BM * 128), row);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {
             for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, resid_u32 + bx * (BM * 128), n0 + 32 * bx, m0);
-            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + hb * (BM * 128), n0 + 64 * hb, m0);
+            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + (slot0 + hb) * (BM * 128), n0 + 64 * hb, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (chain) {
+                // this CTA's two K-blocks to the same slots of the peer (one 32 KB bulk copy through DSMEM)
+                uint32_t r_dst, r_bar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_dst) : "r"(base + slot0 * 16384), "r"(rank ^ 1u));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar) : "r"(a2_peer_bar), "r"(rank ^ 1u));
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(r_dst),
+                             "r"(base + slot0 * 16384), "r"(2 * 16384), "r"(r_bar)
+                             : "memory");
+                mbar_arrive(a2_own_bar);
+            } else {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        }
+        if (chain) {
+            // epilogue of the chained GEMM: + bias, bf16, staged in ring stage 2 (the weight slice is consumed), TMA store
+            mbar_wait(acc2_bar, 0);
+            tcgen05_fence_after();
+            uint32_t pk[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BNL + h * 64 + c0), r);
+                const float4* bb = reinterpret_cast<const float4*>(prm + 5 * BNL + h * 64 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = bb[j >> 2];
+                    __nv_bfloat162 p01 = __floats2bfloat162_rn(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y);
+                    __nv_bfloat162 p23 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p01);
+                    pk[((c0 + j) >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p23);
+                }
+            }
+            uint8_t* qrow = gen_base + 2 * STAGE + h * 16384 + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(qrow + ((ch ^ swz) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmQ, base + 2 * STAGE + hb * 16384, n0 + 64 * hb, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
         }
     }
+    // the peer reads this CTA's shared memory (bulk copy above) until its own chained GEMM has started
+    if (chain) { __syncwarp(); cluster_sync_all(); }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BNL) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BNL)) : "memory");
     }
 }
 
@@ -1441,7 +1521,8 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
 }
 
 int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
-                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s) {
+                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s,
+                         const __nv_bfloat16* W2, const float* bias2, __nv_bfloat16* q2) {
     using namespace tc;
     if (rows.max_rows <= 0) return 0;
     if (K % BK != 0 || lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
@@ -1449,11 +1530,22 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
         set_last_error("fused GEMM+LayerNorm needs K % 64 == 0, lda % 8 == 0 and 16-byte aligned operands");
         return 4;
     }
-    CUtensorMap tmA, tmB, tmX, tmXh;
+    const int chain = (W2 && q2) ? 1 : 0;
+    if (chain && (K != 256 || (reinterpret_cast<uintptr_t>(W2) & 15) || (reinterpret_cast<uintptr_t>(q2) & 15))) {
+        set_last_error("the chained projection of the fused GEMM+LayerNorm kernel needs K == 256 and 16-byte aligned operands");
+        return 4;
+    }
+    CUtensorMap tmA, tmB, tmX, tmXh, tmW2, tmQ;
     if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
     if (int rc = get_tensor_map(W, 256, K, K, lnk::BNL, &tmB)) return rc;
     if (int rc = get_tensor_map(x, rows.max_rows, 256, 256, BM, &tmX, true)) return rc;
     if (int rc = get_tensor_map(xh, rows.max_rows, 256, 256, BM, &tmXh)) return rc;
+    tmW2 = tmB;
+    tmQ = tmXh;
+    if (chain) {
+        if (int rc = get_tensor_map(W2, 256, 256, 256, lnk::BNL, &tmW2)) return rc;
+        if (int rc = get_tensor_map(q2, rows.max_rows, 256, 256, BM, &tmQ)) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_resid_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lnk::SMEM);
@@ -1464,7 +1556,8 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
         attr_set = true;
     }
     const int tiles = (rows.max_rows + BM - 1) / BM;
-    launch_pdl(gemm_resid_ln_kernel, dim3(2 * tiles), dim3(lnk::THREADS), (size_t)lnk::SMEM, s, tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K);
+    launch_pdl(gemm_resid_ln_kernel, dim3(2 * tiles), dim3(lnk::THREADS), (size_t)lnk::SMEM, s, tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K,
+               tmW2, tmQ, bias2, chain);
     return 0;
 }
 

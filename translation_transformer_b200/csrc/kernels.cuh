@@ -45,9 +45,11 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
                         OutT* C, int ldc, RowCount rows, int N, int K, bool relu, cudaStream_t s);
 
 // Fused sub-layer tail for embedding_dim 256 (bf16 path):  x <- LN2?(LN1(x + A W^T + bias)), x fp32 updated in
-// place, xh = bf16 copy.  W is [256, K] bf16; g2/b2 = nullptr without the second LayerNorm.
+// place, xh = bf16 copy.  W is [256, K] bf16; g2/b2 = nullptr without the second LayerNorm.  Optional chained
+// projection of the result (K == 256 only): q2 = xh W2^T + bias2 with W2 [256, 256] bf16 (the cross-attention query).
 int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, float* x, __nv_bfloat16* xh,
-                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s);
+                         const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int K, cudaStream_t s,
+                         const __nv_bfloat16* W2 = nullptr, const float* bias2 = nullptr, __nv_bfloat16* q2 = nullptr);
 
 // Vocabulary projection fused with arg-max (greedy loop, bf16 path): pred[row] = argmax_v(A[row] . W[v] + bias[v]).
 // Returns -1 when the shape does not fit the kernel (K % 64, V <= 512, shared memory) so the caller can fall back.

@@ -94,11 +94,12 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Stage rows [0, nk) of a K/V source into a tile (asynchronously) and zero rows [nk, nfill).
+// Stage rows [row0, nk) of a K/V source into a tile (asynchronously) and zero rows [max(row0, nk), nfill).
 template <int HD>
-__device__ __forceinline__ void stage_rows(const Tile<HD>& t, const __nv_bfloat16* ksrc, const __nv_bfloat16* vsrc, int ld, int nk, int nfill) {
+__device__ __forceinline__ void stage_rows(const Tile<HD>& t, const __nv_bfloat16* ksrc, const __nv_bfloat16* vsrc, int ld, int nk, int nfill,
+                                           int row0 = 0) {
     constexpr int CH = HD / 8, PITCH = Tile<HD>::PITCH;
-    for (int idx = threadIdx.x; idx < nfill * CH; idx += THREADS) {
+    for (int idx = row0 * CH + threadIdx.x; idx < nfill * CH; idx += THREADS) {
         const int j = idx / CH, c = idx % CH;
         __nv_bfloat16* kd = t.k + j * PITCH + c * 8;
         __nv_bfloat16* vd = t.v + j * PITCH + c * 8;
@@ -199,7 +200,11 @@ __global__ void __launch_bounds__(THREADS, 2)
 attn_mma_kernel(Params p) {
     const int g = blockIdx.y, h = blockIdx.x;
     pdl_launch_dependents();
-    pdl_wait();
+    // With a descriptor table (decoding loop) everything but the queries and the K/V rows appended in this very
+    // iteration was written before the iteration's first kernel, which is a fully serialised launch: those reads
+    // may run ahead of the programmatic dependency, i.e. the key staging overlaps the tail of the preceding GEMM.
+    const bool early = p.desc != nullptr;
+    if (!early) pdl_wait();
     if (p.n_groups_dev && g >= *p.n_groups_dev) return;
     extern __shared__ __align__(16) uint8_t attn_smem[];
     constexpr int PITCH = Tile<HD>::PITCH;
@@ -238,11 +243,11 @@ attn_mma_kernel(Params p) {
         __shared__ int s_last_key;
         if (threadIdx.x == 0) s_last_key = 0;
         __syncthreads();
-        auto stage_A = [&](int j0) {
+        auto stage_A = [&](int j0, int row0) {
             const int nk = min(KTA, kA_end - j0);
             if (nk <= 0) return;
             const int nfill = (nk + 31) & ~31;
-            stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk, nfill);
+            stage_rows<HD>(tileA, kbase + (long long)j0 * p.kv_ld, vbase + (long long)j0 * p.kv_ld, p.kv_ld, nk, nfill, row0);
             int last = 0;
             for (int j = threadIdx.x; j < nfill; j += THREADS) {
                 const bool ok = j < nk && !(key_tok && key_tok[j0 + j] == p.pad_id);
@@ -270,7 +275,16 @@ attn_mma_kernel(Params p) {
                 tileB.bias[j] = bad ? -INFINITY : 0.f;
             }
         };
-        stage_A(0);
+        int n_pre = 0;
+        if (early) {
+            // cache rows older than this iteration (everything for cross-attention; all but the last draft row's
+            // worth of positions for the self-attention prefix) before the dependency wait
+            n_pre = min(KTA, kA_end);
+            if (p.spec) n_pre = max(0, n_pre - RL);
+            if (n_pre > 0) stage_rows<HD>(tileA, kbase, vbase, p.kv_ld, n_pre, n_pre);
+            pdl_wait();
+        }
+        stage_A(0, n_pre);
         if (p.spec) stage_B(firstB);
 
         uint32_t qa[2][HD / 16][4];
@@ -301,7 +315,7 @@ attn_mma_kernel(Params p) {
         for (int j0 = 0; j0 < kA_end; j0 += KTA) {
             if (j0 > 0) {   // sequences longer than one window (not reached by this model's shapes)
                 __syncthreads();
-                stage_A(j0);
+                stage_A(j0, 0);
                 cp_async_wait_all();
                 __syncthreads();
             }

@@ -19,7 +19,7 @@
 namespace ttb {
 
 // ---- prepare ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int W, int dl) {
+__global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int W, int dl) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int* row = st.cand_cur + (long long)c * st.ldw;
         int slot0 = -1, fin = 0, hole = 0;
@@ -35,17 +35,99 @@ __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C,
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int run = 0;
+        int run = 0, live = 0;
         for (int c = 0; c < C; ++c) {
             st.c_rowbase[c] = run;
-            if (!st.c_fin[c]) run += st.N;
+            st.c_front[c] = max(0, st.c_slot0[c] - 1);   // clamped: an inconsistent hypothesis raises BC_ERROR, its rows are discarded
+            if (!st.c_fin[c]) {
+                run += st.N;
+                st.live_cand[live] = c;
+                st.live_query[live] = c / beam;
+                ++live;
+            }
         }
         st.ctrl[BC_NLIVE_ROWS] = run;
+        st.ctrl[BC_NLIVE_CANDS] = live;
     }
 }
-void launch_beam_prepare(const BeamState& st, int C, int W, int dl, cudaStream_t s) {
-    beam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, W, dl);
+void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s) {
+    beam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, beam, W, dl);
 }
+
+// ---- KV-cached decoder pass ---------------------------------------------------------------------------------
+// Row t = (live candidate g, draft n, position i): token = last token of the candidate (i = 0) or draft token i-1,
+// sequence position front + i.  Row order matches c_rowbase (rows of live candidate g start at g * N).
+template <typename ActT>
+__global__ void beam_embed_cached_kernel(BeamState st, int beam, int dl, const float* __restrict__ table, const float* __restrict__ pe,
+                                         int E, float* __restrict__ x, ActT* __restrict__ xh) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int per_c = st.N * (dl + 1);
+    if (t >= st.ctrl[BC_NLIVE_CANDS] * per_c) return;
+    const int g = t / per_c, r = t % per_c, n = r / (dl + 1), i = r % (dl + 1);
+    const int c = st.live_cand[g], q = c / beam, f = st.c_front[c];
+    const int tok = (i == 0) ? st.cand_cur[(long long)c * st.ldw + f] : st.drafts[((long long)q * st.N + n) * st.dl0 + i - 1];
+    const float* e = table + (long long)tok * E;
+    const float* p = pe + (long long)(f + i + 1) * E;
+    for (int col = lane; col < E; col += 32) {
+        const float v = e[col] + p[col];
+        x[(long long)t * E + col] = v;
+        if (xh) xh[(long long)t * E + col] = from_f32<ActT>(v);
+    }
+}
+template <typename ActT>
+void launch_beam_embed_cached(const BeamState& st, int beam, int max_rows, int dl, const float* table, const float* pe, int E,
+                              float* x, ActT* xh, cudaStream_t s) {
+    const int T = max_rows * (dl + 1);
+    if (T <= 0) return;
+    beam_embed_cached_kernel<ActT><<<(T + 7) / 8, 256, 0, s>>>(st, beam, dl, table, pe, E, x, xh);
+}
+template void launch_beam_embed_cached<float>(const BeamState&, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
+template void launch_beam_embed_cached<__nv_bfloat16>(const BeamState&, int, int, int, const float*, const float*, int, float*, __nv_bfloat16*,
+                                                      cudaStream_t);
+
+template <typename ActT>
+__global__ void beam_cache_update_kernel(BeamState st, int dl, const ActT* __restrict__ qkv_all, long long qkv_layer_stride, int qkv_ld,
+                                         int E, const ActT* __restrict__ kc_cur, const ActT* __restrict__ vc_cur, ActT* __restrict__ kc_next,
+                                         ActT* __restrict__ vc_next, long long cache_layer_stride, long long cache_cand_stride) {
+    const int cn = blockIdx.x, l = blockIdx.y;
+    const int parent = st.n_parent[cn];
+    if (parent < 0) return;                         // child of a finished hypothesis: never decoded again
+    const int f = st.c_front[parent], keep = st.n_keep[cn], r = st.n_row[cn];
+    const long long lo = (long long)l * cache_layer_stride;
+    const ActT* ks = kc_cur + lo + (long long)parent * cache_cand_stride;
+    const ActT* vs = vc_cur + lo + (long long)parent * cache_cand_stride;
+    ActT* kd = kc_next + lo + (long long)cn * cache_cand_stride;
+    ActT* vd = vc_next + lo + (long long)cn * cache_cand_stride;
+    // parent prefix: f rows of E elements, 16-byte vectors (E * sizeof(ActT) is a multiple of 16)
+    constexpr int VEC = 16 / (int)sizeof(ActT);
+    const long long nvec = (long long)f * E / VEC;
+    const uint4* ks4 = reinterpret_cast<const uint4*>(ks);
+    const uint4* vs4 = reinterpret_cast<const uint4*>(vs);
+    uint4* kd4 = reinterpret_cast<uint4*>(kd);
+    uint4* vd4 = reinterpret_cast<uint4*>(vd);
+    for (long long i = threadIdx.x; i < nvec; i += blockDim.x) { kd4[i] = ks4[i]; vd4[i] = vs4[i]; }
+    // positions f .. f + keep from the chosen draft row of this iteration
+    const ActT* src = qkv_all + (long long)l * qkv_layer_stride + (long long)r * (dl + 1) * qkv_ld;
+    for (int idx = threadIdx.x; idx < (keep + 1) * E; idx += blockDim.x) {
+        const int i = idx / E, col = idx % E;
+        kd[(long long)(f + i) * E + col] = src[(long long)i * qkv_ld + E + col];
+        vd[(long long)(f + i) * E + col] = src[(long long)i * qkv_ld + 2 * E + col];
+    }
+}
+template <typename ActT>
+void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld,
+                              int E, const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
+                              long long cache_cand_stride, cudaStream_t s) {
+    dim3 grid(st.B * st.K, n_layers);
+    beam_cache_update_kernel<ActT><<<grid, 256, 0, s>>>(st, dl, qkv_all, qkv_layer_stride, qkv_ld, E, kc_cur, vc_cur, kc_next, vc_next,
+                                                        cache_layer_stride, cache_cand_stride);
+}
+template void launch_beam_cache_update<float>(const BeamState&, int, const float*, long long, int, int, int, const float*, const float*, float*,
+                                              float*, long long, long long, cudaStream_t);
+template void launch_beam_cache_update<__nv_bfloat16>(const BeamState&, int, const __nv_bfloat16*, long long, int, int, int,
+                                                      const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, long long,
+                                                      long long, cudaStream_t);
 
 __global__ void beam_fill_rows_kernel(BeamState st, int C, int beam, int W, int dl) {
     const int c = blockIdx.x / st.N, n = blockIdx.x % st.N;
@@ -311,7 +393,12 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             }
             dst[col] = t;
         }
-        if (threadIdx.x == 0) st.acc_stat[q * K + k] = fin ? -1 : p;
+        if (threadIdx.x == 0) {
+            st.acc_stat[q * K + k] = fin ? -1 : p;
+            st.n_parent[q * K + k] = fin ? -1 : c;
+            st.n_keep[q * K + k] = p;
+            st.n_row[q * K + k] = r;
+        }
     }
 }
 void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s) {

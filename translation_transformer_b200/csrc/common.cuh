@@ -103,6 +103,7 @@ enum BeamCtrl : int {
     BC_EMPTY_COLS = 3,    // min over new candidates of the number of PAD columns
     BC_ACCEPTED = 4,      // accepted draft tokens of the surviving hypotheses (reference accepted_tokens_num)
     BC_PRODUCED = 5,      // reference produced_non_pad_tokens
+    BC_NLIVE_CANDS = 6,   // unfinished candidates (groups of the KV-cached decoder pass)
     BC_COUNT = 8
 };
 

@@ -124,7 +124,7 @@ struct ttb_engine {
     // forward workspace (typed by the precision's activation type at use)
     DevBuf x, xh, y, qkv, att, q2, hid, logits, tok32, keytok32, pred;
     // encoder products / decoding state
-    DevBuf src32, srclen, desc, memory, memh, crosskv, kcache, vcache, drafts, gen, front, active, ctrl, sel, out64;
+    DevBuf src32, srclen, desc, memory, memh, crosskv, kcache, vcache, kcache2, vcache2, drafts, gen, front, active, ctrl, sel, out64;
     int* h_ctrl = nullptr;  // pinned snapshots of ctrl for lagged polling
     cudaEvent_t poll_ev[4]{};
     cudaEvent_t t0{}, t1{};
@@ -728,13 +728,24 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const long long TS = (long long)B * Ls;
     const int Cmax = B * K, Rmax = Cmax * N;
     const int ldw = max_len + D0 + 4;
-    const long long Tmax = (long long)Rmax * ldw;
+    // KV-cached pass (default): only the dl+1 scored positions of every (candidate, draft) row go through the decoder,
+    // the prefix of a candidate is served from its self-attention cache, which follows the hypotheses through the
+    // re-parenting of every step.  TTB_BEAM_NO_CACHE=1 keeps the full-prefix recomputation (A/B comparisons).
+    static const bool no_cache = [] { const char* v = getenv("TTB_BEAM_NO_CACHE"); return v && v[0] == '1'; }();
+    const bool cached = !no_cache;
+    const long long Tc = (long long)Rmax * (D0 + 1);
+    const long long Tmax = cached ? Tc : (long long)Rmax * ldw;
 
     if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
     if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
     if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
     if (e->drafts.ensure((size_t)B * N * D0 * sizeof(int))) return 1;
-    if (ensure_work<ActT>(e, std::max(Tmax, TS), 1)) return 1;
+    if (ensure_work<ActT>(e, std::max(Tmax, TS), cached ? n_dec : 1)) return 1;
+    const long long cache_c_stride = (long long)ldw * E, cache_l_stride = (long long)Cmax * ldw * E;
+    if (cached) {
+        const size_t cbytes = (size_t)n_dec * cache_l_stride * sizeof(ActT);
+        if (e->kcache.ensure(cbytes) || e->vcache.ensure(cbytes) || e->kcache2.ensure(cbytes) || e->vcache2.ensure(cbytes)) return 1;
+    }
     DevBuf& bb = e->beam;
     // one arena for the small beam buffers
     size_t off = 0;
@@ -747,6 +758,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t n_rp = (size_t)Rmax * (D0 + 1);
     const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
     const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4);
+    const size_t o_lc = take(Cmax * 4), o_lq = take(Cmax * 4), o_cf = take(Cmax * 4), o_np = take(Cmax * 4), o_nk = take(Cmax * 4), o_nr = take(Cmax * 4);
     if (bb.ensure(off)) return 1;
     char* base = bb.as<char>();
 
@@ -771,6 +783,13 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.topv = (float*)(base + o_topv); st.topi = (int*)(base + o_topi); st.nkeep = (int*)(base + o_keep);
     st.lmax = (float*)(base + o_max); st.lsum = (float*)(base + o_sum);
     st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
+    st.live_cand = (int*)(base + o_lc); st.live_query = (int*)(base + o_lq); st.c_front = (int*)(base + o_cf);
+    st.n_parent = (int*)(base + o_np); st.n_keep = (int*)(base + o_nk); st.n_row = (int*)(base + o_nr);
+    ActT* kc_cur = cached ? e->kcache.as<ActT>() : nullptr;
+    ActT* vc_cur = cached ? e->vcache.as<ActT>() : nullptr;
+    ActT* kc_next = cached ? e->kcache2.as<ActT>() : nullptr;
+    ActT* vc_next = cached ? e->vcache2.as<ActT>() : nullptr;
+    const int* n_live_cands = st.ctrl + BC_NLIVE_CANDS;
     float* xg = (float*)(base + o_xg);
     ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
     float* logits = (float*)(base + o_lg);
@@ -787,27 +806,51 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         if (grow > 0) W += grow;
         TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
         const int R = C * N;
-        { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, W, dl, s); }
-        { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, W, dl, s); }
-        RowCount rows(R * W, n_live, W);
-        { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
-        auto self_attn = [&](int, ActT* qkv, ActT* att) {
-            attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, R, n_live, W, W, W, nullptr,
-                 st.rows_tok, W, e->d.tgt_pad_token_idx, true, H, HD, s);
-        };
-        auto cross_attn = [&](int l, ActT* q2, ActT* att) {
-            const ActT* kv = crosskv + (long long)l * TS * 2 * E;
-            attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, W, Ls, Ls, st.row_query,
-                 src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
-        };
-        if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
-        { Scope sc(e, KC_MISC, s); launch_beam_gather<ActT>(st, x, xh, R, W, dl, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
-        RowCount rp_rows(R * (dl + 1), n_live, dl + 1);
-        if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
+        { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, W, dl, s); }
+        if (cached) {
+            RowCount rows(R * (dl + 1), n_live, dl + 1);
+            { Scope sc(e, KC_EMBED, s); launch_beam_embed_cached<ActT>(st, beam, R, dl, e->tgt_emb, e->pe, E, x, xh, s); }
+            auto self_attn = [&](int l, ActT* qkv, ActT* att) {
+                spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, C, n_live_cands,
+                          st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, N, dl, H, HD, ldw, s);
+            };
+            auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+                const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+                attn(q2, E, kv, kv + E, 2 * E, att, E, C, n_live_cands, N * (dl + 1), Ls, Ls, st.live_query,
+                     src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+            };
+            if (decoder_stack<ActT>(e, rows, n_dec, Tc * 3 * E, self_attn, cross_attn, s)) return 1;
+            // every decoder row is a scored position: logits straight from the residual stream
+            if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits, V, rows, false, s)) return 1;
+        } else {
+            { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, W, dl, s); }
+            RowCount rows(R * W, n_live, W);
+            { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
+            auto self_attn = [&](int, ActT* qkv, ActT* att) {
+                attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, R, n_live, W, W, W, nullptr,
+                     st.rows_tok, W, e->d.tgt_pad_token_idx, true, H, HD, s);
+            };
+            auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+                const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+                attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, W, Ls, Ls, st.row_query,
+                     src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+            };
+            if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
+            { Scope sc(e, KC_MISC, s); launch_beam_gather<ActT>(st, x, xh, R, W, dl, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
+            RowCount rp_rows(R * (dl + 1), n_live, dl + 1);
+            if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
+        }
         { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, iters, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_control(st, W, s); }
+        if (cached) {
+            Scope sc(e, KC_CACHE_APPEND, s);
+            launch_beam_cache_update<ActT>(st, dl, e->qkv.as<ActT>(), Tc * 3 * E, n_dec, 3 * E, E, kc_cur, vc_cur, kc_next, vc_next,
+                                           cache_l_stride, cache_c_stride, s);
+            std::swap(kc_cur, kc_next);
+            std::swap(vc_cur, vc_next);
+        }
         TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         TTB_CUDA_OK(cudaStreamSynchronize(s));
         ++iters;
@@ -1016,7 +1059,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     }
     DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
                       &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
-                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam, &e->srclen, &e->desc};
+                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam, &e->srclen, &e->desc, &e->kcache2, &e->vcache2};
     for (DevBuf* b : bufs) b->release();
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);

@@ -145,13 +145,26 @@ struct BeamState {
     int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows
     float* topv; int* topi; int* nkeep; float* lmax; float* lsum;      // per (row, position) statistics
     int* trace_nacc; int* trace_pick;     // optional [iter][B*K][N] / [iter][B*K]
+    // KV-cached decoder pass: live candidates as attention groups, cache bookkeeping of the new candidates
+    int* live_cand; int* live_query;      // [live candidates] candidate index / query index
+    int* c_front;                         // [B*K] cached positions of a candidate = first free slot - 1
+    int* n_parent; int* n_keep; int* n_row;   // [B*K] new candidate: parent (-1: finished parent), accepted draft tokens, decoder row
 };
 void launch_beam_init(const BeamState& st, cudaStream_t s);
-void launch_beam_prepare(const BeamState& st, int C, int W, int dl, cudaStream_t s);
+void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
 void launch_beam_fill_rows(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
 template <typename ActT>
 void launch_beam_gather(const BeamState& st, const float* x, const ActT* xh, int max_rows, int W, int dl, int E,
                         float* xg, ActT* xgh, cudaStream_t s);
+// KV-cached pass: embeds (last token, draft tokens) of every live (candidate, draft) row at positions front .. front+dl
+template <typename ActT>
+void launch_beam_embed_cached(const BeamState& st, int beam, int max_rows, int dl, const float* table, const float* pe, int E,
+                              float* x, ActT* xh, cudaStream_t s);
+// new candidate c' <- cache of its parent [0, front) + K/V of positions front .. front + n_keep of the chosen draft row
+template <typename ActT>
+void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld,
+                              int E, const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
+                              long long cache_cand_stride, cudaStream_t s);
 void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s);
 void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s);
 void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s);

@@ -1,8 +1,16 @@
-"""Oracle (test infrastructure): speculative beam search ("try all the drafts" mode), restated.
+"""Oracle (test infrastructure): speculative beam search, both draft modes, restated.
 
 Reference: /root/reference/src/decoding/speculative_decoding.py:241-598
 (`TranslationInferenceBeamSearchSpeculative.generate_trying_all_the_drafts`, `sample`,
-`calculate_n_accepted_in_drafts`, `topk_in_each_group`, `mask_with_num_logits_according_nucleus`).
+`calculate_n_accepted_in_drafts`, `topk_in_each_group`, `mask_with_num_logits_according_nucleus`) and :600-845
+(`generate_with_smart_drafts`, `get_vocab_tokens_bool_lib` :402-420).
+
+`smart_drafts_mode=True` differs from "try all the drafts" in where a candidate's drafts come from: a library of
+`Ls - 5` windows of `draft_len + 1` source tokens (BOS included) is built once per query; a candidate only tries the
+windows whose FIRST token equals its own last token (at most `n_drafts` of them, in library order; window 0 when
+there is none) and the remaining `draft_len` tokens of the window are the draft (:690-735).  Candidates therefore
+own a different number of decoder rows; the best draft of a candidate is picked by `topk(1)` over its accepted
+lengths padded with -1 to the longest group of the iteration (`topk_in_each_group`, :206-223).
 
 Per iteration, for every candidate (beam) of every query:
 
@@ -47,7 +55,10 @@ def truncated_support(logits_row: torch.Tensor, nucleus: float, max_keep: int):
 
 class BeamSearchSpeculativeOracle:
     def __init__(self, model, max_len: int, n_best: int, draft_len: int, n_drafts: int, vocab_size: int,
-                 pad_token: int, bos_token: int, eos_token: int, C_token: int, keep_trace: bool = False):
+                 pad_token: int, bos_token: int, eos_token: int, C_token: int, keep_trace: bool = False,
+                 smart_drafts_mode: bool = False):
+        self.smart_drafts_mode = smart_drafts_mode
+        self.model_input_lines_num = 0
         self.model = model
         self.max_len = max_len
         self.vocab_size = vocab_size
@@ -82,9 +93,27 @@ class BeamSearchSpeculativeOracle:
     def generate(self, src: torch.Tensor) -> torch.Tensor:
         PAD, EOS, K = self.pad, self.eos, self.n_best
         B = src.shape[0]
-        drafts_all = make_drafts(src[:, 1:].numpy(), self.draft_len, self.requested_drafts_num, self.min_draft_len,
-                                 self.max_draft_len, EOS, PAD, self.C_token)           # (B, N, dl0)
-        N, dl = drafts_all.shape[1], drafts_all.shape[2]
+        smart = self.smart_drafts_mode
+        if smart:
+            # library of Ls - 5 windows of draft_len + 1 tokens, BOS column included (:603-615); the first token of a
+            # window is its key, the rest the draft
+            lib = make_drafts(src.numpy(), self.draft_len + 1, src.shape[1] - 5, self.min_draft_len, self.max_draft_len,
+                              EOS, PAD, self.C_token)                                  # (B, n_lib, dl0 + 1)
+            drafts_all = lib[:, :, 1:]
+            dl = drafts_all.shape[2]
+            # per (query, token): the library windows that start with the token, first n_drafts of them, window 0 if none
+            by_token = []
+            for b in range(B):
+                d = {}
+                for n in range(lib.shape[1]):
+                    d.setdefault(int(lib[b, n, 0]), [])
+                    if len(d[int(lib[b, n, 0])]) < self.requested_drafts_num:
+                        d[int(lib[b, n, 0])].append(n)
+                by_token.append(d)
+        else:
+            drafts_all = make_drafts(src[:, 1:].numpy(), self.draft_len, self.requested_drafts_num, self.min_draft_len,
+                                     self.max_draft_len, EOS, PAD, self.C_token)       # (B, N, dl0)
+            dl = drafts_all.shape[2]
         src_pad = src == self.model.src_pad_token_i
         memory = self.model.encode_src(src, src_pad)
 
@@ -109,25 +138,38 @@ class BeamSearchSpeculativeOracle:
                 pads = np.nonzero(cand[c] == PAD)[0]
                 slots[c] = pads[:dl]
             finished = (cand == EOS).any(axis=1)
-            rows = np.repeat(cand, N, axis=0)
-            row_query = np.repeat(cand_query, N)
+            # drafts tried by every candidate (indices into drafts_all[query])
+            if smart:
+                cand_drafts = []
+                for c in range(C):
+                    last = int(cand[c, int((cand[c] != PAD).sum()) - 1])      # last meaningful token (:693-697)
+                    cand_drafts.append(by_token[int(cand_query[c])].get(last, [0]))
+            else:
+                cand_drafts = [list(range(drafts_all.shape[1]))] * C
+            counts = np.array([len(x) for x in cand_drafts])
+            row_base = np.concatenate([[0], np.cumsum(counts)])
+            self.model_input_lines_num += int(counts.sum())
+            row_cand = np.repeat(np.arange(C), counts)
+            rows = cand[row_cand].copy()
+            row_query = cand_query[row_cand]
             for c in range(C):
-                for n in range(N):
-                    rows[c * N + n, slots[c]] = drafts_all[cand_query[c], n, :dl]
-            first_slot = np.repeat(slots[:, 0], N)
+                for j, n in enumerate(cand_drafts[c]):
+                    rows[row_base[c] + j, slots[c]] = drafts_all[cand_query[c], n, :dl]
+            first_slot = slots[row_cand, 0]
             contiguous = (slots[:, -1] - slots[:, 0] == dl - 1).all()
             if not contiguous:
                 raise NotImplementedError("PAD predicted inside a sequence: non-contiguous draft slots")
-            logits = self._logits(rows, np.repeat(~finished, N), memory, src_pad, row_query, dl, first_slot)  # (C*N, dl+1, V)
+            logits = self._logits(rows, ~finished[row_cand], memory, src_pad, row_query, dl, first_slot)  # (rows, dl+1, V)
 
-            # accepted length of every draft, best draft per candidate (:539-558)
-            n_acc = np.zeros((C, N), dtype=np.int64)
+            # accepted length of every draft, best draft per candidate (:539-558 / :769-780)
+            longest = int(counts.max())
+            n_acc = np.full((C, longest), -1, dtype=np.int64)     # ragged groups are padded with -1 before topk(1)
             for c in range(C):
-                for n in range(N):
+                for j, n in enumerate(cand_drafts[c]):
                     a = 0
-                    while a < dl and int(drafts_all[cand_query[c], n, a]) in truncated_support(logits[c * N + n, a], 0.9975, K):
+                    while a < dl and int(drafts_all[cand_query[c], n, a]) in truncated_support(logits[row_base[c] + j, a], 0.9975, K):
                         a += 1
-                    n_acc[c, n] = a
+                    n_acc[c, j] = a
             pick = np.array([topk_indices(n_acc[c], 1)[0] for c in range(C)])
 
             # leaves of every candidate's tree (:294-400)
@@ -135,9 +177,9 @@ class BeamSearchSpeculativeOracle:
             per_query = [[] for _ in range(B)]
             for c in range(C):
                 q = int(cand_query[c])
-                n = int(pick[c])
-                a = int(n_acc[c, n])
-                lg = logits[c * N + n]                                # (dl+1, V)
+                a = int(n_acc[c, pick[c]])
+                n = int(cand_drafts[c][pick[c]])
+                lg = logits[row_base[c] + pick[c]]                    # (dl+1, V)
                 logprob = lg.softmax(-1).log()
                 draft = drafts_all[q, n, :dl].copy()
                 if a != dl:

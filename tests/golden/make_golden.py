@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py [--only model,drafts,greedy,beam,standard]
+    python tests/golden/make_golden.py [--only model,drafts,greedy,beam,beam_smart,standard]
 
 What it does
   * stubs `pytorch_lightning` (not installed here; only class bases are needed to import
@@ -297,6 +297,9 @@ if __name__ == "__main__":
     if "beam" in todo:
         from make_golden_beam import gen_beam
         gen_beam(ref)
+    if "beam_smart" in todo:
+        from make_golden_beam import gen_beam_smart
+        gen_beam_smart(ref)
     if "standard" in todo:
         from make_golden_standard import gen_standard
         gen_standard(ref)

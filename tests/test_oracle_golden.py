@@ -154,6 +154,43 @@ def test_beam_speculative_oracle_matches_reference(case):
     assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))               # chosen draft indices
 
 
+def _beam_smart_cases():
+    return load_json("beam_smart.json")
+
+
+@pytest.mark.parametrize("case", _beam_smart_cases(), ids=lambda c: c["id"])
+def test_beam_speculative_smart_drafts_oracle_matches_reference(case):
+    """smart_drafts_mode=True (speculative_decoding.py:600-845)."""
+    from oracle.beam_speculative import BeamSearchSpeculativeOracle
+    z = load_npz("beam_smart.npz")
+    cfg, sd = case_weights(case)
+    model = OracleTransformer(sd, cfg.num_heads)
+    seen = []
+    inner = model.decode_tgt
+
+    def spy(tgt, memory, mask):
+        seen.append(sha_tokens(tgt.numpy()))
+        return inner(tgt, memory, mask)
+
+    model.decode_tgt = spy
+    gen = BeamSearchSpeculativeOracle(model, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                      case["vocab"], 0, 1, 2, case["C_token"], keep_trace=True, smart_drafts_mode=True)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+    if case["error"] is not None:
+        with pytest.raises(AssertionError):
+            gen.generate(src)
+        return
+    out = gen.generate(src)
+    assert np.array_equal(out.numpy(), z[case["id"] + "_out"].astype(np.int64))        # all n_best hypotheses, in order
+    assert seen == case["decoder_input_sha1"]                                         # every decoder input
+    assert (gen.model_calls_num, gen.accepted_tokens_num, gen.produced_non_pad_tokens, gen.model_input_lines_num) == \
+        (case["model_calls"], case["accepted_tokens"], case["produced_non_pad_tokens"], case["model_input_lines_num"])
+    nacc = np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace])
+    pick = np.concatenate([t["pick"] for t in gen.trace])
+    assert np.array_equal(nacc, z[case["id"] + "_nacc"].astype(np.int64))               # accepted lengths (padded with -1)
+    assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))               # chosen draft of every candidate
+
+
 # ---------------------------------------------------------------------------------------------
 # standard (non-speculative) decoding, standard_decoding.py
 def _standard_cases():

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TTB_ABI_VERSION 1
+#define TTB_ABI_VERSION 2
 
 #define TTB_PRECISION_FP32 0 /* fp32 FMA GEMMs, exact-parity path (1e-5 logits)            */
 #define TTB_PRECISION_BF16 1 /* tcgen05 bf16 GEMMs, fp32 accumulate (1e-2 logits)          */
@@ -111,15 +111,18 @@ int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, i
                              int32_t pad_token, int32_t bos_token, int32_t eos_token, int64_t* out_dev, int32_t* out_width,
                              ttb_generate_stats* stats, void* stream);
 
-/* ---- speculative_decoding.py:422 TranslationInferenceBeamSearchSpeculative.generate(src),
- * smart_drafts_mode=False ("try all the drafts", :428-598).  out_dev must hold
- * B * n_best * (max_len + clamp(draft_len,5,200) + 4) int64; the hypotheses are written densely as
- * (B, n_best, *out_width).  Optional traces: trace_nacc_dev (max_len, B*n_best, n_drafts) accepted
- * length of every draft, trace_pick_dev (max_len, B*n_best) chosen draft, per iteration. */
+/* ---- speculative_decoding.py:422 TranslationInferenceBeamSearchSpeculative.generate(src)
+ * smart_drafts_mode = 0: "try all the drafts" (:428-598), every candidate tries the n_drafts source windows;
+ * smart_drafts_mode = 1: :600-845, a candidate tries the windows of a (Ls - 5)-window library whose first token equals
+ * its last token (at most n_drafts of them).  out_dev must hold B * n_best * (max_len + clamp(draft_len,5,200) + 4)
+ * int64; the hypotheses are written densely as (B, n_best, *out_width).  Optional traces: trace_nacc_dev
+ * (max_len, B*n_best, n_drafts) accepted length of every draft (-1 behind a candidate's last draft), trace_pick_dev
+ * (max_len, B*n_best) chosen draft, per iteration. */
 int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,
-                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t pad_token, int32_t bos_token,
-                                  int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev, int32_t* out_width,
-                                  int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats, void* stream);
+                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t smart_drafts_mode, int32_t pad_token,
+                                  int32_t bos_token, int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev,
+                                  int32_t* out_width, int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats,
+                                  void* stream);
 
 /* ---- instrumentation (bench.py): per-kernel-class CUDA-event timing on the launching stream.
  * class_mask bit i enables class i (names via ttb_kernel_class_name); totals accumulate over

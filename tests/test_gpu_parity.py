@@ -362,6 +362,63 @@ def test_beam_speculative_fp32_matches_reference_golden(dev, case):
     eng.close()
 
 
+def _beam_smart_cases():
+    return load_json("beam_smart.json")
+
+
+@pytest.mark.parametrize("case", _beam_smart_cases(), ids=lambda c: c["id"])
+def test_beam_speculative_smart_drafts_fp32_matches_reference_golden(dev, case):
+    """smart_drafts_mode=True (speculative_decoding.py:600-845): hypotheses, counters, accepted length of every tried
+    draft (ragged groups padded with -1 like the reference's topk_in_each_group) and the chosen drafts, bit-exact."""
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    z = load_npz("beam_smart.npz")
+    cfg, sd = case_weights(case)
+    eng = _engine(cfg, sd, "fp32")
+    gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                                    case["vocab"], True, 0, 1, 2, case["C_token"], keep_trace=True)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)).to(dev)
+    if case["error"] is not None:
+        with pytest.raises(AssertionError):
+            gen.generate(src)
+        eng.close()
+        return
+    out = gen.generate(src).cpu().numpy()
+    ref = z[case["id"] + "_out"].astype(np.int64)
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)
+    assert (gen.model_calls_num, gen.accepted_tokens_num, gen.produced_non_pad_tokens) == \
+        (case["model_calls"], case["accepted_tokens"], case["produced_non_pad_tokens"])
+    ref_nacc, ref_pick = z[case["id"] + "_nacc"].astype(np.int64), z[case["id"] + "_pick"].astype(np.int64)
+    o_n = o_p = 0
+    assert len(gen.trace) == len(case["topk1_shapes"])
+    for t, (C, L) in zip(gen.trace, case["topk1_shapes"]):
+        na = t["n_accepted"]
+        assert na.shape[0] == C
+        assert np.array_equal(na[:, :L], ref_nacc[o_n:o_n + C * L].reshape(C, L))
+        assert (na[:, L:] == -1).all()
+        assert np.array_equal(t["pick"], ref_pick[o_p:o_p + C])
+        o_n += C * L
+        o_p += C
+    eng.close()
+
+
+def test_beam_speculative_smart_drafts_bf16_runs(dev):
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    z = load_npz("beam_smart.npz")
+    case = [c for c in _beam_smart_cases() if c["id"] == "smart1"][0]
+    cfg, sd = case_weights(case)
+    src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64)).to(dev)
+    eng = _engine(cfg, sd, "bf16")
+    gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"],
+                                                    case["vocab"], True, 0, 1, 2, case["C_token"])
+    out = gen.generate(src).cpu().numpy()
+    ref = z[case["id"] + "_out"].astype(np.int64)
+    assert out.shape[:2] == ref.shape[:2]
+    same = sum(int(out.shape[2] == ref.shape[2] and np.array_equal(out[b, 0], ref[b, 0])) for b in range(ref.shape[0]))
+    assert same >= ref.shape[0] // 2, (same, ref.shape[0])
+    eng.close()
+
+
 def test_beam_speculative_bf16_runs_and_is_consistent(dev):
     """bf16 hypotheses may differ from fp32 at near-ties; check structure and that the best hypothesis
     of most queries matches the fp32 engine."""

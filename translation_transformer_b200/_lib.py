@@ -10,7 +10,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libttb200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PRECISION = {"fp32": 0, "bf16": 1}
 ERR_REF_INDEX, ERR_REF_SHAPE, ERR_REF_ASSERT = 10, 11, 12
 
@@ -49,7 +49,7 @@ SIGNATURES = {
                                       C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_beam_search_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 +
                                  [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(GenerateStats), C.c_void_p]),
-    "ttb_beam_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 11 +
+    "ttb_beam_speculative_generate": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 12 +
                                       [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(GenerateStats), C.c_void_p]),
     "ttb_kernel_class_count": (C.c_int, []),
     "ttb_kernel_class_name": (C.c_char_p, [C.c_int32]),

@@ -18,6 +18,39 @@
 
 namespace ttb {
 
+// drafts of candidate c (query q): all N source drafts, or in smart mode the library windows keyed by its last token
+__device__ __forceinline__ int cand_n_drafts(const BeamState& st, int c) { return st.smart ? st.c_cnt[c] : st.N; }
+__device__ __forceinline__ const int* cand_draft(const BeamState& st, int c, int q, int j) {
+    if (!st.smart) return st.drafts + ((long long)q * st.N + j) * st.dl0;
+    const int n = st.tok_list[((long long)q * st.V + st.c_last[c]) * st.N + j];
+    return st.drafts + ((long long)q * st.n_lib + n) * st.dl0 + 1;      // skip the key token
+}
+
+// ---- smart drafts: windows of the library grouped by their first token (get_vocab_tokens_bool_lib, :402-420) ------
+__global__ void beam_build_lib_kernel(BeamState st) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= st.B * st.V) return;
+    const int b = w / st.V, v = w % st.V;
+    int* list = st.tok_list + (long long)w * st.N;
+    int cnt = 0;
+    for (int n0 = 0; n0 < st.n_lib && cnt < st.N; n0 += 32) {
+        const int n = n0 + lane;
+        const bool hit = n < st.n_lib && st.drafts[((long long)b * st.n_lib + n) * st.dl0] == v;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < st.N) list[pos] = n;                 // the first N windows in library order (:419)
+        cnt += __popc(m);
+    }
+    if (lane == 0) {
+        if (cnt == 0) { list[0] = 0; cnt = 1; }              // "each line needs at least one draft" (:418)
+        st.tok_cnt[w] = cnt < st.N ? cnt : st.N;
+    }
+}
+void launch_beam_build_lib(const BeamState& st, cudaStream_t s) {
+    const int warps = st.B * st.V;
+    beam_build_lib_kernel<<<(warps + 7) / 8, 256, 0, s>>>(st);
+}
+
 // ---- prepare ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int W, int dl) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -35,19 +68,46 @@ __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C,
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int run = 0, live = 0;
+        int run = 0, live = 0, lmax = 0;
         for (int c = 0; c < C; ++c) {
             st.c_rowbase[c] = run;
-            st.c_front[c] = max(0, st.c_slot0[c] - 1);   // clamped: an inconsistent hypothesis raises BC_ERROR, its rows are discarded
+            const int slot0 = st.c_slot0[c];
+            st.c_front[c] = max(0, slot0 - 1);   // clamped: an inconsistent hypothesis raises BC_ERROR, its rows are discarded
+            int cnt = st.N;
+            if (st.smart) {
+                // last meaningful token = the one before the first PAD (hypotheses without interior PADs), or the last
+                // column when the row has no PAD at all (:693-697)
+                const int last = st.cand_cur[(long long)c * st.ldw + (slot0 >= 1 ? slot0 - 1 : (slot0 < 0 ? W - 1 : 0))];
+                st.c_last[c] = last;
+                cnt = st.tok_cnt[(c / beam) * st.V + last];
+                st.c_cnt[c] = cnt;
+            }
+            lmax = max(lmax, cnt);
             if (!st.c_fin[c]) {
-                run += st.N;
-                st.live_cand[live] = c;
-                st.live_query[live] = c / beam;
+                run += cnt;
+                if (!st.smart) {
+                    st.live_cand[live] = c;
+                    st.live_query[live] = c / beam;
+                }
                 ++live;
             }
         }
         st.ctrl[BC_NLIVE_ROWS] = run;
-        st.ctrl[BC_NLIVE_CANDS] = live;
+        st.ctrl[BC_NLIVE_CANDS] = st.smart ? run : live;     // attention groups: candidates, or single rows in smart mode
+        st.ctrl[BC_LMAX] = lmax;
+    }
+    __syncthreads();
+    if (st.smart) {   // every live row is its own attention group: row -> (candidate, query, library window)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (st.c_fin[c]) continue;
+            const int q = c / beam, base = st.c_rowbase[c], cnt = st.c_cnt[c];
+            const int* list = st.tok_list + ((long long)q * st.V + st.c_last[c]) * st.N;
+            for (int j = 0; j < cnt; ++j) {
+                st.live_cand[base + j] = c;
+                st.live_query[base + j] = q;
+                st.row_draft[base + j] = list[j];
+            }
+        }
     }
 }
 void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s) {
@@ -62,11 +122,20 @@ __global__ void beam_embed_cached_kernel(BeamState st, int beam, int dl, const f
                                          int E, float* __restrict__ x, ActT* __restrict__ xh) {
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int per_c = st.N * (dl + 1);
-    if (t >= st.ctrl[BC_NLIVE_CANDS] * per_c) return;
-    const int g = t / per_c, r = t % per_c, n = r / (dl + 1), i = r % (dl + 1);
-    const int c = st.live_cand[g], q = c / beam, f = st.c_front[c];
-    const int tok = (i == 0) ? st.cand_cur[(long long)c * st.ldw + f] : st.drafts[((long long)q * st.N + n) * st.dl0 + i - 1];
+    if (t >= st.ctrl[BC_NLIVE_ROWS] * (dl + 1)) return;
+    const int r = t / (dl + 1), i = t % (dl + 1);
+    int c, f, tok;
+    if (st.smart) {
+        c = st.live_cand[r];
+        f = st.c_front[c];
+        tok = (i == 0) ? st.cand_cur[(long long)c * st.ldw + f]
+                       : st.drafts[((long long)(c / beam) * st.n_lib + st.row_draft[r]) * st.dl0 + i];   // window token i (0 = key)
+    } else {
+        const int g = r / st.N, n = r % st.N;
+        c = st.live_cand[g];
+        f = st.c_front[c];
+        tok = (i == 0) ? st.cand_cur[(long long)c * st.ldw + f] : st.drafts[((long long)(c / beam) * st.N + n) * st.dl0 + i - 1];
+    }
     const float* e = table + (long long)tok * E;
     const float* p = pe + (long long)(f + i + 1) * E;
     for (int col = lane; col < E; col += 32) {
@@ -245,20 +314,25 @@ __global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, in
     if (c >= C) return;
     const int q = c / beam, N = st.N, K = st.K;
     const bool fin = st.c_fin[c] != 0;
+    const int m = cand_n_drafts(st, c);                      // drafts of this candidate
+    const int lmax = st.smart ? st.ctrl[BC_LMAX] : N;        // ragged groups are padded with -1 up to the longest (:206-223)
     for (int n = lane; n < N; n += 32) {
-        int a = 0;
-        if (!fin) {
-            const int r = st.c_rowbase[c] + n;
-            const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
-            while (a < dl) {
-                const long long rp = (long long)r * (dl + 1) + a;
-                const int keep = st.nkeep[rp];
-                const int* ti = st.topi + rp * K;
-                const int tok = dr[a];
-                bool in = false;
-                for (int j = 0; j < keep; ++j) in |= (ti[j] == tok);
-                if (!in) break;
-                ++a;
+        int a = -1;
+        if (n < m) {
+            a = 0;
+            if (!fin) {
+                const int r = st.c_rowbase[c] + n;
+                const int* dr = cand_draft(st, c, q, n);
+                while (a < dl) {
+                    const long long rp = (long long)r * (dl + 1) + a;
+                    const int keep = st.nkeep[rp];
+                    const int* ti = st.topi + rp * K;
+                    const int tok = dr[a];
+                    bool in = false;
+                    for (int j = 0; j < keep; ++j) in |= (ti[j] == tok);
+                    if (!in) break;
+                    ++a;
+                }
             }
         }
         st.c_nacc[(long long)c * N + n] = a;
@@ -268,10 +342,10 @@ __global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, in
     __syncwarp();
     if (lane == 0) {
         int pick = 0;
-        if (st.tie_break == 0 && N < 64) {
-            pick = topk1_torch_cpu(s_nacc, N);
+        if (st.tie_break == 0 && lmax < 64) {
+            pick = topk1_torch_cpu(s_nacc, lmax);
         } else {
-            for (int n = 1; n < N; ++n) if (st.c_nacc[(long long)c * N + n] > st.c_nacc[(long long)c * N + pick]) pick = n;
+            for (int n = 1; n < m; ++n) if (st.c_nacc[(long long)c * N + n] > st.c_nacc[(long long)c * N + pick]) pick = n;
         }
         st.c_pick[c] = pick;
         if (st.trace_pick) st.trace_pick[(long long)iter * st.B * K + c] = pick;
@@ -302,7 +376,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         s_pre[cb * (dl + 2)] = 0.f;
         if (!st.c_fin[c]) {
             const int n = st.c_pick[c], a = st.c_nacc[(long long)c * N + n], r = st.c_rowbase[c] + n;
-            const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+            const int* dr = cand_draft(st, c, q, n);
             for (int i = 0; i < a; ++i) {
                 const long long rp = (long long)r * (dl + 1) + i;
                 run += ref_logprob(logits[rp * V + dr[i]], st.lmax[rp], st.lsum[rp]);
@@ -326,7 +400,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                 const long long rp = (long long)r * (dl + 1) + p;
                 const int tok = st.topi[rp * K + j];
                 const float lg = st.topv[rp * K + j];
-                const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+                const int* dr = cand_draft(st, c, q, n);
                 // excluded: the draft token that continues the accepted path (p < a), BOS in the slot of the first
                 // rejected draft token (p == a < dl); entries whose logit is exactly 0.0 vanish in the reference
                 const int excl = (p < dl) ? (p < a ? dr[p] : st.bos) : -1;
@@ -383,7 +457,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         const bool fin = st.c_fin[c] != 0;
         int n = 0, r = 0;
         if (!fin) { n = st.c_pick[c]; r = st.c_rowbase[c] + n; }
-        const int* dr = st.drafts + ((long long)q * N + n) * st.dl0;
+        const int* dr = fin ? st.drafts : cand_draft(st, c, q, n);
         const int tok = fin ? st.pad : st.topi[((long long)r * (dl + 1) + p) * K + j];
         for (int col = threadIdx.x; col < W; col += blockDim.x) {
             int t = src[col];

@@ -104,6 +104,7 @@ enum BeamCtrl : int {
     BC_ACCEPTED = 4,      // accepted draft tokens of the surviving hypotheses (reference accepted_tokens_num)
     BC_PRODUCED = 5,      // reference produced_non_pad_tokens
     BC_NLIVE_CANDS = 6,   // unfinished candidates (groups of the KV-cached decoder pass)
+    BC_LMAX = 7,          // smart drafts: drafts of the candidate that has the most (length the tie-break emulation pads to)
     BC_COUNT = 8
 };
 

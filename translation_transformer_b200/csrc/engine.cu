@@ -717,7 +717,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
 template <typename ActT>
 static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int max_len, int K, int draft_len, int N,
                     int pad, int bos, int eos, int c_token, int tie_break, int64_t* out_dev, int32_t* out_width,
-                    int32_t* trace_nacc, int32_t* trace_pick, ttb_generate_stats* stats, cudaStream_t user_stream) {
+                    int32_t* trace_nacc, int32_t* trace_pick, ttb_generate_stats* stats, cudaStream_t user_stream, bool smart) {
     const int E = e->E(), H = e->d.num_heads, HD = e->HD(), V = e->d.tgt_vocab_size;
     const int n_dec = (int)e->dec.size();
     cudaStream_t s = e->stream;
@@ -725,6 +725,10 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
     const long long launches0 = e->launches;
     const int D0 = std::min(std::max(5, draft_len), 200);       // speculative_decoding.py:278-284
+    // smart_drafts_mode (:600-615): library of Ls - 5 windows of draft_len + 1 tokens (BOS column included), first token = key
+    const int D_lib = std::min(std::max(5, D0 + 1), 200);
+    const int n_lib = Ls - 5;
+    if (smart) TTB_CHECK(n_lib > 0, "The number of drafts must be greater than 0");
     const long long TS = (long long)B * Ls;
     const int Cmax = B * K, Rmax = Cmax * N;
     const int ldw = max_len + D0 + 4;
@@ -733,13 +737,14 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     // re-parenting of every step.  TTB_BEAM_NO_CACHE=1 keeps the full-prefix recomputation (A/B comparisons).
     static const bool no_cache = [] { const char* v = getenv("TTB_BEAM_NO_CACHE"); return v && v[0] == '1'; }();
     const bool cached = !no_cache;
+    TTB_CHECK(cached || !smart, "smart_drafts_mode needs the KV-cached decoder pass (unset TTB_BEAM_NO_CACHE)");
     const long long Tc = (long long)Rmax * (D0 + 1);
     const long long Tmax = cached ? Tc : (long long)Rmax * ldw;
 
     if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
     if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
     if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
-    if (e->drafts.ensure((size_t)B * N * D0 * sizeof(int))) return 1;
+    if (e->drafts.ensure(smart ? (size_t)B * n_lib * D_lib * sizeof(int) : (size_t)B * N * D0 * sizeof(int))) return 1;
     if (ensure_work<ActT>(e, std::max(Tmax, TS), cached ? n_dec : 1)) return 1;
     const long long cache_c_stride = (long long)ldw * E, cache_l_stride = (long long)Cmax * ldw * E;
     if (cached) {
@@ -758,7 +763,9 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t n_rp = (size_t)Rmax * (D0 + 1);
     const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
     const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4);
-    const size_t o_lc = take(Cmax * 4), o_lq = take(Cmax * 4), o_cf = take(Cmax * 4), o_np = take(Cmax * 4), o_nk = take(Cmax * 4), o_nr = take(Cmax * 4);
+    const size_t o_lc = take(Rmax * 4), o_lq = take(Rmax * 4), o_cf = take(Cmax * 4), o_np = take(Cmax * 4), o_nk = take(Cmax * 4), o_nr = take(Cmax * 4);
+    const size_t o_tc = take(smart ? (size_t)B * V * 4 : 4), o_tl = take(smart ? (size_t)B * V * N * 4 : 4), o_cc = take(Cmax * 4),
+                 o_cl = take(Cmax * 4), o_rd = take(Rmax * 4);
     if (bb.ensure(off)) return 1;
     char* base = bb.as<char>();
 
@@ -770,10 +777,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
     ActT* crosskv = e->crosskv.as<ActT>();
     if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
-    { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D0, N, eos, pad, c_token, e->drafts.as<int>(), s); }
+    if (smart) { Scope sc(e, KC_MISC, s); launch_make_drafts(src32, Ls, B, Ls, D_lib, n_lib, eos, pad, c_token, e->drafts.as<int>(), s); }
+    else { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D0, N, eos, pad, c_token, e->drafts.as<int>(), s); }
 
     BeamState st{};
-    st.B = B; st.K = K; st.N = N; st.dl0 = D0; st.V = V; st.pad = pad; st.bos = bos; st.eos = eos; st.ldw = ldw; st.tie_break = tie_break;
+    st.B = B; st.K = K; st.N = N; st.dl0 = smart ? D_lib : D0; st.V = V; st.smart = smart ? 1 : 0; st.n_lib = n_lib; st.pad = pad; st.bos = bos; st.eos = eos; st.ldw = ldw; st.tie_break = tie_break;
     st.cand_cur = (int*)(base + o_cand0); st.cand_next = (int*)(base + o_cand1);
     st.logp_cur = (float*)(base + o_lp0); st.logp_next = (float*)(base + o_lp1);
     st.drafts = e->drafts.as<int>();
@@ -785,6 +793,8 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
     st.live_cand = (int*)(base + o_lc); st.live_query = (int*)(base + o_lq); st.c_front = (int*)(base + o_cf);
     st.n_parent = (int*)(base + o_np); st.n_keep = (int*)(base + o_nk); st.n_row = (int*)(base + o_nr);
+    st.tok_cnt = (int*)(base + o_tc); st.tok_list = (int*)(base + o_tl); st.c_cnt = (int*)(base + o_cc); st.c_last = (int*)(base + o_cl);
+    st.row_draft = (int*)(base + o_rd);
     ActT* kc_cur = cached ? e->kcache.as<ActT>() : nullptr;
     ActT* vc_cur = cached ? e->vcache.as<ActT>() : nullptr;
     ActT* kc_next = cached ? e->kcache2.as<ActT>() : nullptr;
@@ -794,11 +804,12 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
     float* logits = (float*)(base + o_lg);
     { Scope sc(e, KC_MISC, s); launch_beam_init(st, s); }
+    if (smart) { Scope sc(e, KC_MISC, s); launch_beam_build_lib(st, s); }
 
     float* x = e->x.as<float>();
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
     const int* n_live = st.ctrl + BC_NLIVE_ROWS;
-    int W = 1, empty_cols = 0, filled = 1, budget = max_len - filled - 1, dl = D0, C = B, beam = 1, iters = 0;
+    int W = 1, empty_cols = 0, filled = 1, budget = max_len - filled - 1, dl = smart ? D_lib - 1 : D0, C = B, beam = 1, iters = 0;
     int* hc = e->h_ctrl;
     while (budget >= 1 && filled <= max_len) {
         dl = std::min(budget, dl);
@@ -810,13 +821,16 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         if (cached) {
             RowCount rows(R * (dl + 1), n_live, dl + 1);
             { Scope sc(e, KC_EMBED, s); launch_beam_embed_cached<ActT>(st, beam, R, dl, e->tgt_emb, e->pe, E, x, xh, s); }
+            // attention groups: the N rows of a live candidate share its cache prefix; in smart mode candidates own a
+            // different number of rows, so every row is a group of its own
+            const int G = smart ? R : C, n_per_group = smart ? 1 : N;
             auto self_attn = [&](int l, ActT* qkv, ActT* att) {
-                spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, C, n_live_cands,
-                          st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, N, dl, H, HD, ldw, s);
+                spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, G, n_live_cands,
+                          st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, n_per_group, dl, H, HD, ldw, s);
             };
             auto cross_attn = [&](int l, ActT* q2, ActT* att) {
                 const ActT* kv = crosskv + (long long)l * TS * 2 * E;
-                attn(q2, E, kv, kv + E, 2 * E, att, E, C, n_live_cands, N * (dl + 1), Ls, Ls, st.live_query,
+                attn(q2, E, kv, kv + E, 2 * E, att, E, G, n_live_cands, n_per_group * (dl + 1), Ls, Ls, st.live_query,
                      src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
             };
             if (decoder_stack<ActT>(e, rows, n_dec, Tc * 3 * E, self_attn, cross_attn, s)) return 1;
@@ -1238,9 +1252,10 @@ int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, i
 }
 
 int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,
-                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t pad_token, int32_t bos_token,
-                                  int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev, int32_t* out_width,
-                                  int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats, void* stream) {
+                                  int32_t n_best, int32_t draft_len, int32_t n_drafts, int32_t smart_drafts_mode, int32_t pad_token,
+                                  int32_t bos_token, int32_t eos_token, int32_t c_token, int32_t tie_break, int64_t* out_dev,
+                                  int32_t* out_width, int32_t* trace_nacc_dev, int32_t* trace_pick_dev, ttb_generate_stats* stats,
+                                  void* stream) {
     TTB_CHECK(e && e->finalized, "engine not finalized");
     TTB_CHECK(src_dev && out_dev && B > 0 && Ls > 1 && max_len > 2, "bad arguments");
     TTB_CHECK(n_best >= 1 && n_best <= 32, "n_best must be in [1, 32]");
@@ -1253,9 +1268,11 @@ int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t
     TTB_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     return TTB_DISPATCH(e, beam_api<float>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token, eos_token,
-                                           c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s),
+                                           c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s,
+                                           smart_drafts_mode != 0),
                         beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token,
-                                                eos_token, c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s));
+                                                eos_token, c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s,
+                                                smart_drafts_mode != 0));
 }
 
 int ttb_kernel_class_count(void) { return KC_COUNT; }

@@ -149,7 +149,14 @@ struct BeamState {
     int* live_cand; int* live_query;      // [live candidates] candidate index / query index
     int* c_front;                         // [B*K] cached positions of a candidate = first free slot - 1
     int* n_parent; int* n_keep; int* n_row;   // [B*K] new candidate: parent (-1: finished parent), accepted draft tokens, decoder row
+    // smart_drafts_mode (speculative_decoding.py:600-845): `drafts` is the window library [B][n_lib][dl0] whose first
+    // token is the key; a candidate tries the windows that start with its last token
+    int smart, n_lib;
+    int* tok_cnt; int* tok_list;          // [B][V] number of windows per first token (1..N), [B][V][N] their library indices
+    int* c_cnt; int* c_last;              // [B*K] rows (drafts) of a candidate, its last token
+    int* row_draft;                       // [rows] library index of the row's draft (row_cand / row_query: its candidate / query)
 };
+void launch_beam_build_lib(const BeamState& st, cudaStream_t s);
 void launch_beam_init(const BeamState& st, cudaStream_t s);
 void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
 void launch_beam_fill_rows(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);

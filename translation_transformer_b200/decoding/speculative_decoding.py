@@ -75,18 +75,16 @@ class TranslationInferenceGreedySpeculative:
 
 
 class TranslationInferenceBeamSearchSpeculative:
-    """Mirror of speculative_decoding.py:241-598 (`smart_drafts_mode=False`, the mode every shipped
-    script uses for product prediction and the default retrosynthesis runs).  Same constructor
+    """Mirror of speculative_decoding.py:241-845, both draft modes (`smart_drafts_mode=False`: every candidate tries
+    the n_drafts source windows, :428-598; `True`: windows of a draft library keyed by the candidate's last token,
+    :600-845).  Same constructor
     arguments and counters (`model_calls_num`, `accepted_tokens_num`, `produced_non_pad_tokens`);
     `generate(src)` returns the (B, n_best, width) hypotheses best-first, like the reference."""
 
     def __init__(self, model: B200Transformer, max_len: int, n_best: int, draft_len: int, n_drafts: int,
                  vocab_size: int, smart_drafts_mode: bool, pad_token: int, bos_token: int, eos_token: int,
                  C_token: int, tie_break: str = "torch_cpu", keep_trace: bool = False) -> None:
-        if smart_drafts_mode:
-            raise NotImplementedError("smart_drafts_mode=True (draft library keyed by the last token, "
-                                      "speculative_decoding.py:600-845) is not on the B200 path yet (DESIGN.md §0 row f)")
-        self.smart_drafts_mode = smart_drafts_mode
+        self.smart_drafts_mode = bool(smart_drafts_mode)
         self.model = model
         self.max_len = max_len
         self.vocab_size = vocab_size
@@ -128,7 +126,7 @@ class TranslationInferenceBeamSearchSpeculative:
         width = C.c_int32(0)
         with torch.cuda.device(m.device):
             rc = m.lib.ttb_beam_speculative_generate(
-                m._h, src_d.data_ptr(), B, Ls, self.max_len, K, self.draft_len, N, self.pad_token_idx, self.bos_token_idx,
+                m._h, src_d.data_ptr(), B, Ls, self.max_len, K, self.draft_len, N, int(self.smart_drafts_mode), self.pad_token_idx, self.bos_token_idx,
                 self.eos_token_idx, self.C_token_idx, self.tie_break, out.data_ptr(), C.byref(width),
                 t_nacc.data_ptr() if t_nacc is not None else None, t_pick.data_ptr() if t_pick is not None else None,
                 C.byref(stats), torch.cuda.current_stream(m.device).cuda_stream)

@@ -77,7 +77,11 @@ def workload_name(args):
 
 
 def batch_for(args, rank, step):
-    return synthetic_sources(args.batch_size, args.vocab, seed=100003 * (rank + 1) + step)
+    """Synthetic batch of step `step`.  Weak scaling: per-GPU work is fixed as N grows, so every rank decodes the SAME
+    queries of the step (rotated by its rank); with rank-specific random batches the step time would be the slowest
+    rank's batch, i.e. the maximum of N samples of the batch-to-batch spread (about +-12 % with these sources), which
+    measures the data rather than the system."""
+    return torch.roll(synthetic_sources(args.batch_size, args.vocab, seed=100003 + step), shifts=rank, dims=0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -351,7 +355,8 @@ def main():
                 "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": world * args.batch_size,
-                           "parallelism": f"dp{world} (queries sharded, predictions all-gathered)" if world > 1 else "single GPU",
+                           "parallelism": f"dp{world} (one batch per rank and step: the step's queries rotated by the rank, so "
+                                          f"per-GPU work is identical; predictions all-gathered over NCCL)" if world > 1 else "single GPU",
                            "l2": "256 MiB buffer written between steps (L2 flush)"},
                 "e2e": {"value": e2e_value, "unit": "SMILES/s", "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(host[args.warmup].numel() * 8),
@@ -359,6 +364,26 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_shares": shares,
                 "decoder_calls": calls, "accepted_tokens_per_call": accepted / max(calls, 1),
                 "produced_tokens": produced, "reference_failures": errors[:3]}
+        if world == 1:
+            # BASELINE.json configs[2] beside the headline (same weights): speculative beam search bs=4, n_best=5
+            try:
+                from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+                bgen = TranslationInferenceBeamSearchSpeculative(eng, args.max_len, 5, args.draft_len, args.n_drafts, args.vocab, False,
+                                                                 PAD, BOS, EOS, REPLACE)
+                bsrc = [batch_for(args, 0, i)[:4].to(dev) for i in range(3)]
+                bgen.generate(bsrc[0])
+                torch.cuda.synchronize()
+                c0, t0 = bgen.model_calls_num, time.perf_counter()
+                for b in bsrc[1:]:
+                    bgen.generate(b)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                line["beam_speculative"] = {"workload": "product prediction beam-search speculative bs=4 n_best=5 draft_len=10 n_drafts=23 "
+                                                        "(BASELINE.json configs[2]), same weights and sources, KV-cached",
+                                            "value": 8 / dt, "unit": "SMILES/s", "ms_per_batch": 1000 * dt / 2,
+                                            "decoder_calls_per_batch": (bgen.model_calls_num - c0) / 2}
+            except (RuntimeError, AssertionError) as ex:   # reference-faithful failure modes
+                line["beam_speculative"] = {"error": str(ex)[:120]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle.greedy_speculative import GreedySpeculativeOracle
             from oracle.transformer import OracleTransformer

@@ -1273,6 +1273,426 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 }
 
 // =====================================================================================================
+// Fused feed-forward sub-layer on CTA PAIRS (tcgen05 cta_group::2), same contract as ffn_fused_kernel.
+// One cluster of FOUR CTAs per 256-row block: rank = 2 p + t, t = row tile (128 rows) and position in the MMA pair,
+// p = half of the hidden units.  The pair {2p, 2p+1} runs M = 256 MMAs: each CTA keeps its own 128 rows of X / H as
+// the A operand and stages only HALF of every weight tile (B operand: W1 chunk 64 of 128 hidden rows, W2 chunk 128 of
+// 256 output rows), so the shared-memory and L2 traffic of the weights per row halves against the cta_group::1 kernel
+// (whose main loop is bound by exactly that traffic).  The even CTA of a pair issues every MMA; its mbarriers collect
+// the TMA bytes of both CTAs and the "H written" / "accumulator drained" arrivals of both CTAs' epilogue warps;
+// tcgen05.commit multicasts the "slot free" / "accumulator ready" signals to both.  The partial sums over the two
+// hidden halves are exchanged between ranks r and r ^ 2 (same rows) exactly as in ffn_fused_kernel.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), like CUTLASS's ClusterBarrier::arrive: the data handed over is either
+    // tensor memory (tcgen05.fence::before_thread_sync) or shared memory already fenced into the async proxy; a
+    // cluster-scope release here stalls the arriving thread for ~1000 cycles per arrival
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquires arrivals of the peer CTA
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are counted on an mbarrier of the pair's even CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {   // same barrier offset in every CTA of the mask
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(ffn::THREADS, 1)
+ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmW1h,
+                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ g1,
+                const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F) {
+    using namespace ffn;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint32_t t = rank & 1u, p = rank >> 1;      // row tile / position in the MMA pair, hidden half
+    const uint32_t leader = rank & ~1u;               // even CTA of the pair: issues the MMAs, owns the pair's barriers
+    const uint32_t xpeer = rank ^ 2u;                 // same rows, other hidden half
+    const uint16_t pair_mask = (uint16_t)(3u << leader);
+    const int mblk = (blockIdx.x >> 2) * (2 * BM);
+    const int m0 = mblk + (int)t * BM;
+    const int half = F / 2;                 // hidden units of this pair
+    const int n_chunks = half / 128;
+    const int j_base = (int)p * half;       // first hidden unit of this pair
+    const int n0 = (int)p * 128;            // output columns finalised by this CTA
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    float2* part1 = reinterpret_cast<float2*>(gen + OFF_PART);
+    float2* part2 = part1 + 4 * BM;
+    float* prm = reinterpret_cast<float*>(gen + OFF_PRM);
+    float* b1s = reinterpret_cast<float*>(gen + OFF_B1);
+    const uint32_t bar_base = base + OFF_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                           // used in the even CTA only
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSLOT + s); };
+    const uint32_t x_full = bar_base + 8u * (2 * NSLOT);                                 // even CTA only
+    auto acc1_full = [&](int b) { return bar_base + 8u * (2 * NSLOT + 1 + b); };
+    auto acc1_empty = [&](int b) { return bar_base + 8u * (2 * NSLOT + 3 + b); };       // even CTA only (16 arrivals)
+    const uint32_t h_full = bar_base + 8u * (2 * NSLOT + 5);                             // even CTA only (16 arrivals)
+    const uint32_t h_empty = bar_base + 8u * (2 * NSLOT + 6);
+    const uint32_t acc2_full = bar_base + 8u * (2 * NSLOT + 7);
+    const uint32_t resid_bar = bar_base + 8u * (2 * NSLOT + 8);
+    const uint32_t recv_bar = bar_base + 8u * (2 * NSLOT + 9);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 10));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef TTB_FFN_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][253][0] = 5; g_ffn_ts[2][253][1] = clock64(); }
+#endif
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            mbar_init(x_full, 1);
+            for (int b = 0; b < 2; ++b) { mbar_init(acc1_full(b), 1); mbar_init(acc1_empty(b), 16); }
+            mbar_init(h_full, 16);
+            mbar_init(h_empty, 1);
+            mbar_init(acc2_full, 1);
+            mbar_init(resid_bar, 1);
+            mbar_init(recv_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {   // parameter slices (weights only: independent of earlier kernels)
+        const int tt = threadIdx.x - 64;
+        if (tt < 128) {
+            prm[tt] = bias2 ? __ldg(bias2 + n0 + tt) : 0.f;
+            prm[128 + tt] = __ldg(g1 + n0 + tt);
+            prm[256 + tt] = __ldg(b1 + n0 + tt);
+            prm[384 + tt] = g2 ? __ldg(g2 + n0 + tt) : 1.f;
+            prm[512 + tt] = g2 ? __ldg(b2 + n0 + tt) : 0.f;
+        }
+        for (int i = tt; i < half; i += 256) b1s[i] = bias1 ? __ldg(bias1 + j_base + i) : 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_acc2 = tmem_base, tm_acc1 = tmem_base + 256u;
+    // every CTA of the cluster has initialised its barriers and owns its tensor memory before any remote signal
+    cluster_sync_all();                                                      // cluster barrier phase 0
+#ifdef TTB_FFN_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][254][0] = 6; g_ffn_ts[2][254][1] = clock64(); }
+#endif
+    pdl_launch_dependents();
+    pdl_wait();
+#ifdef TTB_FFN_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
+#endif
+    const bool live = mblk < rows.live();   // uniform per cluster: dead blocks only take part in the cluster barriers
+
+    if (warp == 0) {
+        if (lane == 0 && live) {  // ===== TMA producer (both CTAs of a pair: own X rows, own half of every weight tile) =====
+            [[maybe_unused]] int tsn = 0;
+            FFN_TS(0, tsn, 1);
+            const uint32_t x_full_l = mapa_u32(x_full, leader);
+            if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, &tmXh, kb * BK, m0, x_full_l);
+            int it = 0;
+            auto take_slot = [&]() -> int {
+                const int s = it % NSLOT;
+                const uint32_t ph = (it / NSLOT) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                FFN_TS(0, tsn, 100 + it);
+                if (t == 0) mbar_expect_tx(full_bar(s), 2 * SLOT);
+                ++it;
+                return s;
+            };
+            auto load_w1 = [&](int c) {    // this CTA's 64 of the chunk's 128 hidden rows: four K-blocks [64 x 64]
+                const int s = take_slot();
+                const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
+                const int j0 = j_base + c * 128 + (int)t * 64;
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 8192, &tmW1h, kb * BK, j0, fl);
+            };
+            auto load_w2 = [&](int c) {    // this CTA's 128 of the 256 output rows: two K-blocks [128 x 64] of the chunk
+                const int s = take_slot();
+                const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
+                const int j0 = j_base + c * 128;
+                for (int kk = 0; kk < 2; ++kk) tma_load_2d_pair(dst + kk * 16384, &tmW2, j0 + kk * BK, (int)t * 128, fl);
+            };
+            load_w1(0);
+            for (int c = 0; c < n_chunks; ++c) {
+                if (c + 1 < n_chunks) load_w1(c + 1);
+                load_w2(c);
+            }
+            // residual tile into the (now idle) X region once every MMA has completed
+            mbar_wait(acc2_full, 0);
+            mbar_expect_tx(resid_bar, 65536);
+            for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && live && t == 0) {  // ===== MMA issuer: even CTA of the pair =====
+            constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, 128);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 256);
+            int it = 0;
+            [[maybe_unused]] int tsn = 0;
+            FFN_TS(1, tsn, 1);
+            mbar_wait(x_full, 0);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 2);
+            auto gemm1 = [&](int c) {
+                const int b = c & 1;
+                mbar_wait_cluster(acc1_empty(b), ((c >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                FFN_TS(1, tsn, 1000 + c);
+                const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
+                const int s = it % NSLOT;
+                mbar_wait(full_bar(s), (it / NSLOT) & 1);
+                tcgen05_fence_after();
+                FFN_TS(1, tsn, 2000 + it);
+                const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
+                        const uint64_t bdesc = umma_desc_sw128(slot + kb * 8192 + k * UMMA_K * 2);
+                        umma_bf16_pair(d, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit_pair(empty_bar(s), pair_mask);
+                umma_commit_pair(acc1_full(b), pair_mask);
+                ++it;
+            };
+            auto gemm2 = [&](int c) {
+                mbar_wait_cluster(h_full, c & 1);
+                tcgen05_fence_after();
+                FFN_TS(1, tsn, 3000 + c);
+                const int s = it % NSLOT;
+                mbar_wait(full_bar(s), (it / NSLOT) & 1);
+                tcgen05_fence_after();
+                FFN_TS(1, tsn, 2000 + it);
+                const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(base + OFF_H + kk * 16384 + k * UMMA_K * 2);
+                        const uint64_t bdesc = umma_desc_sw128(slot + kk * 16384 + k * UMMA_K * 2);
+                        umma_bf16_pair(tm_acc2, adesc, bdesc, idesc2, (c | kk | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit_pair(empty_bar(s), pair_mask);
+                umma_commit_pair(h_empty, pair_mask);
+                ++it;
+            };
+            gemm1(0);
+            for (int c = 0; c < n_chunks; ++c) {
+                if (c + 1 < n_chunks) gemm1(c + 1);
+                gemm2(c);
+            }
+            umma_commit_pair(acc2_full, pair_mask);
+            FFN_TS(1, tsn, 9);
+        }
+    }
+
+    // ===== epilogue warps 2..9: thread = (row, 64-column half hh) =====
+    [[maybe_unused]] int tse = 0;
+    [[maybe_unused]] const bool ts_on = threadIdx.x == 64;
+    const bool epi = warp >= 2 && live;
+    const int q = warp & 3;
+    const int hh = warp >= 2 ? ((warp - 2) >> 2) : 0;
+    const int row = q * 32 + lane;
+    const int swz = row & 7;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (epi) {
+        const uint32_t acc1_empty_l0 = mapa_u32(acc1_empty(0), leader), acc1_empty_l1 = mapa_u32(acc1_empty(1), leader);
+        const uint32_t h_full_l = mapa_u32(h_full, leader);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b = c & 1;
+            if (ts_on) FFN_TS(2, tse, 100 + c);
+            mbar_wait(acc1_full(b), (c >> 1) & 1);
+            tcgen05_fence_after();
+            if (ts_on) FFN_TS(2, tse, 200 + c);
+            uint32_t pk[32];   // 64 bf16 values
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 * b + hh * 64 + c0), r);
+                const float4* bb = reinterpret_cast<const float4*>(b1s + c * 128 + hh * 64 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = bb[j >> 2];
+                    const float v0 = fmaxf(__uint_as_float(r[j]) + bv.x, 0.f);
+                    const float v1 = fmaxf(__uint_as_float(r[j + 1]) + bv.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(r[j + 2]) + bv.z, 0.f);
+                    const float v3 = fmaxf(__uint_as_float(r[j + 3]) + bv.w, 0.f);
+                    __nv_bfloat162 p01 = __floats2bfloat162_rn(v0, v1), p23 = __floats2bfloat162_rn(v2, v3);
+                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p01);
+                    pk[((c0 + j) >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p23);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(b ? acc1_empty_l1 : acc1_empty_l0);   // accumulator buffer may be overwritten
+            if (ts_on) FFN_TS(2, tse, 300 + c);
+            mbar_wait(h_empty, (c & 1) ^ 1);                  // GEMM2 of the previous chunk has read H (of both CTAs)
+            if (ts_on) FFN_TS(2, tse, 400 + c);
+            uint8_t* hrow = gen + OFF_H + hh * 16384 + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(hrow + ((ch ^ swz) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(h_full_l);
+            if (ts_on) FFN_TS(2, tse, 500 + c);
+        }
+        mbar_wait(acc2_full, 0);
+        tcgen05_fence_after();
+        if (ts_on) FFN_TS(2, tse, 600);
+    }
+    // ---- reduction of the two partial sums (ranks r and r ^ 2), see ffn_fused_kernel ------------------------
+    uint8_t* recv = gen + OFF_H;             // [128 rows][32 chunks of 16 B], chunk index XOR (row & 31)
+    uint8_t* send = gen + OFF_RING + SLOT;   // same layout
+    if (threadIdx.x == 64 && live) mbar_expect_tx(recv_bar, 65536);
+    __syncwarp();
+    // barrier A ("my main loop is over: my H / ring may be written"), split into arrive / wait around the staging
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (epi) {
+        const int pcol = (int)(p ^ 1u) * 128 + hh * 64;   // the partner's output columns handled by this thread
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_acc2 + lane_base + (uint32_t)(pcol + c0), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int chunk = hh * 16 + (c0 >> 2) + i;
+                *reinterpret_cast<uint4*>(send + row * 512 + ((chunk ^ (row & 31)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    __syncwarp();
+    if (ts_on) FFN_TS(2, tse, 700);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // barrier A (wait): the partner's buffers are free
+    if (ts_on) FFN_TS(2, tse, 701);
+    if (threadIdx.x == 64 && live) {
+        const uint32_t r_recv = mapa_u32(base + OFF_H, xpeer), r_bar = mapa_u32(recv_bar, xpeer);
+        for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(r_recv + i * 16384),
+                         "r"(base + OFF_RING + SLOT + i * 16384), "r"(16384), "r"(r_bar)
+                         : "memory");
+    }
+    float v[64];
+    const int pidx = (int)p * 2 + hh;
+    if (epi) {
+        mbar_wait(resid_bar, 0);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_acc2 + lane_base + (uint32_t)(n0 + hh * 64 + c0), r);
+            const uint8_t* box = gen + (2 * hh + c0 / 32) * 16384 + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
+                const int j = c0 + 4 * c;
+                const float4 bv = *reinterpret_cast<const float4*>(prm + hh * 64 + j);
+                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
+                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
+                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
+                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+            }
+        }
+        mbar_wait_cluster(recv_bar, 0);   // the partner's partial sum has landed (its flight overlapped the loads above)
+        if (ts_on) FFN_TS(2, tse, 702);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int chunk = hh * 16 + c;
+            const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
+            v[4 * c + 0] += pv.x;
+            v[4 * c + 1] += pv.y;
+            v[4 * c + 2] += pv.z;
+            v[4 * c + 3] += pv.w;
+        }
+        float mean, m2;
+        ln_local_stats(v, mean, m2);
+        part1[pidx * BM + row] = make_float2(mean, m2);
+        st_peer_f32x2(smem_u32(&part1[pidx * BM + row]), xpeer, mean, m2);
+    }
+    __syncwarp();
+    if (ts_on) FFN_TS(2, tse, 800);
+    cluster_sync_all();                                                         // barrier C
+    if (ts_on) FFN_TS(2, tse, 801);
+    if (epi) ln_normalise(v, part1, row, prm + 128 + hh * 64, prm + 256 + hh * 64);
+    if (ts_on) FFN_TS(2, tse, 810);
+    if (g2) {
+        if (epi) {
+            float mean, m2;
+            ln_local_stats(v, mean, m2);
+            part2[pidx * BM + row] = make_float2(mean, m2);
+            st_peer_f32x2(smem_u32(&part2[pidx * BM + row]), xpeer, mean, m2);
+        }
+        __syncwarp();
+        cluster_sync_all();
+        if (epi) ln_normalise(v, part2, row, prm + 384 + hh * 64, prm + 512 + hh * 64);
+    }
+    if (epi) {
+        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (the send buffer:
+        // the partner has consumed it before it arrived at barrier C)
+        if (ts_on) FFN_TS(2, tse, 811);
+        ln_store_tiles(v, gen + 2 * hh * 16384, gen + OFF_RING + SLOT + hh * 16384, row);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ts_on) FFN_TS(2, tse, 850);
+        if (threadIdx.x == 64) {
+            for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + bx * 16384, n0 + 32 * bx, m0);
+            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + OFF_RING + SLOT + hb * 16384, n0 + 64 * hb, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (ts_on) FFN_TS(2, tse, 900);
+        }
+    }
+    // the tensor memory of a pair is released together: both CTAs are past their last tcgen05.ld
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// =====================================================================================================
 // Vocabulary projection + arg-max for the greedy loop:  pred[row] = argmax_v (xh[row] . Wc[v] + bc[v])
 // (first maximal index, like torch.argmax).  The logits never leave the SM: one CTA per 128 rows keeps
 // the whole [V x K] classifier weight and its A tile in shared memory (K = 256: 64 KB + 144 KB for V = 288),
@@ -1498,7 +1918,6 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
         attr_set = true;
     }
     const int tiles = (rows.max_rows + BM - 1) / BM;
-    static const int ffn_dbg = [] { const char* v = getenv("TTB_FFN_DBG"); return v ? atoi(v) : 0; }();
 #ifdef TTB_FFN_TIMELINE
     {
         static int n_launch = 0;
@@ -1516,6 +1935,31 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
         }
     }
 #endif
+    // CTA-pair kernel (cta_group::2, clusters of four) whenever all of its clusters are co-resident; TTB_FFN_PAIR=0/1 forces
+    static const int pair_env = [] { const char* v = getenv("TTB_FFN_PAIR"); return v ? atoi(v) : -1; }();
+    if (pair_env != 0) {
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            cudaError_t e = cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn::SMEM);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(4 * kNumSMs);
+            cfg.blockDim = dim3(ffn::THREADS);
+            cfg.dynamicSmemBytes = ffn::SMEM;
+            int n = 0;
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, ffn_pair_kernel, &cfg);
+            max_clusters = e == cudaSuccess ? n : 0;
+            (void)cudaGetLastError();
+            if (getenv("TTB_DEBUG")) fprintf(stderr, "[ttb] ffn_pair_kernel: %d co-resident clusters of 4 (%s)\n", max_clusters, cudaGetErrorString(e));
+        }
+        const int blocks = (rows.max_rows + 2 * BM - 1) / (2 * BM);
+        if (pair_env == 1 || blocks <= max_clusters) {
+            CUtensorMap tmW1h;
+            if (int rc = get_tensor_map(W1, F, 256, 256, 64, &tmW1h)) return rc;
+            launch_pdl(ffn_pair_kernel, dim3(4 * blocks), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1h, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F);
+            return 0;
+        }
+    }
+    static const int ffn_dbg = [] { const char* v = getenv("TTB_FFN_DBG"); return v ? atoi(v) : 0; }();
     launch_pdl(ffn_fused_kernel, dim3(2 * tiles), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F, ffn_dbg);
     return 0;
 }

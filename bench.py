@@ -139,7 +139,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=True):
+def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=True, chained_ffn=False):
     """Algorithmic (flops, bytes) of ALL launches of a kernel class over the iterations in `hist`
     (live queries per iteration); per-unit figures are in DESIGN.md §4.  With the fused kernels the
     sub-layer tails (bias + residual + LayerNorm, fp32 and bf16 copies of the residual stream) are part
@@ -152,7 +152,11 @@ def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=Tr
     ln_flops = 8.0 * rows * E
     stream_bytes = rows * E * (4 + 4 + ab)          # residual in, residual out (fp32), low-precision copy out
     if name == "gemm_ffn1" and fused_ffn:
-        return (4.0 * rows * E * F + ln_flops) * L, (rows * E * ab + stream_bytes) * L + 2 * E * F * ab * L * n_it
+        f, b = (4.0 * rows * E * F + ln_flops) * L, (rows * E * ab + stream_bytes) * L + 2 * E * F * ab * L * n_it
+        if chained_ffn:   # the launch also computes the cross-attention out-projection + LayerNorm (att in, x in/out fp32)
+            f += (2.0 * rows * E * E + ln_flops) * L
+            b += (rows * E * ab + rows * E * 8) * L + E * E * ab * L * n_it
+        return f, b
     if name in ("gemm_self_out", "gemm_cross_out") and fused_ln:
         return (2.0 * rows * E * E + ln_flops) * L, (rows * E * ab + stream_bytes) * L + E * E * ab * L * n_it
     if name == "gemm_ffn2" and fused_ln:
@@ -328,8 +332,9 @@ def main():
         flops = byts = 0.0
         fused_ln = "add_layernorm" not in shares
         fused_ffn = "gemm_ffn2" not in shares
+        chained_ffn = fused_ffn and "gemm_cross_out" not in shares
         for h in hists:
-            f, b = class_work(dominant, args, cfg, h, src_lens_mean, fused_ln, fused_ffn)
+            f, b = class_work(dominant, args, cfg, h, src_lens_mean, fused_ln, fused_ffn, chained_ffn)
             flops += f
             byts += b
         intensity = flops / max(byts, 1.0)
@@ -339,7 +344,8 @@ def main():
             roof = {"bound": "tensor", "achieved": flops / dom_s / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
         else:
             roof = {"bound": "hbm", "achieved": byts / dom_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-        label = {"gemm_ffn1": "ffn_fused_kernel (FFN1+ReLU+FFN2+residual+LayerNorm)" if fused_ffn else "gemm_ffn1",
+        label = {"gemm_ffn1": ("ffn_pair_kernel (cross out-proj+LayerNorm2 + FFN1+ReLU+FFN2+residual+LayerNorm3, cta_group::2)" if chained_ffn else
+                               "ffn_fused_kernel (FFN1+ReLU+FFN2+residual+LayerNorm)") if fused_ffn else "gemm_ffn1",
                  "gemm_self_out": "gemm_resid_ln_kernel (self out-proj)" if fused_ln else "gemm_self_out",
                  "gemm_cross_out": "gemm_resid_ln_kernel (cross out-proj)" if fused_ln else "gemm_cross_out"}.get(dominant, dominant)
         overhead_us = 1000.0 * shares["misc"]["ms"] / shares["misc"]["launches"] if "misc" in shares else None

@@ -1,0 +1,61 @@
+"""In-situ kernel timeline of the decoding loop (CUPTI through torch.profiler): per kernel name the average duration and
+the average gap to the end of the preceding kernel, plus the raw events of a few iterations in the middle of a batch."""
+import json
+import sys
+from collections import defaultdict
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+import bench  # noqa: E402
+
+
+def main():
+    sys.argv = [sys.argv[0]] + sys.argv[1:]
+    args = bench.parse()
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    from translation_transformer_b200.model import B200Transformer
+    cfg, sd = bench.build_weights(args)
+    eng = B200Transformer(cfg, sd, precision=args.precision, device=0)
+    gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, bench.PAD, bench.BOS, bench.EOS, bench.REPLACE)
+    dev = torch.device("cuda", 0)
+    for i in range(3):
+        gen.generate(bench.batch_for(args, 0, i).to(dev))
+    torch.cuda.synchronize()
+    src = bench.batch_for(args, 0, 3).to(dev)
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        gen.generate(src)
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in ev), key=lambda t: t[0])
+    print("events", len(ev))
+    if not ev:
+        return
+    t0 = ev[0][0]
+    agg = defaultdict(lambda: [0, 0.0, 0.0])
+    prev_end = None
+    for s, e, n in ev:
+        short = n.split("(")[0][-60:]
+        a = agg[short]
+        a[0] += 1
+        a[1] += e - s
+        if prev_end is not None:
+            a[2] += s - prev_end
+        prev_end = max(prev_end or e, e)
+    total = ev[-1][1] - t0
+    print(f"span {total / 1000:.2f} ms")
+    print(f"{'kernel':62s} {'n':>6s} {'avg us':>8s} {'gap us':>8s} {'sum ms':>8s}")
+    for k, (n, d, g) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:62s} {n:6d} {d / n:8.2f} {g / n:8.2f} {d / 1000:8.2f}")
+    mid = len(ev) // 2
+    out = Path("gpurun_out") / "timeline_events.txt"
+    with open(out, "w") as f:
+        for s, e, n in ev[mid:mid + 80]:
+            f.write(f"{s - t0:10.1f} {e - t0:10.1f} {e - s:7.2f} {n.split('(')[0][-50:]}\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -329,6 +329,24 @@ static int ffn_block(ttb_engine* e, int kc1, int kc2, const Lin& L1, const Lin& 
     return linear_resid_ln(e, kc2, hid, L1.N, L2, n1, n2, x, xh, y, dst, dsth, rows, s);
 }
 
+// Out-projection + LayerNorm of the preceding sub-layer chained into the fused feed-forward launch (bf16, E = 256, CTA-pair
+// kernel available).  Returns 0 when taken, -1 when not applicable (caller launches the two kernels), > 0 on error.
+static int ffn_block_chained(ttb_engine*, int, const float*, const Lin&, const Norm&, const Lin&, const Lin&, const Norm&, const Norm*, float*, float*,
+                             RowCount, cudaStream_t) {
+    return -1;
+}
+static int ffn_block_chained(ttb_engine* e, int kc, const __nv_bfloat16* att, const Lin& Lo, const Norm& n0, const Lin& L1, const Lin& L2,
+                             const Norm& n1, const Norm* n2, float* x, __nv_bfloat16* xh, RowCount rows, cudaStream_t s) {
+    if (!(Lo.N == 256 && Lo.K == 256 && L2.N == 256 && L1.K == 256 && L1.N % 256 == 0 && L1.N <= 4096 && fused_ffn_enabled() && fused_ln_enabled() &&
+          chain_enabled() && ffn_pair_available(rows.max_rows)))
+        return -1;
+    static const bool off = [] { const char* v = getenv("TTB_NO_FFN_CHAIN"); return v && v[0] == '1'; }();
+    if (off) return -1;
+    Scope sc(e, kc, s);
+    return launch_ffn_fused(xh, L1.wh, L1.b, L2.wh, L2.b, x, n1.g, n1.b, n2 ? n2->g : nullptr, n2 ? n2->b : nullptr, rows, L1.N, s, att, Lo.wh, Lo.b,
+                            n0.g, n0.b) ? 1 : 0;
+}
+
 // Attention dispatch: fp32 path -> SIMT kernels (exact), bf16 path -> tensor-core kernels
 // (TTB_ATTN_SIMT=1 forces the SIMT kernels for A/B comparisons).
 static bool attn_simt_forced() {
@@ -457,6 +475,11 @@ static int decoder_stack(ttb_engine* e, RowCount rows, int qkv_layers, long long
         if (linear_resid_ln(e, KC_GEMM_SELF_OUT, att, E, L.self_out, L.n1, nullptr, x, xh, y, x, xh, rows, s, &cross_q, q2, &chained)) return 1;
         if (!chained && linear<ActT>(e, KC_GEMM_CROSS_Q, a_view<ActT>(x, xh), E, cross_q, q2, E, rows, false, s)) return 1;
         { Scope sc(e, KC_CROSS_ATTN, s); cross_attn(l, q2, att); }
+        // cross-attention out-projection + LayerNorm2 + feed-forward block + LayerNorm3 in one launch where the CTA-pair
+        // feed-forward kernel runs, two launches otherwise
+        int fused = ffn_block_chained(e, KC_GEMM_FFN1, att, L.cross_out, L.n2, L.ff1, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, rows, s);
+        if (fused > 0) return 1;
+        if (fused == 0) continue;
         if (linear_resid_ln(e, KC_GEMM_CROSS_OUT, att, E, L.cross_out, L.n2, nullptr, x, xh, y, x, xh, rows, s)) return 1;
         if (ffn_block(e, KC_GEMM_FFN1, KC_GEMM_FFN2, L.ff1, L.ff2, L.n3, last ? &e->dec_norm : nullptr, x, xh, hid, y, x, xh, rows, s)) return 1;
     }
@@ -633,14 +656,20 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     // decoding live in device memory), so it is captured once into a CUDA graph and replayed.
     static const bool no_graph = [] { const char* v = getenv("TTB_NO_GRAPH"); return v && v[0] == '1'; }();
     const bool use_graph = !no_graph && !trace_dev && e->prof.mask == 0;
+    // Several iterations per graph: back-to-back graph launches of one stream leave the GPU idle for ~12 us (launch latency
+    // plus the control-word copy in between), a graph edge costs ~2 us.  Iterations behind the end of the loop are no-ops
+    // (every kernel reads a live count of zero), so a longer graph only adds a few of those per batch.
+    static const int graph_iters = [] { const char* v = getenv("TTB_GRAPH_ITERS"); const int k = v ? atoi(v) : 4; return k < 1 ? 1 : (k > 16 ? 16 : k); }();
+    const int K_it = use_graph ? graph_iters : 1;
     if (use_graph) {
-        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT), replace};
+        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT) + 16 * K_it, replace};
         if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
             const long long l0 = e->launches;
             cudaGraph_t graph = nullptr;
             TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-            const int rc = enqueue_iteration();
+            int rc = 0;
+            for (int k = 0; k < K_it && !rc; ++k) rc = enqueue_iteration();
             cudaError_t ce = cudaStreamEndCapture(s, &graph);
             if (rc || ce != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
@@ -657,10 +686,11 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
 
     // Lagged polling: the host looks at the control words of iteration (it - LAG) while iterations up
     // to `it` are already queued, so the GPU never waits for the host.
-    constexpr int LAG = 2, RING = 4;
+    constexpr int RING = 4;
+    const int LAG = K_it > 1 ? 1 : 2;   // launches (of K_it iterations each) the host stays ahead of the control words it reads
     int it = 0;
     bool done = false;
-    while (!done && it < max_iters) {
+    while (!done && it * K_it < max_iters) {
         if (use_graph) {
             TTB_CUDA_OK(cudaGraphLaunch(e->graph_exec, s));
             e->launches += e->graph_launches;

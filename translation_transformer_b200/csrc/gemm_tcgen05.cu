@@ -894,8 +894,8 @@ constexpr int X_BYTES = 65536, H_BYTES = 32768;
 constexpr int THREADS = 320;
 constexpr int OFF_H = X_BYTES, OFF_RING = X_BYTES + H_BYTES, OFF_PART = OFF_RING + NSLOT * SLOT;
 constexpr int PART_BYTES = 4 * BM * 8;
-constexpr int OFF_PRM = OFF_PART + 2 * PART_BYTES;           // b2, g1, b1, g2, b2' slices: 5 * 128 floats
-constexpr int OFF_B1 = OFF_PRM + 5 * 128 * 4;                // this CTA's half of linear1.bias (<= 2048 floats)
+constexpr int OFF_PRM = OFF_PART + 3 * PART_BYTES;           // three statistics tables (the third: chained pre-phase)
+constexpr int OFF_B1 = OFF_PRM + 8 * 128 * 4;                // b2, g1, b1, g2, b2', pre-phase bias, g, b slices: 8 * 128 floats
 constexpr int MAX_HALF = 2048;
 constexpr int OFF_BAR = OFF_B1 + MAX_HALF * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
@@ -1330,7 +1330,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(ffn::THREADS, 1)
 ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmW1h,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                 const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ g1,
-                const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F) {
+                const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, RowCount rows, int F,
+                const __grid_constant__ CUtensorMap tmAtt, const __grid_constant__ CUtensorMap tmWoh,
+                const float* __restrict__ bias_o, const float* __restrict__ g0, const float* __restrict__ b0, int chain) {
     using namespace ffn;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -1351,6 +1353,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     uint8_t* gen = smem_raw + (base - raw);
     float2* part1 = reinterpret_cast<float2*>(gen + OFF_PART);
     float2* part2 = part1 + 4 * BM;
+    float2* part0 = part2 + 4 * BM;         // statistics of the chained pre-phase
     float* prm = reinterpret_cast<float*>(gen + OFF_PRM);
     float* b1s = reinterpret_cast<float*>(gen + OFF_B1);
     const uint32_t bar_base = base + OFF_BAR;
@@ -1364,7 +1367,13 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     const uint32_t acc2_full = bar_base + 8u * (2 * NSLOT + 7);
     const uint32_t resid_bar = bar_base + 8u * (2 * NSLOT + 8);
     const uint32_t recv_bar = bar_base + 8u * (2 * NSLOT + 9);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 10));
+    // chained pre-phase (x <- LN0(x + att Wo^T + bo) computed by this kernel, see below)
+    const uint32_t pre_full = bar_base + 8u * (2 * NSLOT + 10);     // even CTA only: Wo halves of both CTAs have landed
+    const uint32_t pre_acc = bar_base + 8u * (2 * NSLOT + 11);      // its accumulator is complete
+    const uint32_t pre_done = bar_base + 8u * (2 * NSLOT + 12);     // ring slots 1-2 (residual tile) are free again
+    const uint32_t x2_recv = bar_base + 8u * (2 * NSLOT + 13);      // the partner's half of the normalised tile has landed
+    const uint32_t x2_full = bar_base + 8u * (2 * NSLOT + 14);      // even CTA only: both CTAs hold the complete tile
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef TTB_FFN_TIMELINE
@@ -1376,6 +1385,10 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1h)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        if (chain) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAtt)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWoh)) : "memory");
+        }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -1387,6 +1400,11 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             mbar_init(acc2_full, 1);
             mbar_init(resid_bar, 1);
             mbar_init(recv_bar, 1);
+            mbar_init(pre_full, 1);
+            mbar_init(pre_acc, 1);
+            mbar_init(pre_done, 1);
+            mbar_init(x2_recv, 1);
+            mbar_init(x2_full, 2);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -1401,6 +1419,11 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             prm[256 + tt] = __ldg(b1 + n0 + tt);
             prm[384 + tt] = g2 ? __ldg(g2 + n0 + tt) : 1.f;
             prm[512 + tt] = g2 ? __ldg(b2 + n0 + tt) : 0.f;
+            if (chain) {
+                prm[640 + tt] = bias_o ? __ldg(bias_o + n0 + tt) : 0.f;
+                prm[768 + tt] = __ldg(g0 + n0 + tt);
+                prm[896 + tt] = __ldg(b0 + n0 + tt);
+            }
         }
         for (int i = tt; i < half; i += 256) b1s[i] = bias1 ? __ldg(bias1 + j_base + i) : 0.f;
     }
@@ -1421,110 +1444,74 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 #endif
     const bool live = mblk < rows.live();   // uniform per cluster: dead blocks only take part in the cluster barriers
 
-    if (warp == 0) {
-        if (lane == 0 && live) {  // ===== TMA producer (both CTAs of a pair: own X rows, own half of every weight tile) =====
-            [[maybe_unused]] int tsn = 0;
-            FFN_TS(0, tsn, 1);
-            const uint32_t x_full_l = mapa_u32(x_full, leader);
-            if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
-            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, &tmXh, kb * BK, m0, x_full_l);
-            int it = 0;
-            auto take_slot = [&]() -> int {
-                const int s = it % NSLOT;
-                const uint32_t ph = (it / NSLOT) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                FFN_TS(0, tsn, 100 + it);
-                if (t == 0) mbar_expect_tx(full_bar(s), 2 * SLOT);
-                ++it;
-                return s;
-            };
-            auto load_w1 = [&](int c) {    // this CTA's 64 of the chunk's 128 hidden rows: four K-blocks [64 x 64]
-                const int s = take_slot();
-                const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
-                const int j0 = j_base + c * 128 + (int)t * 64;
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 8192, &tmW1h, kb * BK, j0, fl);
-            };
-            auto load_w2 = [&](int c) {    // this CTA's 128 of the 256 output rows: two K-blocks [128 x 64] of the chunk
-                const int s = take_slot();
-                const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
-                const int j0 = j_base + c * 128;
-                for (int kk = 0; kk < 2; ++kk) tma_load_2d_pair(dst + kk * 16384, &tmW2, j0 + kk * BK, (int)t * 128, fl);
-            };
-            load_w1(0);
-            for (int c = 0; c < n_chunks; ++c) {
-                if (c + 1 < n_chunks) load_w1(c + 1);
-                load_w2(c);
-            }
-            // residual tile into the (now idle) X region once every MMA has completed
-            mbar_wait(acc2_full, 0);
+    // ---- roles, phase 1 (chained launches only): operands and GEMM of the pre-phase.  The producer / issuer threads come
+    // back to the cluster barrier of the pre-phase before they start the feed-forward main loop.
+    int prod_it = 0;
+    [[maybe_unused]] int tsn = 0;
+    const bool producer = warp == 0 && lane == 0 && live;
+    const bool issuer = warp == 1 && lane == 0 && live && t == 0;
+    auto take_slot = [&]() -> int {
+        const int s = prod_it % NSLOT;
+        const uint32_t ph = (prod_it / NSLOT) & 1;
+        if (chain && prod_it == 1) mbar_wait(pre_done, 0);   // slots 1-2: the pre-phase has stored its fp32 tile
+        mbar_wait(empty_bar(s), ph ^ 1);
+        FFN_TS(0, tsn, 100 + prod_it);
+        if (t == 0) mbar_expect_tx(full_bar(s), 2 * SLOT);
+        ++prod_it;
+        return s;
+    };
+    auto load_w1 = [&](int c) {    // this CTA's 64 of the chunk's 128 hidden rows: four K-blocks [64 x 64]
+        const int s = take_slot();
+        const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
+        const int j0 = j_base + c * 128 + (int)t * 64;
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 8192, &tmW1h, kb * BK, j0, fl);
+    };
+    auto load_w2 = [&](int c) {    // this CTA's 128 of the 256 output rows: two K-blocks [128 x 64] of the chunk
+        const int s = take_slot();
+        const uint32_t dst = base + OFF_RING + s * SLOT, fl = mapa_u32(full_bar(s), leader);
+        const int j0 = j_base + c * 128;
+        for (int kk = 0; kk < 2; ++kk) tma_load_2d_pair(dst + kk * 16384, &tmW2, j0 + kk * BK, (int)t * 128, fl);
+    };
+    constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, 128);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 256);
+    if (producer) {   // ===== TMA producer (both CTAs of a pair: own rows of the A operand, own half of every weight tile) =====
+        FFN_TS(0, tsn, 1);
+        const uint32_t x_full_l = mapa_u32(x_full, leader);
+        if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
+        const CUtensorMap* mapA = chain ? &tmAtt : &tmXh;
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, mapA, kb * BK, m0, x_full_l);
+        if (chain) {
+            // pre-phase operands: this CTA's 64 of the pair's 128 rows of Wo into the (still idle) H region, the fp32
+            // residual tile of its 128 output columns into ring slots 1-2
+            const uint32_t pf_l = mapa_u32(pre_full, leader);
+            if (t == 0) mbar_expect_tx(pre_full, 2 * 32768);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + OFF_H + kb * 8192, &tmWoh, kb * BK, n0 + (int)t * 64, pf_l);
             mbar_expect_tx(resid_bar, 65536);
-            for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
+            for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + OFF_RING + SLOT + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
         }
-    } else if (warp == 1) {
-        if (lane == 0 && live && t == 0) {  // ===== MMA issuer: even CTA of the pair =====
-            constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, 128);
-            constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 256);
-            int it = 0;
-            [[maybe_unused]] int tsn = 0;
-            FFN_TS(1, tsn, 1);
-            mbar_wait(x_full, 0);
+        load_w1(0);   // ring slot 0 is free from the start
+    }
+    if (issuer) {     // ===== MMA issuer: even CTA of the pair =====
+        FFN_TS(1, tsn, 1);
+        mbar_wait(x_full, 0);
+        tcgen05_fence_after();
+        FFN_TS(1, tsn, 2);
+        if (chain) {   // pre-phase GEMM: att (X region) . Wo[128 p .. 128 p + 128)^T -> accumulator buffer 1
+            mbar_wait(pre_full, 0);
             tcgen05_fence_after();
-            FFN_TS(1, tsn, 2);
-            auto gemm1 = [&](int c) {
-                const int b = c & 1;
-                mbar_wait_cluster(acc1_empty(b), ((c >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                FFN_TS(1, tsn, 1000 + c);
-                const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
-                const int s = it % NSLOT;
-                mbar_wait(full_bar(s), (it / NSLOT) & 1);
-                tcgen05_fence_after();
-                FFN_TS(1, tsn, 2000 + it);
-                const uint32_t slot = base + OFF_RING + s * SLOT;
 #pragma unroll
-                for (int kb = 0; kb < 4; ++kb) {
+            for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
-                        const uint64_t bdesc = umma_desc_sw128(slot + kb * 8192 + k * UMMA_K * 2);
-                        umma_bf16_pair(d, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
-                    }
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(base + OFF_H + kb * 8192 + k * UMMA_K * 2);
+                    umma_bf16_pair(tm_acc1 + 128u, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
                 }
-                umma_commit_pair(empty_bar(s), pair_mask);
-                umma_commit_pair(acc1_full(b), pair_mask);
-                ++it;
-            };
-            auto gemm2 = [&](int c) {
-                mbar_wait_cluster(h_full, c & 1);
-                tcgen05_fence_after();
-                FFN_TS(1, tsn, 3000 + c);
-                const int s = it % NSLOT;
-                mbar_wait(full_bar(s), (it / NSLOT) & 1);
-                tcgen05_fence_after();
-                FFN_TS(1, tsn, 2000 + it);
-                const uint32_t slot = base + OFF_RING + s * SLOT;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adesc = umma_desc_sw128(base + OFF_H + kk * 16384 + k * UMMA_K * 2);
-                        const uint64_t bdesc = umma_desc_sw128(slot + kk * 16384 + k * UMMA_K * 2);
-                        umma_bf16_pair(tm_acc2, adesc, bdesc, idesc2, (c | kk | k) != 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit_pair(empty_bar(s), pair_mask);
-                umma_commit_pair(h_empty, pair_mask);
-                ++it;
-            };
-            gemm1(0);
-            for (int c = 0; c < n_chunks; ++c) {
-                if (c + 1 < n_chunks) gemm1(c + 1);
-                gemm2(c);
             }
-            umma_commit_pair(acc2_full, pair_mask);
-            FFN_TS(1, tsn, 9);
+            umma_commit_pair(pre_acc, pair_mask);
         }
     }
+    __syncwarp();
 
     // ===== epilogue warps 2..9: thread = (row, 64-column half hh) =====
     [[maybe_unused]] int tse = 0;
@@ -1535,6 +1522,133 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     const int row = q * 32 + lane;
     const int swz = row & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (chain) {
+        // ---- chained pre-phase: x <- LN0(x + att Wo^T + bo) for this CTA's 128 rows x 128 columns; the fp32 tile goes back
+        // to global memory (it is the residual of the feed-forward block), the bf16 tile becomes K-blocks 2p, 2p+1 of the
+        // A operand in the X region of this CTA and (bulk copy through DSMEM) of the partner with the other columns
+        float v[64];
+        const int pidx0 = (int)p * 2 + hh;
+        if (epi) {
+            mbar_wait(pre_acc, 0);
+            tcgen05_fence_after();
+            mbar_wait(resid_bar, 0);
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 + hh * 64 + c0), r);
+                const uint8_t* box = gen + OFF_RING + SLOT + (2 * hh + c0 / 32) * 16384 + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
+                    const int j = c0 + 4 * c;
+                    const float4 bv = *reinterpret_cast<const float4*>(prm + 640 + hh * 64 + j);
+                    v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
+                    v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
+                    v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
+                    v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+                }
+            }
+            float mean, m2;
+            ln_local_stats(v, mean, m2);
+            part0[pidx0 * BM + row] = make_float2(mean, m2);
+            st_peer_f32x2(smem_u32(&part0[pidx0 * BM + row]), xpeer, mean, m2);
+            if (threadIdx.x == 64) mbar_expect_tx(x2_recv, 32768);
+        }
+        __syncwarp();
+        cluster_sync_all();   // statistics exchanged; every pair's pre-phase GEMM has finished reading its X regions
+        if (epi) {
+            ln_normalise(v, part0, row, prm + 768 + hh * 64, prm + 896 + hh * 64);
+            ln_store_tiles(v, gen + OFF_RING + SLOT + 2 * hh * 16384, gen + (2 * (int)p + hh) * 16384, row);
+            tcgen05_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + OFF_RING + SLOT + bx * 16384, n0 + 32 * bx, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                const uint32_t own = base + 2 * p * 16384;
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mapa_u32(own, xpeer)),
+                             "r"(own), "r"(32768), "r"(mapa_u32(x2_recv, xpeer))
+                             : "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(pre_done);
+                mbar_wait(x2_recv, 0);
+                mbar_arrive_remote(mapa_u32(x2_full, leader));
+            }
+        }
+    }
+    // ---- roles, phase 2: the feed-forward main loop
+    if (producer) {
+        for (int c = 0; c < n_chunks; ++c) {
+            if (c + 1 < n_chunks) load_w1(c + 1);
+            load_w2(c);
+        }
+        // residual tile into the (now idle) X region once every MMA has completed
+        mbar_wait(acc2_full, 0);
+        mbar_expect_tx(resid_bar, 65536);
+        for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
+    }
+    if (issuer) {
+        int it = 0;
+        if (chain) {
+            mbar_wait(x2_full, 0);     // the normalised tile (A operand of GEMM1) is complete in both CTAs
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 3);
+        }
+        auto gemm1 = [&](int c) {
+            const int b = c & 1;
+            mbar_wait_cluster(acc1_empty(b), ((c >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 1000 + c);
+            const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
+            const int s = it % NSLOT;
+            mbar_wait(full_bar(s), (it / NSLOT) & 1);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 2000 + it);
+            const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(slot + kb * 8192 + k * UMMA_K * 2);
+                    umma_bf16_pair(d, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit_pair(empty_bar(s), pair_mask);
+            umma_commit_pair(acc1_full(b), pair_mask);
+            ++it;
+        };
+        auto gemm2 = [&](int c) {
+            mbar_wait_cluster(h_full, c & 1);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 3000 + c);
+            const int s = it % NSLOT;
+            mbar_wait(full_bar(s), (it / NSLOT) & 1);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 2000 + it);
+            const uint32_t slot = base + OFF_RING + s * SLOT;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(base + OFF_H + kk * 16384 + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(slot + kk * 16384 + k * UMMA_K * 2);
+                    umma_bf16_pair(tm_acc2, adesc, bdesc, idesc2, (c | kk | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit_pair(empty_bar(s), pair_mask);
+            umma_commit_pair(h_empty, pair_mask);
+            ++it;
+        };
+        gemm1(0);
+        for (int c = 0; c < n_chunks; ++c) {
+            if (c + 1 < n_chunks) gemm1(c + 1);
+            gemm2(c);
+        }
+        umma_commit_pair(acc2_full, pair_mask);
+        FFN_TS(1, tsn, 9);
+    }
+
     if (epi) {
         const uint32_t acc1_empty_l0 = mapa_u32(acc1_empty(0), leader), acc1_empty_l1 = mapa_u32(acc1_empty(1), leader);
         const uint32_t h_full_l = mapa_u32(h_full, leader);
@@ -1617,7 +1731,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     float v[64];
     const int pidx = (int)p * 2 + hh;
     if (epi) {
-        mbar_wait(resid_bar, 0);
+        mbar_wait(resid_bar, chain ? 1u : 0u);
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t r[32];
@@ -1894,9 +2008,40 @@ int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat1
     return 0;
 }
 
+// Number of co-resident clusters of the CTA-pair kernel (0: not usable); TTB_FFN_PAIR=0/1 forces the choice.
+static int ffn_pair_clusters() {
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        cudaError_t e = cudaFuncSetAttribute(tc::ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ffn::SMEM);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(4 * kNumSMs);
+        cfg.blockDim = dim3(tc::ffn::THREADS);
+        cfg.dynamicSmemBytes = tc::ffn::SMEM;
+        int n = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, tc::ffn_pair_kernel, &cfg);
+        max_clusters = e == cudaSuccess ? n : 0;
+        (void)cudaGetLastError();
+        if (getenv("TTB_DEBUG")) fprintf(stderr, "[ttb] ffn_pair_kernel: %d co-resident clusters of 4 (%s)\n", max_clusters, cudaGetErrorString(e));
+    }
+    return max_clusters;
+}
+bool ffn_pair_available(int max_rows) {
+    static const int pair_env = [] { const char* v = getenv("TTB_FFN_PAIR"); return v ? atoi(v) : -1; }();
+    if (pair_env == 0) return false;
+    const int clusters = ffn_pair_clusters();
+    if (clusters <= 0) return false;
+    return pair_env == 1 || (max_rows + 2 * tc::BM - 1) / (2 * tc::BM) <= clusters;
+}
+
 int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,
-                     float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s) {
+                     float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s,
+                     const __nv_bfloat16* att, const __nv_bfloat16* Wo, const float* bias_o, const float* g0, const float* b0) {
     using namespace tc;
+    const bool chain = att && Wo;
+    if (chain && !ffn_pair_available(rows.max_rows)) {
+        set_last_error("chained feed-forward launch without the CTA-pair kernel");
+        return 4;
+    }
     if (rows.max_rows <= 0) return 0;
     if (F % 256 != 0 || F / 2 > ffn::MAX_HALF || (reinterpret_cast<uintptr_t>(W1) & 15) || (reinterpret_cast<uintptr_t>(W2) & 15) ||
         (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(xh) & 15)) {
@@ -1935,29 +2080,22 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
         }
     }
 #endif
-    // CTA-pair kernel (cta_group::2, clusters of four) whenever all of its clusters are co-resident; TTB_FFN_PAIR=0/1 forces
-    static const int pair_env = [] { const char* v = getenv("TTB_FFN_PAIR"); return v ? atoi(v) : -1; }();
-    if (pair_env != 0) {
-        static int max_clusters = -1;
-        if (max_clusters < 0) {
-            cudaError_t e = cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn::SMEM);
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(4 * kNumSMs);
-            cfg.blockDim = dim3(ffn::THREADS);
-            cfg.dynamicSmemBytes = ffn::SMEM;
-            int n = 0;
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, ffn_pair_kernel, &cfg);
-            max_clusters = e == cudaSuccess ? n : 0;
-            (void)cudaGetLastError();
-            if (getenv("TTB_DEBUG")) fprintf(stderr, "[ttb] ffn_pair_kernel: %d co-resident clusters of 4 (%s)\n", max_clusters, cudaGetErrorString(e));
-        }
+    // CTA-pair kernel (cta_group::2, clusters of four) whenever all of its clusters are co-resident
+    if (ffn_pair_available(rows.max_rows)) {
         const int blocks = (rows.max_rows + 2 * BM - 1) / (2 * BM);
-        if (pair_env == 1 || blocks <= max_clusters) {
-            CUtensorMap tmW1h;
-            if (int rc = get_tensor_map(W1, F, 256, 256, 64, &tmW1h)) return rc;
-            launch_pdl(ffn_pair_kernel, dim3(4 * blocks), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1h, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F);
-            return 0;
+        CUtensorMap tmW1h, tmAtt = tmXh, tmWoh = tmXh;
+        if (int rc = get_tensor_map(W1, F, 256, 256, 64, &tmW1h)) return rc;
+        if (chain) {
+            if ((reinterpret_cast<uintptr_t>(att) & 15) || (reinterpret_cast<uintptr_t>(Wo) & 15)) {
+                set_last_error("chained feed-forward launch needs 16-byte aligned operands");
+                return 4;
+            }
+            if (int rc = get_tensor_map(att, rows.max_rows, 256, 256, BM, &tmAtt)) return rc;
+            if (int rc = get_tensor_map(Wo, 256, 256, 256, 64, &tmWoh)) return rc;
         }
+        launch_pdl(ffn_pair_kernel, dim3(4 * blocks), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1h, tmW2, tmX, bias1, bias2, g1, b1, g2, b2,
+                   rows, F, tmAtt, tmWoh, bias_o, g0, b0, chain ? 1 : 0);
+        return 0;
     }
     static const int ffn_dbg = [] { const char* v = getenv("TTB_FFN_DBG"); return v ? atoi(v) : 0; }();
     launch_pdl(ffn_fused_kernel, dim3(2 * tiles), dim3(ffn::THREADS), (size_t)ffn::SMEM, s, tmXh, tmW1, tmW2, tmX, bias1, bias2, g1, b1, g2, b2, rows, F, ffn_dbg);

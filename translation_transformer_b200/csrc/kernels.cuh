@@ -58,8 +58,13 @@ int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat1
 
 // Fused feed-forward sub-layer for embedding_dim 256 (bf16 path):
 //   x <- LN2?(LN1(x + relu(xh W1^T + b1) W2^T + b2)), x fp32 and its bf16 copy xh both updated in place.
+// Chained form (att, Wo given; only with the CTA-pair kernel, see ffn_pair_available): the same launch first computes the
+// preceding sub-layer tail x <- LN0(x + att Wo^T + bias_o) (the cross-attention out-projection), i.e. xh is not read.
 int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,
-                     float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s);
+                     float* x, const float* g1, const float* b1, const float* g2, const float* b2, RowCount rows, int F, cudaStream_t s,
+                     const __nv_bfloat16* att = nullptr, const __nv_bfloat16* Wo = nullptr, const float* bias_o = nullptr,
+                     const float* g0 = nullptr, const float* b0 = nullptr);
+bool ffn_pair_available(int max_rows);   // the cta_group::2 feed-forward kernel can run all its clusters co-resident
 
 // ---- attention.cu ---------------------------------------------------------------------------
 // Generic masked attention over "groups".  Queries of group g are tokens g*Lq .. g*Lq+Lq-1 of

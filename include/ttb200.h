@@ -140,6 +140,11 @@ int ttb_engine_get_history(ttb_engine* e, int32_t* live_queries_out, int32_t cap
 int ttb_gemm(int32_t precision, const void* A_dev, const void* W_dev, const float* bias_dev, float* C_dev,
              int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 
+/* Same with a bf16 result (the form the decoder uses for the QKV / cross K-V projections: wide K = 256 projections run
+ * on the CTA-pair kernel). */
+int ttb_gemm_bf16_out(const void* A_dev, const void* W_dev, const float* bias_dev, void* C_dev, int32_t M, int32_t N, int32_t K,
+                      int32_t relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

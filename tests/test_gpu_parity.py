@@ -204,6 +204,20 @@ def test_gemm_bf16_tcgen05_vs_torch(dev):
             ref = ref.clamp_min(0)
         err = (Cm.double() - ref).abs().max().item()
         assert err < 2e-3, (M, N, K, relu, err)
+    # bf16 result: K = 256 and N a multiple of 384 / 256 run on the CTA-pair kernel (cta_group::2) from 1024 rows on,
+    # the other shapes on the persistent kernel; error bound = bf16 rounding of the result
+    for (M, N, K, relu) in ((8096, 768, 256, 0), (2000, 768, 256, 1), (1025, 512, 256, 0), (1300, 1536, 256, 0), (700, 768, 256, 0), (3000, 256, 256, 0)):
+        A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+        W = (torch.randn(N, K, generator=g) * 0.1).to(dev).bfloat16()
+        b = torch.randn(N, generator=g).to(dev)
+        Cm = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.ttb_gemm_bf16_out(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, relu, None), "ttb_gemm_bf16_out")
+        torch.cuda.synchronize()
+        ref = A.float().double() @ W.float().double().t() + b.double()
+        if relu:
+            ref = ref.clamp_min(0)
+        err = ((Cm.double() - ref).abs() / (1.0 + ref.abs())).max().item()
+        assert err < 6e-3, (M, N, K, relu, err)
 
 
 @pytest.mark.parametrize("name", ["small", "full"])

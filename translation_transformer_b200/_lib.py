@@ -58,6 +58,7 @@ SIGNATURES = {
     "ttb_engine_get_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "ttb_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                            C.c_int32, C.c_void_p]),
+    "ttb_gemm_bf16_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

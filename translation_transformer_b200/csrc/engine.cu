@@ -1346,4 +1346,16 @@ int ttb_gemm(int32_t precision, const void* A_dev, const void* W_dev, const floa
     return 0;
 }
 
+int ttb_gemm_bf16_out(const void* A_dev, const void* W_dev, const float* bias_dev, void* C_dev, int32_t M, int32_t N, int32_t K,
+                      int32_t relu, void* stream) {
+    TTB_CHECK(A_dev && W_dev && C_dev && M > 0 && N > 0 && K > 0, "bad arguments");
+    TTB_CHECK(K % 64 == 0, "K must be a multiple of 64");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (int rc = launch_gemm_bf16_tc<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(A_dev), K, static_cast<const __nv_bfloat16*>(W_dev), bias_dev,
+                                                    static_cast<__nv_bfloat16*>(C_dev), N, RowCount(M), N, K, relu != 0, s))
+        return rc;
+    TTB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

@@ -1807,6 +1807,159 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 }
 
 // =====================================================================================================
+// Wide projection with K = 256 on CTA pairs (cta_group::2):  C[M, N] = A[M, 256] W[N, 256]^T + bias (+ReLU), bf16 out.
+// The persistent kernel re-loads the A tile for every 128-column tile of the output (QKV: six times) and every CTA
+// stages whole weight tiles, so a QKV launch moves ~50 MB from L2 into shared memory and is bound by exactly that.
+// Here one pair owns 256 rows x (CHUNKS x 128) columns: each CTA keeps its own 128 rows of A (64 KB, loaded once) and
+// HALF of the pair's weight rows (CHUNKS x 32 KB), everything resident at once (no ring), M = 256 MMAs into CHUNKS
+// accumulator tiles of 128 columns.  Traffic per QKV launch: 20 MB.  Epilogue per chunk as soon as its accumulator is
+// complete: + bias -> bf16 -> swizzled staging tile in the (consumed) weight region of the chunk -> TMA store.
+namespace pgk {
+constexpr int THREADS = 320;
+constexpr int MAXC = 3;
+constexpr int OFF_W = 65536;                                  // after the A tile
+constexpr int OFF_BIAS = OFF_W + MAXC * 32768;
+constexpr int OFF_BAR = OFF_BIAS + MAXC * 128 * 4;
+constexpr int SMEM = OFF_BAR + 128 + 1024;
+}  // namespace pgk
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pgk::THREADS, 1)
+gemm_pair_k256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, RowCount rows, int chunks,
+                      int pairs_per_block, int relu) {
+    using namespace pgk;
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(t));
+    const int pair = blockIdx.x >> 1;
+    const int mblk = (pair / pairs_per_block) * (2 * BM);
+    const int m0 = mblk + (int)t * BM;
+    const int col0 = (pair % pairs_per_block) * chunks * 128;   // first output column of the pair
+    const uint16_t pair_mask = 3;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    float* bias_sm = reinterpret_cast<float*>(gen + OFF_BIAS);
+    const uint32_t bar_base = base + OFF_BAR;
+    const uint32_t a_full = bar_base;                                       // even CTA: A tiles of both CTAs
+    auto w_full = [&](int c) { return bar_base + 8u * (1 + c); };          // even CTA: weight halves of chunk c
+    auto acc_full = [&](int c) { return bar_base + 8u * (1 + MAXC + c); }; // both CTAs: accumulator of chunk c complete
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (1 + 2 * MAXC));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(a_full, 1);
+            for (int c = 0; c < MAXC; ++c) { mbar_init(w_full(c), 1); mbar_init(acc_full(c), 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int tt = threadIdx.x - 64;
+        for (int i = tt; i < chunks * 128; i += 256) bias_sm[i] = bias ? __ldg(bias + col0 + i) : 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();   // both CTAs have initialised their barriers and own their tensor memory
+    pdl_launch_dependents();
+    // the weights do not depend on earlier kernels: they are requested before the dependency wait
+    const bool producer = warp == 0 && lane == 0;
+    if (producer) {
+        for (int c = 0; c < chunks; ++c) {
+            const uint32_t wl = mapa_u32(w_full(c), 0);
+            if (t == 0) mbar_expect_tx(w_full(c), 2 * 32768);
+            for (int kb = 0; kb < 4; ++kb)
+                tma_load_2d_pair(base + OFF_W + c * 32768 + kb * 8192, &tmWh, kb * BK, col0 + c * 128 + (int)t * 64, wl);
+        }
+    }
+    pdl_wait();
+    const bool live = mblk < rows.live();   // uniform per pair
+    if (producer) {
+        if (live) {
+            const uint32_t al = mapa_u32(a_full, 0);
+            if (t == 0) mbar_expect_tx(a_full, 2 * 65536);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, &tmA, kb * BK, m0, al);
+        } else if (t == 0) {
+            for (int c = 0; c < chunks; ++c) mbar_wait(w_full(c), 0);   // requested weights must land before the pair may exit
+        }
+    } else if (warp == 1 && lane == 0 && live && t == 0) {   // ===== MMA issuer: even CTA =====
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, 128);
+        mbar_wait(a_full, 0);
+        tcgen05_fence_after();
+        for (int c = 0; c < chunks; ++c) {
+            mbar_wait(w_full(c), 0);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
+                    const uint64_t bdesc = umma_desc_sw128(base + OFF_W + c * 32768 + kb * 8192 + k * UMMA_K * 2);
+                    umma_bf16_pair(tmem_base + (uint32_t)(c * 128), adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit_pair(acc_full(c), pair_mask);
+        }
+    }
+    // ===== epilogue warps 2..9: thread = (row, 64-column half hh of the chunk) =====
+    if (warp >= 2 && live) {
+        const int q = warp & 3, hh = (warp - 2) >> 2;
+        const int row = q * 32 + lane, swz = row & 7;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        for (int c = 0; c < chunks; ++c) {
+            mbar_wait(acc_full(c), 0);
+            tcgen05_fence_after();
+            uint32_t pk[32];   // 64 bf16 values
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(c * 128 + hh * 64 + c0), r);
+                const float4* bb = reinterpret_cast<const float4*>(bias_sm + c * 128 + hh * 64 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = bb[j >> 2];
+                    float v0 = __uint_as_float(r[j]) + bv.x, v1 = __uint_as_float(r[j + 1]) + bv.y;
+                    float v2 = __uint_as_float(r[j + 2]) + bv.z, v3 = __uint_as_float(r[j + 3]) + bv.w;
+                    if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                    __nv_bfloat162 p01 = __floats2bfloat162_rn(v0, v1), p23 = __floats2bfloat162_rn(v2, v3);
+                    pk[(c0 + j) >> 1] = *reinterpret_cast<uint32_t*>(&p01);
+                    pk[((c0 + j) >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p23);
+                }
+            }
+            // the weight halves of chunk c (32 KB) are consumed: they become the two [128 x 64] output boxes of the chunk
+            uint8_t* orow = gen + OFF_W + c * 32768 + hh * 16384 + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(orow + ((ch ^ swz) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmC, base + OFF_W + c * 32768 + hb * 16384, col0 + c * 128 + hb * 64, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the tensor memory of a pair is released together
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// =====================================================================================================
 // Vocabulary projection + arg-max for the greedy loop:  pred[row] = argmax_v (xh[row] . Wc[v] + bc[v])
 // (first maximal index, like torch.argmax).  The logits never leave the SM: one CTA per 128 rows keeps
 // the whole [V x K] classifier weight and its A tile in shared memory (K = 256: 64 KB + 144 KB for V = 288),
@@ -1938,6 +2091,29 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     }
     CUtensorMap tmA, tmB;
     if (int rc = get_tensor_map(A, rows.max_rows, K, lda, BM, &tmA)) return rc;
+    if constexpr (std::is_same<OutT, __nv_bfloat16>::value) {
+        // wide K = 256 projections (QKV, cross K/V): CTA-pair kernel, every operand resident, A loaded once per row
+        static const bool pair_off = [] { const char* v = getenv("TTB_GEMM_PAIR"); return v && v[0] == '0'; }();
+        const int chunks = N % 384 == 0 ? 3 : (N % 256 == 0 && N >= 512 ? 2 : 0);
+        if (!pair_off && K == 256 && chunks && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && rows.max_rows >= 1024) {
+            static bool attr = false;
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(gemm_pair_k256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pgk::SMEM);
+                if (e != cudaSuccess) {
+                    set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
+                    return 1;
+                }
+                attr = true;
+            }
+            CUtensorMap tmWh, tmC;
+            if (int rc = get_tensor_map(W, N, K, K, 64, &tmWh)) return rc;
+            if (int rc = get_tensor_map(C, rows.max_rows, N, ldc, BM, &tmC)) return rc;
+            const int blocks = (rows.max_rows + 2 * BM - 1) / (2 * BM), ppb = N / (chunks * 128);
+            launch_pdl(gemm_pair_k256_kernel, dim3(2 * blocks * ppb), dim3(pgk::THREADS), (size_t)pgk::SMEM, s, tmA, tmWh, tmC, bias, rows, chunks, ppb,
+                       relu ? 1 : 0);
+            return 0;
+        }
+    }
     if (int rc = get_tensor_map(W, N, K, K, BN, &tmB)) return rc;
     static const bool use_v1 = [] { const char* v = getenv("TTB_GEMM_V1"); return v && v[0] == '1'; }();
     constexpr int which = std::is_same<OutT, float>::value ? 0 : 1;

@@ -13,18 +13,25 @@ import bench  # noqa: E402
 
 
 def main():
-    sys.argv = [sys.argv[0]] + sys.argv[1:]
+    beam = "--beam" in sys.argv
+    sys.argv = [a for a in sys.argv if a != "--beam"]
     args = bench.parse()
     from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
     from translation_transformer_b200.model import B200Transformer
     cfg, sd = bench.build_weights(args)
     eng = B200Transformer(cfg, sd, precision=args.precision, device=0)
     gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, bench.PAD, bench.BOS, bench.EOS, bench.REPLACE)
+    nq = args.batch_size
+    if beam:   # BASELINE.json configs[2]: speculative beam search bs=4, n_best=5
+        from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+        gen = TranslationInferenceBeamSearchSpeculative(eng, args.max_len, 5, args.draft_len, args.n_drafts, args.vocab, False,
+                                                        bench.PAD, bench.BOS, bench.EOS, bench.REPLACE)
+        nq = 4
     dev = torch.device("cuda", 0)
     for i in range(3):
-        gen.generate(bench.batch_for(args, 0, i).to(dev))
+        gen.generate(bench.batch_for(args, 0, i)[:nq].to(dev))
     torch.cuda.synchronize()
-    src = bench.batch_for(args, 0, 3).to(dev)
+    src = bench.batch_for(args, 0, 3)[:nq].to(dev)
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         gen.generate(src)
         torch.cuda.synchronize()

@@ -53,18 +53,29 @@ void launch_beam_build_lib(const BeamState& st, cudaStream_t s) {
 
 // ---- prepare ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int W, int dl) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // one warp per candidate row, coalesced scan: first PAD column, EOS anywhere, a real token behind the first PAD
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int c = warp; c < C; c += n_warps) {
         const int* row = st.cand_cur + (long long)c * st.ldw;
-        int slot0 = -1, fin = 0, hole = 0;
-        for (int j = 0; j < W; ++j) {
+        int first_pad = 0x7fffffff, last_real = -1, fin = 0;
+        for (int j = lane; j < W; j += 32) {
             const int t = row[j];
             if (t == st.eos) fin = 1;
-            if (t == st.pad) { if (slot0 < 0) slot0 = j; }
-            else if (slot0 >= 0) hole = 1;           // a real token after a PAD: draft slots not contiguous
+            if (t == st.pad) first_pad = min(first_pad, j); else last_real = max(last_real, j);
         }
-        st.c_slot0[c] = slot0;
-        st.c_fin[c] = fin;
-        if (hole || slot0 < 1 || slot0 + dl + 1 > W) atomicExch(&st.ctrl[BC_ERROR], 3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            first_pad = min(first_pad, __shfl_xor_sync(0xffffffffu, first_pad, o));
+            last_real = max(last_real, __shfl_xor_sync(0xffffffffu, last_real, o));
+            fin |= __shfl_xor_sync(0xffffffffu, fin, o);
+        }
+        if (lane == 0) {
+            const int slot0 = first_pad == 0x7fffffff ? -1 : first_pad;
+            const int hole = slot0 >= 0 && last_real > slot0;   // a real token after a PAD: draft slots not contiguous
+            st.c_slot0[c] = slot0;
+            st.c_fin[c] = fin;
+            if (hole || slot0 < 1 || slot0 + dl + 1 > W) atomicExch(&st.ctrl[BC_ERROR], 3);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -268,6 +279,8 @@ __global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const flo
     sum = warp_sum(sum);
     float* topv = st.topv + (long long)rp * K;
     int* topi = st.topi + (long long)rp * K;
+    float my_v = -INFINITY;
+    int my_i = -1;
     for (int j = 0; j < K; ++j) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
@@ -285,25 +298,34 @@ __global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const flo
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
             if (lane + 32 * k == bi) v[k] = -INFINITY;                          // taken
+        // every lane holds (bv, bi) after the butterfly: lane j keeps entry j for the support scan below
+        if (lane == (j & 31)) { my_v = bv; my_i = bi == 0x7fffffff ? -1 : bi; }
         if (lane == 0) { topv[j] = bv; topi[j] = bi == 0x7fffffff ? -1 : bi; }
     }
-    __syncwarp();
-    if (lane == 0) {
-        st.lmax[rp] = mx;
-        st.lsum[rp] = sum;
+    {
+        // truncated support: entry j is kept while the exclusive cumulative probability of entries 0..j-1 is < 0.9975
+        // (sequential sum in entry order, as the reference's cumsum; K <= 32 entries live one per lane)
         int keep = 1;
         float cum = 0.f;
-        for (int j = 1; j < K && topi[j] >= 0; ++j) {
-            cum += expf(topv[j - 1] - mx) / sum;
+        for (int j = 1; j < K; ++j) {
+            const float pv = __shfl_sync(0xffffffffu, my_v, j - 1);
+            const int ij = __shfl_sync(0xffffffffu, my_i, j);
+            if (ij < 0) break;
+            cum += expf(pv - mx) / sum;
             if (cum < 0.9975f) keep = j + 1; else break;
         }
-        st.nkeep[rp] = keep;
+        if (lane == 0) {
+            st.lmax[rp] = mx;
+            st.lsum[rp] = sum;
+            st.nkeep[rp] = keep;
+        }
     }
 }
 void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s) {
     const int T = max_rows * (dl + 1);
     if (T <= 0) return;
-    if (st.V <= 512) beam_stats_kernel<16><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
+    if (st.V <= 320) beam_stats_kernel<10><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
+    else if (st.V <= 512) beam_stats_kernel<16><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
     else beam_stats_kernel<32><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
 }
 
@@ -491,14 +513,22 @@ __global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) 
     if (threadIdx.x == 0) { s_all_fin = 1; s_min_pad = 0x7fffffff; s_acc = 0; s_cnt = 0; }
     __syncthreads();
     const int R = st.B * st.K;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int r = warp; r < R; r += n_warps) {   // one warp per new hypothesis, coalesced scan
         const int* row = st.cand_next + (long long)r * st.ldw;
         int pads = 0, fin = 0;
-        for (int j = 0; j < W; ++j) { pads += row[j] == st.pad; fin |= row[j] == st.eos; }
-        if (!fin) atomicAnd(&s_all_fin, 0);
-        atomicMin(&s_min_pad, pads);
-        const int a = st.acc_stat[r];
-        if (a >= 0) { atomicAdd(&s_acc, a); atomicAdd(&s_cnt, 1); }
+        for (int j = lane; j < W; j += 32) { const int t = row[j]; pads += t == st.pad; fin |= t == st.eos; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pads += __shfl_xor_sync(0xffffffffu, pads, o);
+            fin |= __shfl_xor_sync(0xffffffffu, fin, o);
+        }
+        if (lane == 0) {
+            if (!fin) atomicAnd(&s_all_fin, 0);
+            atomicMin(&s_min_pad, pads);
+            const int a = st.acc_stat[r];
+            if (a >= 0) { atomicAdd(&s_acc, a); atomicAdd(&s_cnt, 1); }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -349,7 +349,7 @@ def main():
     insitu = None
     if rank == 0 and not args.no_insitu:
         try:
-            insitu = insitu_kernel_times(lambda: one_step(args.warmup, False))
+            insitu = insitu_kernel_times(lambda: gen.generate(devb[args.warmup]))   # rank-local: no collective in here
         except Exception as ex:   # CUPTI not available: the event-bracket figures stand alone
             insitu = {"error": str(ex)[:120]}
 

@@ -114,3 +114,29 @@ def test_query_sharding_and_prediction_gather_gloo_world2(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_predict_driver_batches_and_synthetic_vocab(tmp_path):
+    """scripts/predict.py: file -> fixed-size batches in file order (seq2seq_wrappers.py:122-128, 168-175) and the
+    synthetic vocabulary decodes / re-encodes one to one (the CSV of a synthetic run can be tokenized back)."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("predict_driver", Path(__file__).resolve().parent.parent / "scripts" / "predict.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    golden = Path(__file__).resolve().parent / "golden"
+    args = types.SimpleNamespace(synthetic=0, src_file=str(golden / "product_prediction_src_test.txt"),
+                                 tgt_file=str(golden / "product_prediction_tgt_test.txt"), vocab_path=None, batch_size=4, vocab=288)
+    tk, batches = mod.load_batches(args)
+    lines = [l.strip() for l in open(args.src_file) if l.strip()]
+    assert sum(b["src_tokens"].shape[0] for b in batches) == len(lines)
+    assert all(b["src_tokens"].shape[0] == 4 for b in batches[:-1])
+    assert tk.decode(batches[0]["src_tokens"][1].tolist()) == lines[1]
+    assert int(batches[0]["src_tokens"][0, 0]) == tk.bos_token_idx and int((batches[0]["src_tokens"] == tk.pad_token_idx).sum()) > 0
+    stk = mod.synthetic_tokenizer(288)
+    assert stk.n_tokens == 288 and stk.encoder_dict["c"] == 7
+    ids = list(range(4, 288))
+    assert stk.encode(stk.decode(ids))[1:-1] == ids
+    args2 = types.SimpleNamespace(synthetic=70, batch_size=32, vocab=288)
+    _, sb = mod.load_batches(args2)
+    assert [b["src_tokens"].shape[0] for b in sb] == [32, 32, 6]

@@ -330,8 +330,8 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
     const uint32_t tmem_base = *tmem_slot;
     // everything above is independent of earlier kernels; from here on their results are needed
     pdl_launch_dependents();
+    const int M = rows.live();   // written before this programmatic chain started (see gemm_pair_k256_kernel): fetched ahead of the wait
     pdl_wait();
-    const int M = rows.live();
     const int n_tiles_n = (N + BN - 1) / BN;
     const int total_tiles = ((M + BM - 1) / BM) * n_tiles_n;   // CTAs beyond it skip straight to the teardown
 
@@ -683,8 +683,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     // everything above is independent of earlier kernels (weights only); from here on their results are needed
     pdl_launch_dependents();
+    const int live_rows = rows.live();   // written before this programmatic chain started (see gemm_pair_k256_kernel): fetched ahead of the wait
     pdl_wait();
-    const bool live = m0 < rows.live();   // uniform per cluster: dead tiles only take part in the barriers
+    const bool live = m0 < live_rows;    // uniform per cluster: dead tiles only take part in the barriers
 
     if (warp == 0) {
         if (lane == 0 && live) {  // ===== TMA producer =====
@@ -984,11 +985,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     const uint32_t tm_acc2 = tmem_base, tm_acc1 = tmem_base + 256u;
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // phase 0: "this CTA is running"
     pdl_launch_dependents();
+    const int live_rows = rows.live();   // written before this programmatic chain started: fetched ahead of the wait
     pdl_wait();
 #ifdef TTB_FFN_TIMELINE
     if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
 #endif
-    const bool live = m0 < rows.live();   // uniform per cluster: dead tiles only take part in the barriers
+    const bool live = m0 < live_rows;   // uniform per cluster: dead tiles only take part in the barriers
 
     if (warp == 0) {
         if (lane == 0 && live) {  // ===== TMA producer =====
@@ -1438,11 +1440,12 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][254][0] = 6; g_ffn_ts[2][254][1] = clock64(); }
 #endif
     pdl_launch_dependents();
+    const int live_rows = rows.live();   // written before this programmatic chain started: fetched ahead of the wait
     pdl_wait();
 #ifdef TTB_FFN_TIMELINE
     if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
 #endif
-    const bool live = mblk < rows.live();   // uniform per cluster: dead blocks only take part in the cluster barriers
+    const bool live = mblk < live_rows;   // uniform per cluster: dead blocks only take part in the cluster barriers
 
     // ---- roles, phase 1 (chained launches only): operands and GEMM of the pre-phase.  The producer / issuer threads come
     // back to the cluster barrier of the pre-phase before they start the feed-forward main loop.
@@ -1563,16 +1566,17 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
-                for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + OFF_RING + SLOT + bx * 16384, n0 + 32 * bx, m0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // the tile halves first: they gate GEMM1; the fp32 store only gates ring slots 1-2 (second weight tile)
                 const uint32_t own = base + 2 * p * 16384;
                 asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mapa_u32(own, xpeer)),
                              "r"(own), "r"(32768), "r"(mapa_u32(x2_recv, xpeer))
                              : "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                mbar_arrive(pre_done);
+                for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + OFF_RING + SLOT + bx * 16384, n0 + 32 * bx, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 mbar_wait(x2_recv, 0);
                 mbar_arrive_remote(mapa_u32(x2_full, leader));
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(pre_done);
             }
         }
     }
@@ -1883,8 +1887,12 @@ gemm_pair_k256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tma_load_2d_pair(base + OFF_W + c * 32768 + kb * 8192, &tmWh, kb * BK, col0 + c * 128 + (int)t * 64, wl);
         }
     }
+    // The live row count is written by the bookkeeping kernel that ends the previous decoding iteration (or opens this
+    // one); the launch right behind that kernel is a fully serialised one, so no kernel of a programmatic chain can run
+    // ahead of it: the count is fetched before the dependency wait (its ~1000-cycle round trip leaves the critical path).
+    const int live_rows = rows.live();
     pdl_wait();
-    const bool live = mblk < rows.live();   // uniform per pair
+    const bool live = mblk < live_rows;   // uniform per pair
     if (producer) {
         if (live) {
             const uint32_t al = mapa_u32(a_full, 0);
@@ -2010,8 +2018,8 @@ classifier_argmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
+    const int M = rows.live();   // written before this programmatic chain started (see gemm_pair_k256_kernel): fetched ahead of the wait
     pdl_wait();
-    const int M = rows.live();
     const bool live = m0 < M;
 
     if (warp == 0) {

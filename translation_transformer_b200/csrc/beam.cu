@@ -131,6 +131,7 @@ void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cu
 template <typename ActT>
 __global__ void beam_embed_cached_kernel(BeamState st, int beam, int dl, const float* __restrict__ table, const float* __restrict__ pe,
                                          int E, float* __restrict__ x, ActT* __restrict__ xh) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= st.ctrl[BC_NLIVE_ROWS] * (dl + 1)) return;
@@ -160,7 +161,7 @@ void launch_beam_embed_cached(const BeamState& st, int beam, int max_rows, int d
                               float* x, ActT* xh, cudaStream_t s) {
     const int T = max_rows * (dl + 1);
     if (T <= 0) return;
-    beam_embed_cached_kernel<ActT><<<(T + 7) / 8, 256, 0, s>>>(st, beam, dl, table, pe, E, x, xh);
+    launch_pdl(beam_embed_cached_kernel<ActT>, dim3((T + 7) / 8), dim3(256), 0, s, st, beam, dl, table, pe, E, x, xh);
 }
 template void launch_beam_embed_cached<float>(const BeamState&, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
 template void launch_beam_embed_cached<__nv_bfloat16>(const BeamState&, int, int, int, const float*, const float*, int, float*, __nv_bfloat16*,
@@ -170,6 +171,7 @@ template <typename ActT>
 __global__ void beam_cache_update_kernel(BeamState st, int dl, const ActT* __restrict__ qkv_all, long long qkv_layer_stride, int qkv_ld,
                                          int E, const ActT* __restrict__ kc_cur, const ActT* __restrict__ vc_cur, ActT* __restrict__ kc_next,
                                          ActT* __restrict__ vc_next, long long cache_layer_stride, long long cache_cand_stride) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     const int cn = blockIdx.x, l = blockIdx.y;
     const int parent = st.n_parent[cn];
     if (parent < 0) return;                         // child of a finished hypothesis: never decoded again
@@ -200,7 +202,7 @@ void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, 
                               int E, const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
                               long long cache_cand_stride, cudaStream_t s) {
     dim3 grid(st.B * st.K, n_layers);
-    beam_cache_update_kernel<ActT><<<grid, 256, 0, s>>>(st, dl, qkv_all, qkv_layer_stride, qkv_ld, E, kc_cur, vc_cur, kc_next, vc_next,
+    launch_pdl(beam_cache_update_kernel<ActT>, dim3(grid), dim3(256), 0, s, st, dl, qkv_all, qkv_layer_stride, qkv_ld, E, kc_cur, vc_cur, kc_next, vc_next,
                                                         cache_layer_stride, cache_cand_stride);
 }
 template void launch_beam_cache_update<float>(const BeamState&, int, const float*, long long, int, int, int, const float*, const float*, float*,
@@ -259,6 +261,7 @@ template void launch_beam_gather<__nv_bfloat16>(const BeamState&, const float*, 
 // the best token always kept; speculative_decoding.py:886-899).
 template <int VPL>
 __global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const float* __restrict__ logits, int dl) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     const int rp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (rp >= st.ctrl[BC_NLIVE_ROWS] * (dl + 1)) return;
@@ -324,13 +327,14 @@ __global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const flo
 void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s) {
     const int T = max_rows * (dl + 1);
     if (T <= 0) return;
-    if (st.V <= 320) beam_stats_kernel<10><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
-    else if (st.V <= 512) beam_stats_kernel<16><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
-    else beam_stats_kernel<32><<<(T + 7) / 8, 256, 0, s>>>(st, logits, dl);
+    if (st.V <= 320) launch_pdl(beam_stats_kernel<10>, dim3((T + 7) / 8), dim3(256), 0, s, st, logits, dl);
+    else if (st.V <= 512) launch_pdl(beam_stats_kernel<16>, dim3((T + 7) / 8), dim3(256), 0, s, st, logits, dl);
+    else launch_pdl(beam_stats_kernel<32>, dim3((T + 7) / 8), dim3(256), 0, s, st, logits, dl);
 }
 
 // ---- accepted lengths + best draft per candidate ------------------------------------------------------------
 __global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, int beam, int dl, int iter) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     const int c = blockIdx.x, lane = threadIdx.x;
     __shared__ int s_nacc[64];
     if (c >= C) return;
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, in
     }
 }
 void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s) {
-    beam_choose_kernel<<<C, 32, 0, s>>>(st, C, beam, dl, iter);
+    launch_pdl(beam_choose_kernel, dim3(C), dim3(32), 0, s, st, C, beam, dl, iter);
 }
 
 // ---- leaves of the continuation trees, n_best best per query ------------------------------------------------------
@@ -382,6 +386,7 @@ void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, 
 __device__ __forceinline__ float ref_logprob(float logit, float mx, float sum) { return logf(expf(logit - mx) / sum); }
 
 __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam, int W, int dl, const float* __restrict__ logits) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     extern __shared__ float s_score[];                 // [beam][(dl+1)][K] leaf scores, -inf when absent
     __shared__ float s_red_v[256];
     __shared__ int s_red_i[256];
@@ -504,11 +509,12 @@ void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const floa
         cudaFuncSetAttribute(beam_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    beam_expand_kernel<<<st.B, 256, smem, s>>>(st, beam, W, dl, logits);
+    launch_pdl(beam_expand_kernel, dim3(st.B), dim3(256), smem, s, st, beam, W, dl, logits);
 }
 
 // ---- loop control ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) {
+    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     __shared__ int s_all_fin, s_min_pad, s_acc, s_cnt;
     if (threadIdx.x == 0) { s_all_fin = 1; s_min_pad = 0x7fffffff; s_acc = 0; s_cnt = 0; }
     __syncthreads();
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) 
         st.ctrl[BC_PRODUCED] += s_acc + s_cnt;
     }
 }
-void launch_beam_control(const BeamState& st, int W, cudaStream_t s) { beam_control_kernel<<<1, 256, 0, s>>>(st, W); }
+void launch_beam_control(const BeamState& st, int W, cudaStream_t s) { launch_pdl(beam_control_kernel, dim3(1), dim3(256), 0, s, st, W); }
 
 __global__ void beam_init_kernel(BeamState st) {
     const long long n = (long long)st.B * st.K * st.ldw;

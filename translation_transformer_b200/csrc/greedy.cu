@@ -93,7 +93,10 @@ __global__ void greedy_advance_kernel(GreedyState st, const float* __restrict__ 
                                       const ActT* __restrict__ qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld,
                                       ActT* __restrict__ kcache, ActT* __restrict__ vcache, long long cache_layer_stride,
                                       long long cache_query_stride, int cache_ld) {
-    pdl_launch_dependents();
+    // Launched with the programmatic attribute behind the accept kernel (scheduled while it runs, starts when it is
+    // complete) but WITHOUT an early trigger of its own dependents: the kernels of the decoding iteration read the
+    // control words and descriptor table of the accept kernel ahead of their dependency waits, so none of them may be
+    // scheduled before this kernel has seen the accept kernel complete.
     pdl_wait();
     if (st.ctrl[CTRL_DONE]) return;   // after DONE neither the cache nor the embeddings are read again
     if ((int)blockIdx.x >= n_embed_blocks) {
@@ -135,7 +138,7 @@ void launch_greedy_advance(const GreedyState& st, const float* table, const floa
     const int T = st.B * st.N * (st.D + 1);
     const int n_embed_blocks = (T + 7) / 8;
     // first kernel of the captured iteration: plain launch (its predecessor is the previous graph launch)
-    greedy_advance_kernel<ActT><<<n_embed_blocks + st.B * n_layers, 256, 0, s>>>(st, table, pe, E, x, xh, n_embed_blocks, qkv_all,
+    launch_pdl(greedy_advance_kernel<ActT>, dim3(n_embed_blocks + st.B * n_layers), dim3(256), 0, s, st, table, pe, E, x, xh, n_embed_blocks, qkv_all,
                                                                               qkv_layer_stride, n_layers, qkv_ld, kcache, vcache,
                                                                               cache_layer_stride, cache_query_stride, cache_ld);
 }

@@ -1328,6 +1328,39 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
                  : "memory");
 }
 
+// A operand from tensor memory (this CTA's 128 rows, 16 K elements = 8 columns per instruction), B from shared memory
+__device__ __forceinline__ void umma_bf16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+        " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// one K-block (64 bf16 = 32 words of this thread's row, 128-byte swizzle) from shared memory into 32 tensor-memory columns
+__device__ __forceinline__ void smem_kblock_to_tmem(const uint8_t* kblock, int row, uint32_t taddr) {
+    const int swz = row & 7;
+    uint32_t w[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(kblock + row * 128 + ((c ^ swz) << 4));
+        w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
+    }
+    tmem_st_32x32(taddr, w);
+}
+
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(ffn::THREADS, 1)
 ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmW1h,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
@@ -1361,7 +1394,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     const uint32_t bar_base = base + OFF_BAR;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };                           // used in the even CTA only
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSLOT + s); };
-    const uint32_t x_full = bar_base + 8u * (2 * NSLOT);                                 // even CTA only
+    const uint32_t x_full = bar_base + 8u * (2 * NSLOT);   // chained: even CTA only (att tiles of both CTAs); else local (own X tile)
     auto acc1_full = [&](int b) { return bar_base + 8u * (2 * NSLOT + 1 + b); };
     auto acc1_empty = [&](int b) { return bar_base + 8u * (2 * NSLOT + 3 + b); };       // even CTA only (16 arrivals)
     const uint32_t h_full = bar_base + 8u * (2 * NSLOT + 5);                             // even CTA only (16 arrivals)
@@ -1374,7 +1407,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     const uint32_t pre_acc = bar_base + 8u * (2 * NSLOT + 11);      // its accumulator is complete
     const uint32_t pre_done = bar_base + 8u * (2 * NSLOT + 12);     // ring slots 1-2 (residual tile) are free again
     const uint32_t x2_recv = bar_base + 8u * (2 * NSLOT + 13);      // the partner's half of the normalised tile has landed
-    const uint32_t x2_full = bar_base + 8u * (2 * NSLOT + 14);      // even CTA only: both CTAs hold the complete tile
+    const uint32_t x2_full = bar_base + 8u * (2 * NSLOT + 14);      // even CTA only: both CTAs hold the A operand of GEMM1 in TMEM
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1406,7 +1439,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             mbar_init(pre_acc, 1);
             mbar_init(pre_done, 1);
             mbar_init(x2_recv, 1);
-            mbar_init(x2_full, 2);
+            mbar_init(x2_full, 16);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -1433,7 +1466,10 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_acc2 = tmem_base, tm_acc1 = tmem_base + 256u;
+    // tensor memory: acc2 (256 columns), acc1 (128, ONE buffer: the tensor pipe runs GEMM2 of the previous chunk while the
+    // epilogue warps drain it), and the A operand of GEMM1 (this CTA's 128 rows x 256 bf16 = 128 columns, two K elements
+    // per 32-bit cell): GEMM1 reads it from tensor memory instead of 64 KB of shared memory per hidden chunk
+    const uint32_t tm_acc2 = tmem_base, tm_acc1 = tmem_base + 256u, tm_xa = tmem_base + 384u;
     // every CTA of the cluster has initialised its barriers and owns its tensor memory before any remote signal
     cluster_sync_all();                                                      // cluster barrier phase 0
 #ifdef TTB_FFN_TIMELINE
@@ -1479,11 +1515,13 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 256);
     if (producer) {   // ===== TMA producer (both CTAs of a pair: own rows of the A operand, own half of every weight tile) =====
         FFN_TS(0, tsn, 1);
-        const uint32_t x_full_l = mapa_u32(x_full, leader);
-        if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
-        const CUtensorMap* mapA = chain ? &tmAtt : &tmXh;
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, mapA, kb * BK, m0, x_full_l);
-        if (chain) {
+        if (!chain) {   // own X tile: copied into tensor memory by this CTA's epilogue warps
+            mbar_expect_tx(x_full, X_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d(base + kb * 16384, &tmXh, kb * BK, m0, x_full);
+        } else {
+            const uint32_t x_full_l = mapa_u32(x_full, leader);
+            if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, &tmAtt, kb * BK, m0, x_full_l);
             // pre-phase operands: this CTA's 64 of the pair's 128 rows of Wo into the (still idle) H region, the fp32
             // residual tile of its 128 output columns into ring slots 1-2
             const uint32_t pf_l = mapa_u32(pre_full, leader);
@@ -1496,10 +1534,10 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     }
     if (issuer) {     // ===== MMA issuer: even CTA of the pair =====
         FFN_TS(1, tsn, 1);
-        mbar_wait(x_full, 0);
-        tcgen05_fence_after();
-        FFN_TS(1, tsn, 2);
-        if (chain) {   // pre-phase GEMM: att (X region) . Wo[128 p .. 128 p + 128)^T -> accumulator buffer 1
+        if (chain) {   // pre-phase GEMM: att (X region) . Wo[128 p .. 128 p + 128)^T -> acc1
+            mbar_wait(x_full, 0);
+            tcgen05_fence_after();
+            FFN_TS(1, tsn, 2);
             mbar_wait(pre_full, 0);
             tcgen05_fence_after();
 #pragma unroll
@@ -1508,7 +1546,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
                     const uint64_t bdesc = umma_desc_sw128(base + OFF_H + kb * 8192 + k * UMMA_K * 2);
-                    umma_bf16_pair(tm_acc1 + 128u, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
+                    umma_bf16_pair(tm_acc1, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
                 }
             }
             umma_commit_pair(pre_acc, pair_mask);
@@ -1538,7 +1576,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 + hh * 64 + c0), r);
+                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(hh * 64 + c0), r);
                 const uint8_t* box = gen + OFF_RING + SLOT + (2 * hh + c0 / 32) * 16384 + row * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -1562,6 +1600,15 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         if (epi) {
             ln_normalise(v, part0, row, prm + 768 + hh * 64, prm + 896 + hh * 64);
             ln_store_tiles(v, gen + OFF_RING + SLOT + 2 * hh * 16384, gen + (2 * (int)p + hh) * 16384, row);
+            {   // own 64 columns of the normalised row -> A operand in tensor memory (K elements 128 p + 64 hh ..)
+                uint32_t w[32];
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    __nv_bfloat162 pp = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
+                    w[jj] = *reinterpret_cast<uint32_t*>(&pp);
+                }
+                tmem_st_32x32(tm_xa + lane_base + (uint32_t)(64 * (int)p + 32 * hh), w);
+            }
             tcgen05_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1573,12 +1620,26 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                              : "memory");
                 for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + OFF_RING + SLOT + bx * 16384, n0 + 32 * bx, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                mbar_wait(x2_recv, 0);
-                mbar_arrive_remote(mapa_u32(x2_full, leader));
+            }
+            // the partner's 128 columns (K-blocks 2(1-p), 2(1-p)+1 of the X region, landed through DSMEM) -> tensor memory
+            mbar_wait(x2_recv, 0);
+            smem_kblock_to_tmem(gen + (2 * (int)(p ^ 1u) + hh) * 16384, row, tm_xa + lane_base + (uint32_t)(64 * (int)(p ^ 1u) + 32 * hh));
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_u32(x2_full, leader));
+            if (threadIdx.x == 64) {   // ring slots 1-2 are free once the fp32 store has read them
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(pre_done);
             }
         }
+    } else if (epi) {
+        // own X tile (TMA, swizzled shared memory) -> A operand in tensor memory: K-blocks 2 hh, 2 hh + 1 of this thread's row
+        mbar_wait(x_full, 0);
+        smem_kblock_to_tmem(gen + (2 * hh) * 16384, row, tm_xa + lane_base + (uint32_t)(64 * hh));
+        smem_kblock_to_tmem(gen + (2 * hh + 1) * 16384, row, tm_xa + lane_base + (uint32_t)(64 * hh + 32));
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa_u32(x2_full, leader));
     }
     // ---- roles, phase 2: the feed-forward main loop
     if (producer) {
@@ -1593,17 +1654,14 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     }
     if (issuer) {
         int it = 0;
-        if (chain) {
-            mbar_wait(x2_full, 0);     // the normalised tile (A operand of GEMM1) is complete in both CTAs
-            tcgen05_fence_after();
-            FFN_TS(1, tsn, 3);
-        }
+        mbar_wait(x2_full, 0);     // the A operand of GEMM1 is complete in the tensor memory of both CTAs
+        tcgen05_fence_after();
+        FFN_TS(1, tsn, 3);
         auto gemm1 = [&](int c) {
-            const int b = c & 1;
-            mbar_wait_cluster(acc1_empty(b), ((c >> 1) & 1) ^ 1);
+            if (c > 0) mbar_wait_cluster(acc1_empty(0), (c - 1) & 1);   // the epilogue warps of both CTAs have drained chunk c-1
             tcgen05_fence_after();
             FFN_TS(1, tsn, 1000 + c);
-            const uint32_t d = tm_acc1 + (uint32_t)(128 * b);
+            const uint32_t d = tm_acc1;
             const int s = it % NSLOT;
             mbar_wait(full_bar(s), (it / NSLOT) & 1);
             tcgen05_fence_after();
@@ -1613,13 +1671,12 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adesc = umma_desc_sw128(base + kb * 16384 + k * UMMA_K * 2);
                     const uint64_t bdesc = umma_desc_sw128(slot + kb * 8192 + k * UMMA_K * 2);
-                    umma_bf16_pair(d, adesc, bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
+                    umma_bf16_pair_ts(d, tm_xa + (uint32_t)(kb * 32 + k * 8), bdesc, idesc1, (kb | k) != 0 ? 1u : 0u);
                 }
             }
             umma_commit_pair(empty_bar(s), pair_mask);
-            umma_commit_pair(acc1_full(b), pair_mask);
+            umma_commit_pair(acc1_full(0), pair_mask);
             ++it;
         };
         auto gemm2 = [&](int c) {
@@ -1654,19 +1711,18 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     }
 
     if (epi) {
-        const uint32_t acc1_empty_l0 = mapa_u32(acc1_empty(0), leader), acc1_empty_l1 = mapa_u32(acc1_empty(1), leader);
+        const uint32_t acc1_empty_l0 = mapa_u32(acc1_empty(0), leader);
         const uint32_t h_full_l = mapa_u32(h_full, leader);
         for (int c = 0; c < n_chunks; ++c) {
-            const int b = c & 1;
             if (ts_on) FFN_TS(2, tse, 100 + c);
-            mbar_wait(acc1_full(b), (c >> 1) & 1);
+            mbar_wait(acc1_full(0), c & 1);
             tcgen05_fence_after();
             if (ts_on) FFN_TS(2, tse, 200 + c);
             uint32_t pk[32];   // 64 bf16 values
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(128 * b + hh * 64 + c0), r);
+                tmem_ld_32x32(tm_acc1 + lane_base + (uint32_t)(hh * 64 + c0), r);
                 const float4* bb = reinterpret_cast<const float4*>(b1s + c * 128 + hh * 64 + c0);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -1682,7 +1738,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(b ? acc1_empty_l1 : acc1_empty_l0);   // accumulator buffer may be overwritten
+            if (lane == 0) mbar_arrive_remote(acc1_empty_l0);   // accumulator may be overwritten
             if (ts_on) FFN_TS(2, tse, 300 + c);
             mbar_wait(h_empty, (c & 1) ^ 1);                  // GEMM2 of the previous chunk has read H (of both CTAs)
             if (ts_on) FFN_TS(2, tse, 400 + c);

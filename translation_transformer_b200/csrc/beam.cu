@@ -542,6 +542,14 @@ __global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) 
         st.ctrl[BC_EMPTY_COLS] = s_min_pad;
         st.ctrl[BC_ACCEPTED] += s_acc;
         st.ctrl[BC_PRODUCED] += s_acc + s_cnt;
+        if (st.host_ctrl) {
+            // the host reads the control words straight from its own (pinned, mapped) memory: no copy engine, no stream
+            // synchronisation between this kernel and the cache update that follows it
+            volatile int* h = st.host_ctrl;
+            for (int i = 0; i < BC_COUNT; ++i) h[i] = st.ctrl[i];
+            __threadfence_system();
+            h[BC_COUNT] = st.host_seq;
+        }
     }
 }
 void launch_beam_control(const BeamState& st, int W, cudaStream_t s) { launch_pdl(beam_control_kernel, dim3(1), dim3(256), 0, s, st, W); }

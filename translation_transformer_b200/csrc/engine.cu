@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <string>
@@ -821,6 +822,12 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.topv = (float*)(base + o_topv); st.topi = (int*)(base + o_topi); st.nkeep = (int*)(base + o_keep);
     st.lmax = (float*)(base + o_max); st.lsum = (float*)(base + o_sum);
     st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
+    {
+        void* dp = nullptr;
+        e->h_ctrl[BC_COUNT] = 0;
+        st.host_ctrl = cudaHostGetDevicePointer(&dp, e->h_ctrl, 0) == cudaSuccess ? static_cast<int*>(dp) : nullptr;
+        (void)cudaGetLastError();
+    }
     st.live_cand = (int*)(base + o_lc); st.live_query = (int*)(base + o_lq); st.c_front = (int*)(base + o_cf);
     st.n_parent = (int*)(base + o_np); st.n_keep = (int*)(base + o_nk); st.n_row = (int*)(base + o_nr);
     st.tok_cnt = (int*)(base + o_tc); st.tok_list = (int*)(base + o_tl); st.c_cnt = (int*)(base + o_cc); st.c_last = (int*)(base + o_cl);
@@ -887,6 +894,9 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, iters, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
+        // the control kernel writes the control words and, last, the iteration's sequence number into pinned host memory:
+        // the host reads them while the caches are still being re-parented and enqueues the next iteration behind that
+        st.host_seq = iters + 1;
         { Scope sc(e, KC_ACCEPT, s); launch_beam_control(st, W, s); }
         if (cached) {
             Scope sc(e, KC_CACHE_APPEND, s);
@@ -895,8 +905,23 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             std::swap(kc_cur, kc_next);
             std::swap(vc_cur, vc_next);
         }
-        TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
-        TTB_CUDA_OK(cudaStreamSynchronize(s));
+        {
+            volatile int* flag = hc + BC_COUNT;
+            bool seen = false;
+            for (long spin = 0; !seen; ++spin) {
+                seen = *flag == iters + 1;
+                if (!seen && (spin & 0x3FFF) == 0x3FFF) {
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q == cudaSuccess) {   // stream drained: the words are there (or the launch was lost: take a copy)
+                        if (*flag != iters + 1) TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
+                        seen = true;
+                    } else if (q != cudaErrorNotReady) {
+                        TTB_CUDA_OK(q);
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
         ++iters;
         if (hc[BC_ERROR]) break;
         std::swap(st.cand_cur, st.cand_next);

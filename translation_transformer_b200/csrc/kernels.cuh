@@ -147,6 +147,8 @@ struct BeamState {
     float* logp_cur; float* logp_next;    // [B*K]
     const int* drafts;                    // [B][N][dl0]
     int* c_slot0; int* c_fin; int* c_rowbase; int* c_nacc; int* c_pick; int* acc_stat; int* ctrl;
+    int* host_ctrl;   // pinned host mirror of ctrl (device-accessible): BC_COUNT words + a sequence word written last
+    int host_seq;     // value of the sequence word for this iteration
     int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows
     float* topv; int* topi; int* nkeep; float* lmax; float* lsum;      // per (row, position) statistics
     int* trace_nacc; int* trace_pick;     // optional [iter][B*K][N] / [iter][B*K]

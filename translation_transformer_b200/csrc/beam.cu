@@ -188,7 +188,8 @@ __global__ void beam_cache_update_kernel(BeamState st, int dl, const ActT* __res
     const uint4* vs4 = reinterpret_cast<const uint4*>(vs);
     uint4* kd4 = reinterpret_cast<uint4*>(kd);
     uint4* vd4 = reinterpret_cast<uint4*>(vd);
-    for (long long i = threadIdx.x; i < nvec; i += blockDim.x) { kd4[i] = ks4[i]; vd4[i] = vs4[i]; }
+    for (long long i = (long long)blockIdx.z * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.z * blockDim.x) { kd4[i] = ks4[i]; vd4[i] = vs4[i]; }
+    if (blockIdx.z != 0) return;
     // positions f .. f + keep from the chosen draft row of this iteration
     const ActT* src = qkv_all + (long long)l * qkv_layer_stride + (long long)r * (dl + 1) * qkv_ld;
     for (int idx = threadIdx.x; idx < (keep + 1) * E; idx += blockDim.x) {
@@ -201,7 +202,7 @@ template <typename ActT>
 void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld,
                               int E, const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
                               long long cache_cand_stride, cudaStream_t s) {
-    dim3 grid(st.B * st.K, n_layers);
+    dim3 grid(st.B * st.K, n_layers, 4);   // z: four slices of the parent's prefix
     launch_pdl(beam_cache_update_kernel<ActT>, dim3(grid), dim3(256), 0, s, st, dl, qkv_all, qkv_layer_stride, qkv_ld, E, kc_cur, vc_cur, kc_next, vc_next,
                                                         cache_layer_stride, cache_cand_stride);
 }
@@ -333,40 +334,48 @@ void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, i
 }
 
 // ---- accepted lengths + best draft per candidate ------------------------------------------------------------
-__global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, int beam, int dl, int iter) {
+// One CTA per candidate.  "Is draft token a of draft n inside the truncated support of its position?" is evaluated for all
+// (draft, position) pairs in parallel (two dependent global loads each instead of a chain of up to 2 dl per draft); the
+// accepted length of a draft is the length of its leading run of hits.
+__global__ void __launch_bounds__(256) beam_choose_kernel(BeamState st, int C, int beam, int dl, int iter, int par) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
-    const int c = blockIdx.x, lane = threadIdx.x;
+    const int c = blockIdx.x;
     __shared__ int s_nacc[64];
+    extern __shared__ unsigned char s_hit[];                 // [m][dl] when par
     if (c >= C) return;
     const int q = c / beam, N = st.N, K = st.K;
     const bool fin = st.c_fin[c] != 0;
     const int m = cand_n_drafts(st, c);                      // drafts of this candidate
     const int lmax = st.smart ? st.ctrl[BC_LMAX] : N;        // ragged groups are padded with -1 up to the longest (:206-223)
-    for (int n = lane; n < N; n += 32) {
+    const int rb = st.c_rowbase[c];
+    auto hit = [&](int n, int a) -> bool {
+        const long long rp = (long long)(rb + n) * (dl + 1) + a;
+        const int keep = st.nkeep[rp];
+        const int* ti = st.topi + rp * K;
+        const int tok = cand_draft(st, c, q, n)[a];
+        bool in = false;
+        for (int j = 0; j < keep; ++j) in |= (ti[j] == tok);
+        return in;
+    };
+    if (par && !fin) {
+        for (int idx = threadIdx.x; idx < m * dl; idx += blockDim.x) s_hit[idx] = hit(idx / dl, idx % dl) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
         int a = -1;
         if (n < m) {
             a = 0;
             if (!fin) {
-                const int r = st.c_rowbase[c] + n;
-                const int* dr = cand_draft(st, c, q, n);
-                while (a < dl) {
-                    const long long rp = (long long)r * (dl + 1) + a;
-                    const int keep = st.nkeep[rp];
-                    const int* ti = st.topi + rp * K;
-                    const int tok = dr[a];
-                    bool in = false;
-                    for (int j = 0; j < keep; ++j) in |= (ti[j] == tok);
-                    if (!in) break;
-                    ++a;
-                }
+                if (par) { while (a < dl && s_hit[n * dl + a]) ++a; }
+                else { while (a < dl && hit(n, a)) ++a; }
             }
         }
         st.c_nacc[(long long)c * N + n] = a;
         if (n < 64) s_nacc[n] = a;
         if (st.trace_nacc) st.trace_nacc[((long long)iter * st.B * K + c) * N + n] = a;
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
         int pick = 0;
         if (st.tie_break == 0 && lmax < 64) {
             pick = topk1_torch_cpu(s_nacc, lmax);
@@ -378,7 +387,9 @@ __global__ void __launch_bounds__(32) beam_choose_kernel(BeamState st, int C, in
     }
 }
 void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s) {
-    launch_pdl(beam_choose_kernel, dim3(C), dim3(32), 0, s, st, C, beam, dl, iter);
+    const size_t smem = (size_t)st.N * (dl > 0 ? dl : 1);
+    const int par = smem <= 40 * 1024 ? 1 : 0;
+    launch_pdl(beam_choose_kernel, dim3(C), dim3(256), par ? smem : 0, s, st, C, beam, dl, iter, par);
 }
 
 // ---- leaves of the continuation trees, n_best best per query ------------------------------------------------------
@@ -396,18 +407,27 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
     const int per_c = (dl + 1) * K, total = beam * per_c;
     float* s_pre = s_score + total;                    // [beam][dl+2] running log-prob of the accepted path
     if (threadIdx.x == 0) s_valid = 0;
-    // accepted-path prefix sums (sequential fp32 adds, same association as the reference's cumsum)
-    for (int cb = threadIdx.x; cb < beam; cb += blockDim.x) {
+    // accepted-path prefix sums (sequential fp32 adds, same association as the reference's cumsum): one warp per
+    // candidate, the terms are fetched by the lanes in parallel and added in order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int cb = warp; cb < beam; cb += n_warps) {
         const int c = q * beam + cb;
         float run = 0.f;
-        s_pre[cb * (dl + 2)] = 0.f;
+        if (lane == 0) s_pre[cb * (dl + 2)] = 0.f;
         if (!st.c_fin[c]) {
             const int n = st.c_pick[c], a = st.c_nacc[(long long)c * N + n], r = st.c_rowbase[c] + n;
             const int* dr = cand_draft(st, c, q, n);
-            for (int i = 0; i < a; ++i) {
-                const long long rp = (long long)r * (dl + 1) + i;
-                run += ref_logprob(logits[rp * V + dr[i]], st.lmax[rp], st.lsum[rp]);
-                s_pre[cb * (dl + 2) + i + 1] = run;
+            for (int i0 = 0; i0 < a; i0 += 32) {
+                float term = 0.f;
+                if (i0 + lane < a) {
+                    const long long rp = (long long)r * (dl + 1) + i0 + lane;
+                    term = ref_logprob(logits[rp * V + dr[i0 + lane]], st.lmax[rp], st.lsum[rp]);
+                }
+                const int cnt = min(32, a - i0);
+                for (int i = 0; i < cnt; ++i) {
+                    run += __shfl_sync(0xffffffffu, term, i);
+                    if (lane == 0) s_pre[cb * (dl + 2) + i0 + i + 1] = run;
+                }
             }
         }
     }
@@ -451,30 +471,33 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             const float sc = s_score[L];
             if (sc > bv || (sc == bv && sc != -INFINITY && L < bi)) { bv = sc; bi = L; }
         }
-        s_red_v[threadIdx.x] = bv;
-        s_red_i[threadIdx.x] = bi;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) {
-                const float ov = s_red_v[threadIdx.x + o];
-                const int oi = s_red_i[threadIdx.x + o];
-                if (ov > s_red_v[threadIdx.x] || (ov == s_red_v[threadIdx.x] && oi < s_red_i[threadIdx.x])) {
-                    s_red_v[threadIdx.x] = ov;
-                    s_red_i[threadIdx.x] = oi;
-                }
-            }
-            __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (threadIdx.x == 0) {
-            const int L = s_red_i[0];
-            s_sel[k] = L;
-            st.logp_next[q * K + k] = s_red_v[0];
-            s_score[L] = -INFINITY;
+        if (lane == 0) { s_red_v[warp] = bv; s_red_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = lane < n_warps ? s_red_v[lane] : -INFINITY;
+            bi = lane < n_warps ? s_red_i[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                s_sel[k] = bi;
+                st.logp_next[q * K + k] = bv;
+                s_score[bi] = -INFINITY;
+            }
         }
         __syncthreads();
     }
-    // materialise the K new candidates
-    for (int k = 0; k < K; ++k) {
+    // materialise the K new candidates: one warp per candidate
+    for (int k = warp; k < K; k += n_warps) {
         const int L = s_sel[k];
         const int cb = L / per_c, p = (L % per_c) / K, j = L % K;
         const int c = q * beam + cb;
@@ -486,7 +509,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         if (!fin) { n = st.c_pick[c]; r = st.c_rowbase[c] + n; }
         const int* dr = fin ? st.drafts : cand_draft(st, c, q, n);
         const int tok = fin ? st.pad : st.topi[((long long)r * (dl + 1) + p) * K + j];
-        for (int col = threadIdx.x; col < W; col += blockDim.x) {
+        for (int col = lane; col < W; col += 32) {
             int t = src[col];
             if (col >= slot0 && col <= slot0 + dl) {
                 const int o = col - slot0;
@@ -494,7 +517,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             }
             dst[col] = t;
         }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             st.acc_stat[q * K + k] = fin ? -1 : p;
             st.n_parent[q * K + k] = fin ? -1 : c;
             st.n_keep[q * K + k] = p;

@@ -530,3 +530,16 @@ def test_standard_beam_search_bf16_runs_and_is_consistent(dev):
             same += int(np.array_equal(out[b, 0, :w], ref[b, 0, :w]) and out.shape[2] == ref.shape[2])
             total += 1
     assert same >= 0.7 * total, (same, total)
+
+
+def test_ffn_pair_kernel_matches_cta_group1_kernel(dev):
+    """The CTA-pair feed-forward kernel (cta_group::2, clusters of four, chained out-projection, A operand in tensor
+    memory) and the cta_group::1 kernel + separate out-projection kernel give bit-identical logits: golden inputs, a
+    ragged batch, and a batch with more 256-row blocks than co-resident clusters (each mode in its own process)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    script = Path(__file__).resolve().parent.parent / "scripts" / "ffn_pair_check.py"
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "WORST 0.0" in r.stdout

@@ -2270,7 +2270,10 @@ bool ffn_pair_available(int max_rows) {
     if (pair_env == 0) return false;
     const int clusters = ffn_pair_clusters();
     if (clusters <= 0) return false;
-    return pair_env == 1 || (max_rows + 2 * tc::BM - 1) / (2 * tc::BM) <= clusters;
+    // also with more 256-row blocks than co-resident clusters (several waves): measured 1.3 % faster than the
+    // cta_group::1 kernel + separate out-projection on the retrosynthesis beam search (80 blocks, 33 clusters)
+    (void)max_rows;
+    return true;
 }
 
 int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bias1, const __nv_bfloat16* W2, const float* bias2,

@@ -56,6 +56,14 @@ def main():
     print(f"{'kernel':62s} {'n':>6s} {'avg us':>8s} {'gap us':>8s} {'sum ms':>8s}")
     for k, (n, d, g) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:62s} {n:6d} {d / n:8.2f} {g / n:8.2f} {d / 1000:8.2f}")
+    # idle time: intervals in which no kernel (or copy) is running
+    idle, cover_end, idle_by_next = 0.0, ev[0][1], defaultdict(float)
+    for st_, en_, n_ in ev[1:]:
+        if st_ > cover_end:
+            idle += st_ - cover_end
+            idle_by_next[n_.split("(")[0][-40:]] += st_ - cover_end
+        cover_end = max(cover_end, en_)
+    print(f"idle {idle / 1000:.2f} ms of {total / 1000:.2f} ms; before: " + ", ".join(f"{k} {v / 1000:.2f}" for k, v in sorted(idle_by_next.items(), key=lambda kv: -kv[1])[:6]))
     mid = len(ev) // 2
     out = Path("gpurun_out") / "timeline_events.txt"
     with open(out, "w") as f:

@@ -12,7 +12,7 @@
 //   beam_choose   -> accepted length of every draft, best draft per candidate (torch-CPU topk(1) order)
 //   beam_expand   -> per query: scores of all leaves of the continuation trees of its candidates, the
 //                    n_best best become the next candidates
-//   beam_control  -> all-finished flag, number of trailing empty columns, acceptance statistics
+//   (loop control: all-finished flag, trailing empty columns, acceptance statistics -> the last CTA of beam_expand)
 #include "kernels.cuh"
 #include "topk_emul.cuh"
 
@@ -392,7 +392,9 @@ void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, 
     launch_pdl(beam_choose_kernel, dim3(C), dim3(256), par ? smem : 0, s, st, C, beam, dl, iter, par);
 }
 
-// ---- leaves of the continuation trees, n_best best per query ------------------------------------------------------
+// ---- leaves of the continuation trees, n_best best per query, loop control ---------------------------------------
+// Accumulators of the loop control behind the BC_COUNT control words (reset by the CTA that finalises an iteration)
+constexpr int BCX_ALL_FIN = BC_COUNT, BCX_MIN_PAD = BC_COUNT + 1, BCX_ACC = BC_COUNT + 2, BCX_CNT = BC_COUNT + 3, BCX_TICKET = BC_COUNT + 4;
 // log softmax exactly as the reference evaluates it: log(exp(x - max) / sum)   (:378)
 __device__ __forceinline__ float ref_logprob(float logit, float mx, float sum) { return logf(expf(logit - mx) / sum); }
 
@@ -460,11 +462,9 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
     }
     if (my_valid) atomicAdd(&s_valid, my_valid);
     __syncthreads();
-    if (s_valid < K) {
-        if (threadIdx.x == 0) atomicExch(&st.ctrl[BC_ERROR], 4);   // reference: assert min(group length) >= k (:195)
-        return;
-    }
-    for (int k = 0; k < K; ++k) {                      // K rounds of block-wide argmax (ties: lower leaf index)
+    const bool ok = s_valid >= K;
+    if (!ok && threadIdx.x == 0) atomicExch(&st.ctrl[BC_ERROR], 4);   // reference: assert min(group length) >= k (:195)
+    for (int k = 0; ok && k < K; ++k) {                // K rounds of block-wide argmax (ties: lower leaf index)
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         for (int L = threadIdx.x; L < total; L += blockDim.x) {
@@ -496,8 +496,9 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         }
         __syncthreads();
     }
-    // materialise the K new candidates: one warp per candidate
-    for (int k = warp; k < K; k += n_warps) {
+    // materialise the K new candidates: one warp per candidate; the loop control's view of the new rows (PAD columns,
+    // EOS anywhere, accepted draft tokens) is accumulated on the way
+    for (int k = warp; ok && k < K; k += n_warps) {
         const int L = s_sel[k];
         const int cb = L / per_c, p = (L % per_c) / K, j = L % K;
         const int c = q * beam + cb;
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         if (!fin) { n = st.c_pick[c]; r = st.c_rowbase[c] + n; }
         const int* dr = fin ? st.drafts : cand_draft(st, c, q, n);
         const int tok = fin ? st.pad : st.topi[((long long)r * (dl + 1) + p) * K + j];
+        int pads = 0, has_eos = 0;
         for (int col = lane; col < W; col += 32) {
             int t = src[col];
             if (col >= slot0 && col <= slot0 + dl) {
@@ -516,12 +518,47 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                 t = o < p ? dr[o] : (o == p ? tok : st.pad);
             }
             dst[col] = t;
+            pads += t == st.pad;
+            has_eos |= t == st.eos;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pads += __shfl_xor_sync(0xffffffffu, pads, o);
+            has_eos |= __shfl_xor_sync(0xffffffffu, has_eos, o);
         }
         if (lane == 0) {
             st.acc_stat[q * K + k] = fin ? -1 : p;
             st.n_parent[q * K + k] = fin ? -1 : c;
             st.n_keep[q * K + k] = p;
             st.n_row[q * K + k] = r;
+            if (!has_eos) atomicAnd(&st.ctrl[BCX_ALL_FIN], 0);
+            atomicMin(&st.ctrl[BCX_MIN_PAD], pads);
+            if (!fin) { atomicAdd(&st.ctrl[BCX_ACC], p); atomicAdd(&st.ctrl[BCX_CNT], 1); }
+        }
+    }
+    // ---- loop control: the CTA that arrives last publishes the control words of the iteration (also into the pinned
+    // host mirror, sequence number last) and resets the accumulators
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st.ctrl[BCX_TICKET], 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int acc = atomicAdd(&st.ctrl[BCX_ACC], 0), cnt = atomicAdd(&st.ctrl[BCX_CNT], 0);
+            st.ctrl[BC_ALL_FINISHED] = atomicAdd(&st.ctrl[BCX_ALL_FIN], 0);
+            st.ctrl[BC_EMPTY_COLS] = atomicAdd(&st.ctrl[BCX_MIN_PAD], 0);
+            st.ctrl[BC_ACCEPTED] += acc;
+            st.ctrl[BC_PRODUCED] += acc + cnt;
+            st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
+            if (st.host_ctrl) {
+                // what the host needs per iteration, packed into ONE 64-bit word of its own (pinned, mapped) memory:
+                // sequence number | error | all finished | empty columns.  One posted store: no copy engine, no stream
+                // synchronisation, no system-scope fence between this kernel and the cache update that follows it.
+                const unsigned long long word = ((unsigned long long)(unsigned)st.host_seq << 32) |
+                                                ((unsigned long long)(atomicAdd(&st.ctrl[BC_ERROR], 0) & 0xff) << 24) |
+                                                ((unsigned long long)(st.ctrl[BC_ALL_FINISHED] & 0xff) << 16) |
+                                                (unsigned long long)(st.ctrl[BC_EMPTY_COLS] & 0xffff);
+                *reinterpret_cast<volatile unsigned long long*>(st.host_ctrl) = word;
+            }
         }
     }
 }
@@ -535,48 +572,6 @@ void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const floa
     launch_pdl(beam_expand_kernel, dim3(st.B), dim3(256), smem, s, st, beam, W, dl, logits);
 }
 
-// ---- loop control ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) beam_control_kernel(BeamState st, int W) {
-    pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
-    __shared__ int s_all_fin, s_min_pad, s_acc, s_cnt;
-    if (threadIdx.x == 0) { s_all_fin = 1; s_min_pad = 0x7fffffff; s_acc = 0; s_cnt = 0; }
-    __syncthreads();
-    const int R = st.B * st.K;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    for (int r = warp; r < R; r += n_warps) {   // one warp per new hypothesis, coalesced scan
-        const int* row = st.cand_next + (long long)r * st.ldw;
-        int pads = 0, fin = 0;
-        for (int j = lane; j < W; j += 32) { const int t = row[j]; pads += t == st.pad; fin |= t == st.eos; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            pads += __shfl_xor_sync(0xffffffffu, pads, o);
-            fin |= __shfl_xor_sync(0xffffffffu, fin, o);
-        }
-        if (lane == 0) {
-            if (!fin) atomicAnd(&s_all_fin, 0);
-            atomicMin(&s_min_pad, pads);
-            const int a = st.acc_stat[r];
-            if (a >= 0) { atomicAdd(&s_acc, a); atomicAdd(&s_cnt, 1); }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st.ctrl[BC_ALL_FINISHED] = s_all_fin;
-        st.ctrl[BC_EMPTY_COLS] = s_min_pad;
-        st.ctrl[BC_ACCEPTED] += s_acc;
-        st.ctrl[BC_PRODUCED] += s_acc + s_cnt;
-        if (st.host_ctrl) {
-            // the host reads the control words straight from its own (pinned, mapped) memory: no copy engine, no stream
-            // synchronisation between this kernel and the cache update that follows it
-            volatile int* h = st.host_ctrl;
-            for (int i = 0; i < BC_COUNT; ++i) h[i] = st.ctrl[i];
-            __threadfence_system();
-            h[BC_COUNT] = st.host_seq;
-        }
-    }
-}
-void launch_beam_control(const BeamState& st, int W, cudaStream_t s) { launch_pdl(beam_control_kernel, dim3(1), dim3(256), 0, s, st, W); }
-
 __global__ void beam_init_kernel(BeamState st) {
     const long long n = (long long)st.B * st.K * st.ldw;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -586,6 +581,7 @@ __global__ void beam_init_kernel(BeamState st) {
     if (blockIdx.x == 0) {
         for (int b = threadIdx.x; b < st.B * st.K; b += blockDim.x) { st.logp_cur[b] = 0.f; st.logp_next[b] = 0.f; }
         if (threadIdx.x < BC_COUNT) st.ctrl[threadIdx.x] = 0;
+        if (threadIdx.x == 0) { st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0; }
     }
 }
 void launch_beam_init(const BeamState& st, cudaStream_t s) { beam_init_kernel<<<64, 256, 0, s>>>(st); }

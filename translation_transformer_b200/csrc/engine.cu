@@ -789,7 +789,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t o_cand0 = take((size_t)Cmax * ldw * 4), o_cand1 = take((size_t)Cmax * ldw * 4);
     const size_t o_lp0 = take(Cmax * 4), o_lp1 = take(Cmax * 4);
     const size_t o_slot = take(Cmax * 4), o_fin = take(Cmax * 4), o_base = take(Cmax * 4), o_nacc = take((size_t)Cmax * N * 4);
-    const size_t o_pick = take(Cmax * 4), o_acc = take(Cmax * 4), o_ctrl = take(BC_COUNT * 4);
+    const size_t o_pick = take(Cmax * 4), o_acc = take(Cmax * 4), o_ctrl = take(16 * 4);   // control words + loop-control accumulators
     const size_t o_rows = take((size_t)Rmax * ldw * 4), o_rc = take(Rmax * 4), o_rq = take(Rmax * 4), o_rs = take(Rmax * 4);
     const size_t n_rp = (size_t)Rmax * (D0 + 1);
     const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
@@ -824,8 +824,8 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
     {
         void* dp = nullptr;
-        e->h_ctrl[BC_COUNT] = 0;
-        st.host_ctrl = cudaHostGetDevicePointer(&dp, e->h_ctrl, 0) == cudaSuccess ? static_cast<int*>(dp) : nullptr;
+        e->h_ctrl[16] = e->h_ctrl[17] = 0;
+        st.host_ctrl = cudaHostGetDevicePointer(&dp, e->h_ctrl + 16, 0) == cudaSuccess ? static_cast<int*>(dp) : nullptr;
         (void)cudaGetLastError();
     }
     st.live_cand = (int*)(base + o_lc); st.live_query = (int*)(base + o_lq); st.c_front = (int*)(base + o_cf);
@@ -848,6 +848,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const int* n_live = st.ctrl + BC_NLIVE_ROWS;
     int W = 1, empty_cols = 0, filled = 1, budget = max_len - filled - 1, dl = smart ? D_lib - 1 : D0, C = B, beam = 1, iters = 0;
     int* hc = e->h_ctrl;
+    hc[BC_ERROR] = 0;
     while (budget >= 1 && filled <= max_len) {
         dl = std::min(budget, dl);
         const int grow = dl + 1 - empty_cols;
@@ -893,11 +894,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         }
         { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, iters, s); }
-        { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
-        // the control kernel writes the control words and, last, the iteration's sequence number into pinned host memory:
-        // the host reads them while the caches are still being re-parented and enqueues the next iteration behind that
+        // the expand kernel also closes the iteration: its last CTA writes the control words and, last, the iteration's
+        // sequence number into pinned host memory; the host reads them while the caches are still being re-parented and
+        // enqueues the next iteration behind that
         st.host_seq = iters + 1;
-        { Scope sc(e, KC_ACCEPT, s); launch_beam_control(st, W, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
         if (cached) {
             Scope sc(e, KC_CACHE_APPEND, s);
             launch_beam_cache_update<ActT>(st, dl, e->qkv.as<ActT>(), Tc * 3 * E, n_dec, 3 * E, E, kc_cur, vc_cur, kc_next, vc_next,
@@ -905,22 +906,31 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             std::swap(kc_cur, kc_next);
             std::swap(vc_cur, vc_next);
         }
-        {
-            volatile int* flag = hc + BC_COUNT;
+        {   // spin on the packed word the expand kernel posts (sequence | error | all finished | empty columns)
+            volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(hc + 16);
+            unsigned long long w = 0;
             bool seen = false;
             for (long spin = 0; !seen; ++spin) {
-                seen = *flag == iters + 1;
+                w = *word;
+                seen = (unsigned)(w >> 32) == (unsigned)(iters + 1);
                 if (!seen && (spin & 0x3FFF) == 0x3FFF) {
                     const cudaError_t q = cudaStreamQuery(s);
-                    if (q == cudaSuccess) {   // stream drained: the words are there (or the launch was lost: take a copy)
-                        if (*flag != iters + 1) TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
+                    if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy
+                        w = *word;
+                        if ((unsigned)(w >> 32) != (unsigned)(iters + 1)) {
+                            TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
+                            w = ((unsigned long long)(unsigned)(iters + 1) << 32) | ((unsigned long long)(hc[BC_ERROR] & 0xff) << 24) |
+                                ((unsigned long long)(hc[BC_ALL_FINISHED] & 0xff) << 16) | (unsigned long long)(hc[BC_EMPTY_COLS] & 0xffff);
+                        }
                         seen = true;
                     } else if (q != cudaErrorNotReady) {
                         TTB_CUDA_OK(q);
                     }
                 }
             }
-            std::atomic_thread_fence(std::memory_order_acquire);
+            hc[BC_ERROR] = (int)((w >> 24) & 0xff);
+            hc[BC_ALL_FINISHED] = (int)((w >> 16) & 0xff);
+            hc[BC_EMPTY_COLS] = (int)(w & 0xffff);
         }
         ++iters;
         if (hc[BC_ERROR]) break;
@@ -948,9 +958,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->t0, e->t1);
     if (stats) {
+        int fin_ctrl[BC_COUNT] = {};
+        if (iters > 0) TTB_CUDA_OK(cudaMemcpy(fin_ctrl, st.ctrl, sizeof(fin_ctrl), cudaMemcpyDeviceToHost));
         stats->model_calls = iters;
-        stats->accepted_tokens = hc[BC_ACCEPTED];
-        stats->produced_tokens = hc[BC_PRODUCED];
+        stats->accepted_tokens = fin_ctrl[BC_ACCEPTED];
+        stats->produced_tokens = fin_ctrl[BC_PRODUCED];
         stats->unfinished = 0;
         stats->error = err;
         stats->gpu_launches = (int32_t)(e->launches - launches0);

@@ -182,7 +182,6 @@ void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, 
 void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s);
 void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s);
 void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s);
-void launch_beam_control(const BeamState& st, int W, cudaStream_t s);
 void launch_beam_export(const int* cand, int ldw, int R, int W, long long* out, cudaStream_t s);
 // ---- std_beam.cu : standard beam search (standard_decoding.py:90-174) -------------------------------------------
 struct StdBeamState {

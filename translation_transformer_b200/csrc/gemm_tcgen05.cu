@@ -606,6 +606,14 @@ __device__ __forceinline__ void ln_store_tiles(const float (&v)[64], uint8_t* f3
     }
 }
 
+#ifdef TTB_LNK_TIMELINE
+// Debug build only: clock64 stamps of thread 64 of CTA 0
+__device__ long long g_lnk_ts[16];
+#define LNK_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_lnk_ts[i] = clock64(); } while (0)
+#else
+#define LNK_TS(i) do { } while (0)
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(lnk::THREADS, 1)
 gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXh,
@@ -641,6 +649,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = K / BK;
+    LNK_TS(0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -684,7 +693,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // everything above is independent of earlier kernels (weights only); from here on their results are needed
     pdl_launch_dependents();
     const int live_rows = rows.live();   // written before this programmatic chain started (see gemm_pair_k256_kernel): fetched ahead of the wait
+    LNK_TS(1);
     pdl_wait();
+    LNK_TS(2);
     const bool live = m0 < live_rows;    // uniform per cluster: dead tiles only take part in the barriers
 
     if (warp == 0) {
@@ -740,7 +751,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (epi) {
         mbar_wait(tfull_bar, 0);
         tcgen05_fence_after();
+        LNK_TS(3);
         mbar_wait(resid_bar, 0);
+        LNK_TS(4);
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t r[32];
@@ -759,6 +772,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         float mean, m2;
         ln_local_stats(v, mean, m2);
+        LNK_TS(5);
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // phase 0: the peer is running
         ln_publish(part1, pidx, row, rank, mean, m2);
         // chained GEMM: expect the peer's half of the normalised tile (it is sent after the barrier below)
@@ -768,7 +782,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     __syncwarp();
+    LNK_TS(6);
     cluster_sync_all();
+    LNK_TS(7);
     if (epi) ln_normalise(v, part1, row, prm + BNL + h * 64, prm + 2 * BNL + h * 64);
     if (g2) {   // final LayerNorm of the stack on top (uniform branch)
         if (epi) {
@@ -800,15 +816,15 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // fp32 tile back into the residual boxes (in place), bf16 tile into the idle ring: K-block slots 2*rank + h of
         // the 128 x 256 tile that the chained GEMM reads as its A operand (slots 0, 1 without a chained GEMM)
         const int slot0 = chain ? 2 * (int)rank : 0;
+        LNK_TS(8);
         ln_store_tiles(v, resid_sm + 2 * h * (BM * 128), gen_base + (slot0 + h) * (BM * 128), row);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        LNK_TS(9);
         if (threadIdx.x == 64) {
-            for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, resid_u32 + bx * (BM * 128), n0 + 32 * bx, m0);
-            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + (slot0 + hb) * (BM * 128), n0 + 64 * hb, m0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (chain) {
-                // this CTA's two K-blocks to the same slots of the peer (one 32 KB bulk copy through DSMEM)
+                // first (it gates the chained GEMM of the peer): this CTA's two K-blocks to the same slots of the peer, one
+                // 32 KB bulk copy through DSMEM
                 uint32_t r_dst, r_bar;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_dst) : "r"(base + slot0 * 16384), "r"(rank ^ 1u));
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar) : "r"(a2_peer_bar), "r"(rank ^ 1u));
@@ -816,14 +832,18 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                              "r"(base + slot0 * 16384), "r"(2 * 16384), "r"(r_bar)
                              : "memory");
                 mbar_arrive(a2_own_bar);
-            } else {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
+            for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, resid_u32 + bx * (BM * 128), n0 + 32 * bx, m0);
+            for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + (slot0 + hb) * (BM * 128), n0 + 64 * hb, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (!chain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         if (chain) {
             // epilogue of the chained GEMM: + bias, bf16, staged in ring stage 2 (the weight slice is consumed), TMA store
+            LNK_TS(10);
             mbar_wait(acc2_bar, 0);
             tcgen05_fence_after();
+            LNK_TS(11);
             uint32_t pk[32];
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -847,13 +867,16 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
                 for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmQ, base + 2 * STAGE + hb * 16384, n0 + 64 * hb, m0);
+                LNK_TS(12);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                LNK_TS(13);
             }
         }
     }
     // the peer reads this CTA's shared memory (bulk copy above) until its own chained GEMM has started
     if (chain) { __syncwarp(); cluster_sync_all(); }
+    LNK_TS(14);
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -2381,6 +2404,18 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
         attr_set = true;
     }
     const int tiles = (rows.max_rows + BM - 1) / BM;
+#ifdef TTB_LNK_TIMELINE
+    {
+        static int n_launch = 0;
+        if (++n_launch == 400) {
+            cudaStreamSynchronize(s);
+            long long h[16];
+            cudaMemcpyFromSymbol(h, g_lnk_ts, sizeof(h));
+            FILE* f = fopen("gpurun_out/lnk_timeline.txt", "w");
+            if (f) { for (int i = 0; i < 15; ++i) fprintf(f, "%d %lld\n", i, h[i] ? h[i] - h[2] : -1); fclose(f); }
+        }
+    }
+#endif
     launch_pdl(gemm_resid_ln_kernel, dim3(2 * tiles), dim3(lnk::THREADS), (size_t)lnk::SMEM, s, tmA, tmB, tmX, tmXh, bias, g1, b1, g2, b2, rows, K,
                tmW2, tmQ, bias2, chain);
     return 0;

@@ -659,7 +659,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }   // full: A and W arrive separately
             mbar_init(tfull_bar, 1);
             mbar_init(resid_bar, 1);
             mbar_init(w2_bar, 1);
@@ -667,6 +667,14 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(a2_own_bar, 1);
             mbar_init(acc2_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // The weights do not depend on earlier kernels: the W K-blocks of the first ring fill are requested right here,
+            // at the very top of the CTA (before the tensor-memory allocation, the parameter loads and the dependency
+            // wait), so they are in flight during the whole prologue of every CTA, also of those that only get their SM
+            // when a CTA of the preceding kernel exits.
+            for (int kb = 0; kb < (KB < NST ? KB : NST); ++kb) {
+                mbar_expect_tx(full_bar(kb), BNL * BK * 2);
+                tma_load_2d(base + kb * STAGE + A_BYTES, &tmB, kb * BK, n0, full_bar(kb));
+            }
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(2 * BNL)) : "memory");
@@ -698,16 +706,23 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     LNK_TS(2);
     const bool live = m0 < live_rows;    // uniform per cluster: dead tiles only take part in the barriers
 
+    const int n_pre = KB < NST ? KB : NST;   // W K-blocks requested in the prologue
     if (warp == 0) {
+        if (lane == 0 && !live) {   // requested weights must land before the CTA may exit
+            for (int kb = 0; kb < n_pre; ++kb) { mbar_arrive(full_bar(kb)); mbar_wait(full_bar(kb), 0); }
+        }
         if (lane == 0 && live) {  // ===== TMA producer =====
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % NST;
                 const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), STAGE);
                 const uint32_t a_dst = base + s * STAGE, b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(full_bar(s), A_BYTES);
                 tma_load_2d(a_dst, &tmA, kb * BK, m0, full_bar(s));
-                tma_load_2d(b_dst, &tmB, kb * BK, n0, full_bar(s));
+                if (kb >= n_pre) {
+                    mbar_expect_tx(full_bar(s), BNL * BK * 2);
+                    tma_load_2d(b_dst, &tmB, kb * BK, n0, full_bar(s));
+                }
                 if (kb == (KB < NST ? KB : NST) - 1) {   // residual tile: queued behind the first ring fill
                     mbar_expect_tx(resid_bar, RESID_BYTES);
                     for (int bx = 0; bx < 4; ++bx) tma_load_2d(resid_u32 + bx * (BM * 128), &tmX, n0 + 32 * bx, m0, resid_bar);

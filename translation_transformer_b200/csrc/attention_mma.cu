@@ -205,7 +205,13 @@ attn_mma_kernel(Params p) {
     // may run ahead of the programmatic dependency, i.e. the key staging overlaps the tail of the preceding GEMM.
     const bool early = p.desc != nullptr;
     if (!early) pdl_wait();
-    if (p.n_groups_dev && g >= *p.n_groups_dev) return;
+    // the three scalar fetches every CTA starts with are issued together (behind the early-exit test the compiler could
+    // not hoist them: two dependent global round trips)
+    int4 dsc = make_int4(0, 0, 0, 0x7fffffff);
+    if (p.desc) dsc = p.desc[g];
+    const int dynLk = p.lk_dev ? *p.lk_dev : 0;
+    const int n_groups_live = p.n_groups_dev ? *p.n_groups_dev : 0x7fffffff;
+    if (g >= n_groups_live) return;
     extern __shared__ __align__(16) uint8_t attn_smem[];
     constexpr int PITCH = Tile<HD>::PITCH;
     Tile<HD> tileA, tileB;
@@ -216,10 +222,7 @@ attn_mma_kernel(Params p) {
     tileA.bias = reinterpret_cast<float*>(tileB.v + KTB * PITCH);
     tileB.bias = tileA.bias + KTA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int4 dsc = make_int4(0, 0, 0, 0x7fffffff);
-    if (p.desc) dsc = p.desc[g];
     const int kvg = p.desc ? dsc.x : (p.spec ? p.active[g] : (p.kvmap ? p.kvmap[g] : g));
-    const int dynLk = p.lk_dev ? *p.lk_dev : 0;
     const int Lk_all = p.spec ? (p.desc ? dsc.y : p.front[kvg]) : (p.lk_dev ? dynLk : p.Lk);
     const int Lk = p.spec ? Lk_all : (p.desc ? min(Lk_all, dsc.w) : (p.lk_group ? min(Lk_all, p.lk_group[kvg]) : Lk_all));
     const long long kv_group_stride = p.lk_dev ? dynLk : p.kv_group_stride;

@@ -98,13 +98,16 @@ __global__ void greedy_advance_kernel(GreedyState st, const float* __restrict__ 
     // control words and descriptor table of the accept kernel ahead of their dependency waits, so none of them may be
     // scheduled before this kernel has seen the accept kernel complete.
     pdl_wait();
-    if (st.ctrl[CTRL_DONE]) return;   // after DONE neither the cache nor the embeddings are read again
+    // the control words and the per-slot records are fetched together, ahead of the tests that use them (as dependent
+    // loads they would be three to five global round trips in a row); the slot indices are in range for every CTA
+    const int done = st.ctrl[CTRL_DONE], n_sel = st.ctrl[CTRL_N_SEL], n_active = st.ctrl[CTRL_N_ACTIVE];
     if ((int)blockIdx.x >= n_embed_blocks) {
         // K/V of the accepted positions of the chosen draft (recorded in st.sel by the accept kernel) -> cache
         const int idx = blockIdx.x - n_embed_blocks;
         const int g = idx / n_layers, l = idx % n_layers;
-        if (g >= st.ctrl[CTRL_N_SEL]) return;
-        const int b = st.sel[g * 4 + 0], f = st.sel[g * 4 + 1], pick = st.sel[g * 4 + 2], a = st.sel[g * 4 + 3];
+        const int4 sel = *reinterpret_cast<const int4*>(st.sel + g * 4);
+        if (done || g >= n_sel) return;   // after DONE neither the cache nor the embeddings are read again
+        const int b = sel.x, f = sel.y, pick = sel.z, a = sel.w;
         const ActT* src = qkv_all + (long long)l * qkv_layer_stride + ((long long)g * st.N + pick) * (st.D + 1) * qkv_ld;
         ActT* kd = kcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
         ActT* vd = vcache + (long long)l * cache_layer_stride + (long long)b * cache_query_stride + (long long)f * cache_ld;
@@ -118,9 +121,9 @@ __global__ void greedy_advance_kernel(GreedyState st, const float* __restrict__ 
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int per_q = st.N * (st.D + 1);
-    if (t >= st.ctrl[CTRL_N_ACTIVE] * per_q) return;
-    const int g = t / per_q, r = t % per_q, n = r / (st.D + 1), i = r % (st.D + 1);
+    const int g = min(t / per_q, st.B - 1), r = t % per_q, n = r / (st.D + 1), i = r % (st.D + 1);
     const int4 d = st.desc[g];
+    if (done || t >= n_active * per_q) return;
     const int b = d.x, f = d.y;
     const int tok = (i == 0) ? d.z : st.drafts[((long long)b * st.N + n) * st.D + i - 1];
     const float* e = table + (long long)tok * E;

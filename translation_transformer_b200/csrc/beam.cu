@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C,
                 if (!st.smart) {
                     st.live_cand[live] = c;
                     st.live_query[live] = c / beam;
+                    if (st.desc_self) {
+                        const int f = st.c_front[c];
+                        st.desc_self[live] = make_int4(c, f, st.cand_cur[(long long)c * st.ldw + f], 0x7fffffff);
+                        st.desc_cross[live] = make_int4(c / beam, 0, 0, st.src_len ? st.src_len[c / beam] : 0x7fffffff);
+                    }
                 }
                 ++live;
             }
@@ -113,10 +118,14 @@ __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C,
             if (st.c_fin[c]) continue;
             const int q = c / beam, base = st.c_rowbase[c], cnt = st.c_cnt[c];
             const int* list = st.tok_list + ((long long)q * st.V + st.c_last[c]) * st.N;
+            const int f = st.c_front[c];
+            const int4 ds = make_int4(c, f, st.cand_cur[(long long)c * st.ldw + f], 0x7fffffff);
+            const int4 dc = make_int4(q, 0, 0, st.src_len ? st.src_len[q] : 0x7fffffff);
             for (int j = 0; j < cnt; ++j) {
                 st.live_cand[base + j] = c;
                 st.live_query[base + j] = q;
                 st.row_draft[base + j] = list[j];
+                if (st.desc_self) { st.desc_self[base + j] = ds; st.desc_cross[base + j] = dc; }
             }
         }
     }

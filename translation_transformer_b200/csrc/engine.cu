@@ -796,7 +796,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4);
     const size_t o_lc = take(Rmax * 4), o_lq = take(Rmax * 4), o_cf = take(Cmax * 4), o_np = take(Cmax * 4), o_nk = take(Cmax * 4), o_nr = take(Cmax * 4);
     const size_t o_tc = take(smart ? (size_t)B * V * 4 : 4), o_tl = take(smart ? (size_t)B * V * N * 4 : 4), o_cc = take(Cmax * 4),
-                 o_cl = take(Cmax * 4), o_rd = take(Rmax * 4);
+                 o_cl = take(Cmax * 4), o_rd = take(Rmax * 4), o_ds = take(Rmax * 16), o_dc = take(Rmax * 16);
     if (bb.ensure(off)) return 1;
     char* base = bb.as<char>();
 
@@ -832,6 +832,13 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.n_parent = (int*)(base + o_np); st.n_keep = (int*)(base + o_nk); st.n_row = (int*)(base + o_nr);
     st.tok_cnt = (int*)(base + o_tc); st.tok_list = (int*)(base + o_tl); st.c_cnt = (int*)(base + o_cc); st.c_last = (int*)(base + o_cl);
     st.row_draft = (int*)(base + o_rd);
+    static const bool no_desc = [] { const char* v = getenv("TTB_BEAM_NO_DESC"); return v && v[0] == '1'; }();
+    if (cached && !no_desc) {
+        // per-query source length: the cross-attention kernels skip the padding behind it
+        if (e->srclen.ensure((size_t)B * sizeof(int))) return 1;
+        { Scope sc(e, KC_MISC, s); launch_row_lengths(src32, B, Ls, e->d.src_pad_token_idx, e->srclen.as<int>(), s); }
+        st.desc_self = (int4*)(base + o_ds); st.desc_cross = (int4*)(base + o_dc); st.src_len = e->srclen.as<int>();
+    }
     ActT* kc_cur = cached ? e->kcache.as<ActT>() : nullptr;
     ActT* vc_cur = cached ? e->vcache.as<ActT>() : nullptr;
     ActT* kc_next = cached ? e->kcache2.as<ActT>() : nullptr;
@@ -864,12 +871,12 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             const int G = smart ? R : C, n_per_group = smart ? 1 : N;
             auto self_attn = [&](int l, ActT* qkv, ActT* att) {
                 spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, G, n_live_cands,
-                          st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, n_per_group, dl, H, HD, ldw, s);
+                          st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, n_per_group, dl, H, HD, ldw, s, st.desc_self);
             };
             auto cross_attn = [&](int l, ActT* q2, ActT* att) {
                 const ActT* kv = crosskv + (long long)l * TS * 2 * E;
                 attn(q2, E, kv, kv + E, 2 * E, att, E, G, n_live_cands, n_per_group * (dl + 1), Ls, Ls, st.live_query,
-                     src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
+                     src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, nullptr, nullptr, st.desc_cross);
             };
             if (decoder_stack<ActT>(e, rows, n_dec, Tc * 3 * E, self_attn, cross_attn, s)) return 1;
             // every decoder row is a scored position: logits straight from the residual stream

@@ -147,6 +147,10 @@ struct BeamState {
     float* logp_cur; float* logp_next;    // [B*K]
     const int* drafts;                    // [B][N][dl0]
     int* c_slot0; int* c_fin; int* c_rowbase; int* c_nacc; int* c_pick; int* acc_stat; int* ctrl;
+    // per live attention group (written by beam_prepare): {candidate, front, token at front, -} for the self-attention
+    // over the candidate caches and {query, -, -, source length} for the cross-attention: one 16-byte load per CTA instead
+    // of the chain live list -> front -> token, and everything the attention kernels may read ahead of their dependency wait
+    int4* desc_self; int4* desc_cross; const int* src_len;
     int* host_ctrl;   // pinned host mirror of ctrl (device-accessible): BC_COUNT words + a sequence word written last
     int host_seq;     // value of the sequence word for this iteration
     int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows

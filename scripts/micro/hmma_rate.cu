@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hmma_rate hmma_rate.cu ; run on the GPU box: ./scripts/micro/hmma_rate
 // Micro-benchmark: throughput and latency of the legacy mma.sync.m16n8k16 (bf16) path on sm_100a.
 #include <cstdio>
 #include <cuda_runtime.h>

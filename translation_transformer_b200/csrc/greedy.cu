@@ -22,37 +22,34 @@ namespace ttb {
 // token matrix.  `active` / `front` / `gen` may point to shared-memory copies of the state (accept
 // kernel) or to the global arrays (init kernel); `col_live` is [W] ints of shared scratch.
 __device__ void plan_next_iteration(const GreedyState& st, const int* active, const int* front, const int* gen,
-                                    int n_active, int W, int* s_tmp, int* col_live) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tmp[0] = 0, s_tmp[1] = 0;
+                                    int n_active, int W, int* /*s_tmp*/, int* /*col_live*/) {
     __syncthreads();
     if (n_active == 0 || W >= st.max_len) {
         if (threadIdx.x == 0) { st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
         return;
     }
-    // a column is dead when every live row holds PAD there
-    for (int c = threadIdx.x; c < W; c += blockDim.x) col_live[c] = 0;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < n_active * W; idx += blockDim.x) {
-        const int g = idx / W, c = idx % W;
-        const int b = active[g];
-        if (c <= front[b] && gen[(long long)b * st.gen_ld + c] != st.pad) col_live[c] = 1;
+    // a column is dead when every live row holds PAD there: one column per thread (and pass), rows in the inner loop, the
+    // dead columns are counted by the barrier itself
+    int dead_total = 0;
+    for (int c0 = 0; c0 < W; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        int live = 0;
+        if (c < W)
+            for (int g = 0; g < n_active; ++g) {
+                const int b = active[g];
+                live |= (c <= front[b] && gen[(long long)b * st.gen_ld + c] != st.pad) ? 1 : 0;
+            }
+        dead_total += __syncthreads_count(c < W && !live);
     }
-    __syncthreads();
-    int dead = 0;
-    for (int c = threadIdx.x; c < W; c += blockDim.x) dead += col_live[c] ? 0 : 1;
-    if (dead) atomicAdd(&s_tmp[0], dead);
-    __syncthreads();
-    const int Wn = W + st.D + 1 - s_tmp[0];
+    const int Wn = W + st.D + 1 - dead_total;   // the barrier counts are the same in every thread
     int oob = 0;
     for (int g = threadIdx.x; g < n_active; g += blockDim.x)
         if (front[active[g]] + 1 + st.D > Wn - 1) oob = 1;
-    if (oob) atomicOr(&s_tmp[1], 1);
-    __syncthreads();
+    const int any_oob = __syncthreads_or(oob);
     if (threadIdx.x == 0) {
         st.ctrl[CTRL_PREV_WIDTH] = W;
         st.ctrl[CTRL_WIDTH] = Wn;
-        if (s_tmp[1]) { st.ctrl[CTRL_ERROR] = 1; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
+        if (any_oob) { st.ctrl[CTRL_ERROR] = 1; st.ctrl[CTRL_DONE] = 1; st.ctrl[CTRL_N_LEFT] = n_active; st.ctrl[CTRL_N_ACTIVE] = 0; }
     }
 }
 
@@ -160,6 +157,12 @@ template void launch_greedy_advance<__nv_bfloat16>(const GreedyState&, const flo
 // compaction, dead-column scan) never wait on global memory; updates are written through.
 constexpr int ACCEPT_MAX_SMEM_INTS = 50 * 1024;   // token matrices larger than 200 KB stay in global memory
 
+#ifdef TTB_ACC_TIMELINE
+__device__ long long g_acc_ts[16];
+#define ACC_TS(i) do { if (threadIdx.x == 0) g_acc_ts[i] = clock64(); } while (0)
+#else
+#define ACC_TS(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int stage_gen) {
     __shared__ int s_tmp[2];
     __shared__ int s_acc, s_tok, s_err;
@@ -172,11 +175,18 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
     int* s_newact = s_fin + B;                   // [B]
     int* s_srclen = s_newact + B;                // [B]
     int* s_nacc_all = s_srclen + B;              // [warps][64]
-    int* col_live = s_nacc_all + n_warps * 64;   // [gen_ld]
+    int* s_tok_all = s_nacc_all + n_warps * 64;  // [warps][16] predictions of the chosen draft row
+    int* col_live = s_tok_all + n_warps * 16;    // [gen_ld]
     int* s_gen = col_live + st.gen_ld;           // [B][gen_ld] when stage_gen
     int* s_nacc = s_nacc_all + warp * 64;
+    int* s_tokw = s_tok_all + warp * 16;
+    // every lane scores one draft and D + 1 <= 16: the predictions of the chosen row are still in its lane's registers,
+    // the token append takes them from there (through shared memory) instead of a second global round trip
+    const bool keep_pred = N <= 32 && D + 1 <= 16;
+    ACC_TS(0);
     pdl_launch_dependents();
     pdl_wait();
+    ACC_TS(1);
     // ---- round 1: independent loads --------------------------------------------------------------
     const int done = st.ctrl[CTRL_DONE];
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
@@ -188,16 +198,28 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
         s_front[b] = st.front[b];
         s_srclen[b] = st.src_len ? st.src_len[b] : 0x7fffffff;
     }
-    if (stage_gen)
-        for (int idx = threadIdx.x; idx < B * st.gen_ld; idx += blockDim.x) s_gen[idx] = st.gen[idx];
+    if (stage_gen) {
+        // all loads of a thread in flight before the first store (a plain copy loop waits for every load: seven global
+        // round trips for the 27 KB of B = 32, max_len = 200)
+        const int total = B * st.gen_ld;
+        for (int i0 = 0; i0 < total; i0 += 8 * blockDim.x) {
+            int tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int idx = i0 + u * blockDim.x + threadIdx.x; tmp[u] = idx < total ? st.gen[idx] : 0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int idx = i0 + u * blockDim.x + threadIdx.x; if (idx < total) s_gen[idx] = tmp[u]; }
+        }
+    }
     if (done) return;
     int* G = stage_gen ? s_gen : st.gen;
     if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; if (st.hist) st.hist[iter] = n_active; }
     __syncthreads();
+    ACC_TS(2);
     for (int g = warp; g < n_active; g += n_warps) {
         const int b = s_active[g];
         const int f = s_front[b];
         int best_val = -1, best_first = 0x7fffffff;
+        int kept[16];
         for (int n = lane; n < N; n += 32) {
             const int* pr = st.pred + ((long long)g * N + n) * (D + 1);
             const int* dr = st.drafts + ((long long)b * N + n) * D;
@@ -208,11 +230,12 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     dv[u] = (a0 + u < D) ? dr[a0 + u] : -1;
-                    pv[u] = (a0 + u < D) ? pr[a0 + u] : -2;
+                    pv[u] = (a0 + u <= D) ? pr[a0 + u] : -2;   // pr[D]: the token behind a fully accepted draft (dv = -1 there)
                 }
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     if (open && dv[u] == pv[u]) ++a; else open = false;
+                    kept[u] = pv[u];
                 }
             }
             if (n < 64) s_nacc[n] = (a << 8) | n;   // packed for the tie-break emulation
@@ -243,8 +266,15 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
         int* row = G + (long long)b * st.gen_ld;
         int* grow = st.gen + (long long)b * st.gen_ld;
         bool fin_l = false;
+        if (keep_pred) {
+            if (lane == pick) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s_tokw[u] = kept[u];
+            }
+            __syncwarp();
+        }
         for (int j = lane; j <= D; j += 32) {
-            const int t = (j <= a) ? pr[j] : st.pad;
+            const int t = (j <= a) ? (keep_pred ? s_tokw[j] : pr[j]) : st.pad;
             row[f + 1 + j] = t;
             if (stage_gen) grow[f + 1 + j] = t;
             fin_l |= (j <= a) && (t == st.eos);
@@ -269,7 +299,9 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
             for (int c = lane; c < Wn; c += 32) o[c] = (c <= f + a + 1) ? row[c] : st.pad;
         }
     }
+    ACC_TS(3);
     __syncthreads();
+    ACC_TS(4);
     // order-preserving compaction of the live list (boolean masking in the reference): warp 0, ballot prefix sums
     if (warp == 0) {
         int w = 0;
@@ -298,13 +330,15 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
         }
     }
     __syncthreads();
+    ACC_TS(5);
     if (s_err) return;
     const int n_left = s_tmp[0];
     plan_next_iteration(st, s_newact, s_front, G, n_left, Wn, s_tmp, col_live);
+    ACC_TS(6);
 }
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     const int warps = st.B < 32 ? (st.B < 4 ? 4 : st.B) : 32;
-    const size_t base_ints = (size_t)5 * st.B + (size_t)warps * 64 + st.gen_ld;
+    const size_t base_ints = (size_t)5 * st.B + (size_t)warps * 80 + st.gen_ld;
     const size_t gen_ints = (size_t)st.B * st.gen_ld;
     const int stage_gen = base_ints + gen_ints <= (size_t)ACCEPT_MAX_SMEM_INTS ? 1 : 0;
     const size_t smem = (base_ints + (stage_gen ? gen_ints : 0)) * sizeof(int);
@@ -313,6 +347,18 @@ void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
         cudaFuncSetAttribute(greedy_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ACCEPT_MAX_SMEM_INTS * sizeof(int)));
         attr_smem = ACCEPT_MAX_SMEM_INTS * sizeof(int);
     }
+#ifdef TTB_ACC_TIMELINE
+    {
+        static int n_launch = 0;
+        if (++n_launch == 100) {
+            cudaStreamSynchronize(s);
+            long long h[16];
+            cudaMemcpyFromSymbol(h, g_acc_ts, sizeof(h));
+            FILE* f = fopen("gpurun_out/acc_timeline.txt", "w");
+            if (f) { for (int i = 0; i < 7; ++i) fprintf(f, "%d %lld\n", i, h[i] - h[1]); fclose(f); }
+        }
+    }
+#endif
     launch_pdl(greedy_accept_kernel, dim3(1), dim3(warps * 32), smem, s, st, stage_gen);
 }
 

@@ -5,7 +5,10 @@
     python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU port of the reference)
 
 One "step" = one batch of `--batch-size` synthetic USPTO-MIT-shape queries decoded to completion
-through `TranslationInferenceGreedySpeculative.generate` (BASELINE.json configs[1]).  Multi-GPU runs
+through `TranslationInferenceGreedySpeculative.generate` (BASELINE.json configs[1]).  The K timed steps are
+decoded with `--in-flight` (default 2) batches at a time per GPU, each on its own engine and stream
+(pipeline.py; same predictions, batches are independent); the strictly sequential figure is reported
+beside it as `one_batch_in_flight`.  Multi-GPU runs
 shard the queries (each rank decodes its own batches, weak scaling) and all-gather the predictions.
 Prints ONE JSON line on rank 0.
 """
@@ -41,7 +44,7 @@ METRIC = "SMILES/sec (greedy speculative, product prediction)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -57,6 +60,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-insitu", action="store_true", help="skip the extra CUPTI-profiled step (kernels_in_situ)")
     ap.add_argument("--tie-break", default="torch_cpu", choices=["torch_cpu", "lowest_index"])
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="bs=32 batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
+                         "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
 
@@ -219,7 +225,7 @@ def run_reference(args, rank, world):
     from oracle.transformer import OracleTransformer
     cfg, sd = build_weights(args)
     model = OracleTransformer(sd, cfg.num_heads)
-    nq = args.cpu_queries
+    nq = args.cpu_queries if args.warmup + args.steps <= 8 else 1    # ~6.5 s of host time per query: keep the run to minutes
     times = []
     for i in range(args.warmup + args.steps):
         src = batch_for(args, 0, i)[:nq]
@@ -255,6 +261,7 @@ def main():
     from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
     from translation_transformer_b200.distributed import gather_predictions
     from translation_transformer_b200.model import B200Transformer
+    from translation_transformer_b200.pipeline import InFlightDecoder
 
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path"
     torch.cuda.set_device(local_rank)
@@ -264,22 +271,26 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd = build_weights(args)
-    eng = B200Transformer(cfg, sd, precision=args.precision, device=local_rank)
-    gen = TranslationInferenceGreedySpeculative(eng, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE,
-                                                tie_break=args.tie_break)
+    n_fly = max(1, args.in_flight)
+    engs = [B200Transformer(cfg, sd, precision=args.precision, device=local_rank) for _ in range(n_fly)]
+    gens = [TranslationInferenceGreedySpeculative(e, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE,
+                                                  tie_break=args.tie_break) for e in engs]
+    eng, gen = engs[0], gens[0]          # the instrumented / profiled steps run on the first engine alone
+    fly = InFlightDecoder(gens, device=local_rank) if n_fly > 1 else None
     lib = eng.lib
     n_total = args.warmup + args.steps + 1
     host = [batch_for(args, rank, i).pin_memory() for i in range(n_total)]
     devb = [h.to(dev) for h in host]
     out_host = torch.empty(args.batch_size, 1, args.max_len, dtype=torch.int64).pin_memory()
+    out_hosts = [torch.empty_like(out_host).pin_memory() for _ in range(args.steps)] if fly else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     errors = []
 
-    def one_step(i, e2e):
+    def one_step(i, e2e, g=None):
         flush.zero_()
         src = host[i].to(dev, non_blocking=True) if e2e else devb[i]
         try:
-            out = gen.generate(src)
+            out = (g or gen).generate(src)
         except RuntimeError as ex:   # reference-faithful failure modes (see oracle/greedy_speculative.py)
             errors.append(str(ex)[:80])
             out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
@@ -295,12 +306,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e, first):
+    def pre_resident(i):
+        flush.zero_()                                   # on the worker's stream, like everything of its step
+        return devb[i]
+
+    def pre_host(i):
+        flush.zero_()
+        return host[i].to(dev, non_blocking=True)
+
+    def timed(e2e, first, pipelined=True):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for k in range(args.steps):
-            one_step(first + k, e2e)
+        if fly and pipelined:
+            # all K steps are submitted at once; `n_fly` of them are decoded at any time, each on its own engine and stream
+            # (flush, input copy, decoding loop, result copy); this thread collects them in step order
+            futs = [fly.submit(first + k, pre=pre_host if e2e else pre_resident,
+                               post=(lambda o, k=k: (out_hosts[k].copy_(o, non_blocking=True), o)[1]) if e2e else None) for k in range(args.steps)]
+            for f in futs:
+                try:
+                    out = f.result()
+                except RuntimeError as ex:   # reference-faithful failure modes (see oracle/greedy_speculative.py)
+                    errors.append(str(ex)[:80])
+                    out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
+                if world > 1:
+                    gather_predictions(out, counts=[args.batch_size] * world)   # NCCL all-gather of the predictions
+        else:
+            for k in range(args.steps):
+                one_step(first + k, e2e)
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -309,8 +342,15 @@ def main():
         return float(ms.item())
 
     # ---- warm-up (also sizes every workspace) -------------------------------------------------
-    for i in range(args.warmup):
-        one_step(i, False)
+    for g in gens:
+        for i in range(args.warmup):
+            one_step(i, False, g)
+    if fly:   # and W more through the worker threads, `n_fly` at a time (thread start-up, per-thread CUDA state)
+        for f in [fly.submit(i % args.warmup, pre=pre_resident) for i in range(args.warmup * n_fly)]:
+            try:
+                f.result()
+            except RuntimeError:
+                pass
     # ---- one instrumented step: CUDA-event time of every kernel class -> dominant kernel ---------
     n_cls = lib.ttb_kernel_class_count()
     names = [lib.ttb_kernel_class_name(i).decode() for i in range(n_cls)]
@@ -333,15 +373,18 @@ def main():
     lib.ttb_engine_set_profiling(eng._h, 0)
 
     # ---- timed region 1: inputs resident in HBM, no instrumentation -------------------------------
-    calls0, launches0, acc0, tok0 = gen.model_calls_num, gen.gpu_launches, gen.accepted_tokens_num, gen.produced_tokens_num
+    def counters():
+        return [sum(getattr(g, n) for g in gens) for n in ("model_calls_num", "gpu_launches", "accepted_tokens_num", "produced_tokens_num")]
+
+    one_ms = timed(False, args.warmup, pipelined=False) if fly else None    # strictly one batch after the other
+    calls0, launches0, acc0, tok0 = counters()
     sampler = ClockSampler(local_rank, args.clock_period_ms)
     if rank == 0:
         sampler.start()
     timed_ms = timed(False, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    calls = gen.model_calls_num - calls0
-    launches = gen.gpu_launches - launches0
-    accepted, produced = gen.accepted_tokens_num - acc0, gen.produced_tokens_num - tok0
+    calls1, launches1, acc1, tok1 = counters()
+    calls, launches, accepted, produced = calls1 - calls0, launches1 - launches0, acc1 - acc0, tok1 - tok0
 
     # ---- timed region 2: end to end through the public API with host buffers ---------------------
     e2e_ms = timed(True, args.warmup)
@@ -408,13 +451,18 @@ def main():
                 "config": {"workload": workload_name(args), "global_batch": world * args.batch_size,
                            "parallelism": f"dp{world} (one batch per rank and step: the step's queries rotated by the rank, so "
                                           f"per-GPU work is identical; predictions all-gathered over NCCL)" if world > 1 else "single GPU",
-                           "l2": "256 MiB buffer written between steps (L2 flush)"},
+                           "batches_in_flight": n_fly,
+                           "l2": "256 MiB buffer written before every step (L2 flush)"},
                 "e2e": {"value": e2e_value, "unit": "SMILES/s", "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(host[args.warmup].numel() * 8),
                         "d2h_bytes_per_step": int(out_host.numel() * 8)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_shares": shares,
                 "decoder_calls": calls, "accepted_tokens_per_call": accepted / max(calls, 1),
                 "produced_tokens": produced, "reference_failures": errors[:3]}
+        if one_ms is not None:
+            line["one_batch_in_flight"] = {"value": queries / (one_ms / 1000.0), "unit": "SMILES/s", "ms_per_step": one_ms / args.steps,
+                                           "what": "the same K steps strictly one after the other on one engine (the kernel-level "
+                                                   "figures of `roofline` / `kernels_in_situ` are measured in this mode)"}
         if insitu:
             line["kernels_in_situ"] = insitu
         if world == 1:

@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--output", help="prediction CSV (reference format); omitted -> predictions are not saved")
     ap.add_argument("--report-file")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="batches decoded concurrently per GPU (one engine each, pipeline.py); 1 = the reference's sequential loop")
     return ap.parse_args()
 
 
@@ -122,7 +124,7 @@ def main():
         src_tokenizer=tk, tgt_tokenizer=tk, generation=args.generation, beam_size=args.beam_size,
         max_len=args.max_len, n_drafts=args.n_drafts, draft_len=args.draft_len, smart_drafts_mode=args.smart_drafts_mode,
         report_prediction_time=rank == 0, report_prediction_file=args.report_file, state_dict=sd, precision=args.precision,
-        device=local_rank, seed=args.seed, **PRODUCT_PREDICTION)
+        device=local_rank, seed=args.seed, batches_in_flight=max(1, args.in_flight), **PRODUCT_PREDICTION)
 
     mine = shard_batches(len(batches), rank, world)
     n_best = 1 if args.generation in ("greedy", "greedy_speculative") else args.beam_size
@@ -133,13 +135,24 @@ def main():
     model.on_predict_start()
     t0 = time.perf_counter()
     local = []
-    for bi in mine:
-        src = batches[bi]["src_tokens"].to(dev, non_blocking=True)
-        try:
-            pred = model.predict_step({"src_tokens": src}, bi)
-        except RuntimeError:          # the reference's own failure modes: keep the row count
-            failures += 1
-            pred = torch.zeros(src.shape[0], n_best, args.max_len, dtype=torch.int64, device=dev)
+    mine = list(mine)
+
+    def failed(i, ex):               # the reference's own failure modes: keep the row count
+        nonlocal failures
+        failures += 1
+        return torch.zeros(batches[mine[i]]["src_tokens"].shape[0], n_best, args.max_len, dtype=torch.int64, device=dev)
+
+    if args.in_flight > 1:
+        preds = model.predict_batches([batches[bi] for bi in mine], on_error=failed)
+    else:
+        def sequential():
+            for i, bi in enumerate(mine):
+                try:
+                    yield model.predict_step({"src_tokens": batches[bi]["src_tokens"].to(dev, non_blocking=True)}, bi)
+                except RuntimeError as ex:
+                    yield failed(i, ex)
+        preds = sequential()
+    for pred in preds:
         if pred.shape[2] < args.max_len:   # beam searches return the width they reached
             pred = torch.nn.functional.pad(pred, (0, args.max_len - pred.shape[2]))
         local.append(pred[:, :, :args.max_len])
@@ -162,7 +175,7 @@ def main():
                 lo += k
         print(json.dumps({"queries": n, "n_gpus": world, "seconds": round(dt, 3), "smiles_per_s": round(n / dt, 1),
                           "generation": args.generation, "batch_size": args.batch_size, "precision": args.precision,
-                          "model_calls_rank0": model.generator.model_calls_num, "reference_failures_rank0": failures,
+                          "batches_in_flight": max(1, args.in_flight), "model_calls_rank0": model._counter("model_calls_num"), "reference_failures_rank0": failures,
                           "output": args.output}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -543,3 +543,41 @@ def test_ffn_pair_kernel_matches_cta_group1_kernel(dev):
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "WORST 0.0" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("generation", ["greedy_speculative", "beam_search_speculative"])
+def test_batches_in_flight_give_the_sequential_predictions(dev, generation):
+    """pipeline.py / `predict_batches`: three batches decoded concurrently by three engines (own streams, workspaces and
+    CUDA graphs) return, in order, exactly what `predict_step` returns batch by batch (bf16 benchmark model shape)."""
+    from helpers import FULL
+    from translation_transformer_b200.lightning_model import VanillaEncoderDecoderTransformerLightning
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("predict_driver", Path(__file__).resolve().parent.parent / "scripts" / "predict.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    vocab = 96
+    tk = mod.synthetic_tokenizer(vocab)
+    model = VanillaEncoderDecoderTransformerLightning(
+        src_tokenizer=tk, tgt_tokenizer=tk, generation=generation, beam_size=3, max_len=40, n_drafts=5, draft_len=6,
+        smart_drafts_mode=False, report_prediction_time=False, precision="bf16", device=0, seed=99, batches_in_flight=3, **FULL)
+    batches = [{"src_tokens": _ragged_sources(4 if i % 2 else 3, 12, 30, vocab, seed=500 + i)} for i in range(7)]
+
+    def run(fn):
+        try:
+            return fn()
+        except RuntimeError as ex:      # the reference's own failure modes are results too
+            return str(ex)[:40]
+
+    seq = [run(lambda b=b, i=i: model.predict_step({"src_tokens": b["src_tokens"].to(dev)}, i).cpu()) for i, b in enumerate(batches)]
+    calls_seq = model._counter("model_calls_num")
+    par = [p if isinstance(p, str) else p.cpu() for p in model.predict_batches(batches, on_error=lambda i, ex: str(ex)[:40])]
+    assert model._counter("model_calls_num") == 2 * calls_seq
+    assert sum(g.model_calls_num > 0 for g in model.generators) >= 2      # the batches really went to several engines
+    assert len(par) == len(seq)
+    for a, b in zip(seq, par):
+        assert type(a) is type(b)
+        assert a == b if isinstance(a, str) else torch.equal(a, b)
+    for m in model.models:
+        m.close()

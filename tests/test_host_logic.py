@@ -140,3 +140,50 @@ def test_predict_driver_batches_and_synthetic_vocab(tmp_path):
     args2 = types.SimpleNamespace(synthetic=70, batch_size=32, vocab=288)
     _, sb = mod.load_batches(args2)
     assert [b["src_tokens"].shape[0] for b in sb] == [32, 32, 6]
+
+
+def test_in_flight_decoder_keeps_submission_order_and_bounds_concurrency():
+    """pipeline.py: K generators decode K batches at a time from host threads; results come back in submission order,
+    a failing batch is replaced through `on_error`, generators must not share an engine."""
+    import threading
+    import time as _time
+    from translation_transformer_b200.pipeline import InFlightDecoder
+
+    class FakeEngine:
+        pass
+
+    state = {"now": 0, "peak": 0}
+    lock = threading.Lock()
+
+    class FakeGen:
+        def __init__(self):
+            self.model, self.model_calls_num = FakeEngine(), 0
+
+        def generate(self, src):
+            with lock:
+                state["now"] += 1
+                state["peak"] = max(state["peak"], state["now"])
+            _time.sleep(0.02 if int(src[0]) % 2 else 0.005)   # completion order differs from submission order
+            with lock:
+                state["now"] -= 1
+            self.model_calls_num += 1
+            if int(src[0]) == 5:
+                raise RuntimeError("reference failure mode")
+            return src * 2
+
+    gens = [FakeGen(), FakeGen(), FakeGen()]
+    dec = InFlightDecoder(gens, device=None)
+    srcs = [torch.tensor([i, i + 1]) for i in range(11)]
+    out = list(dec.map(srcs, pre=lambda s: s + 0, post=lambda o: o + 1, on_error=lambda i, ex: torch.tensor([-1, -1])))
+    for i, o in enumerate(out):
+        assert o.tolist() == ([-1, -1] if i == 5 else [2 * i + 1, 2 * i + 3])
+    assert 2 <= state["peak"] <= 3
+    assert dec.counter("model_calls_num") == 11 and len(dec) == 3
+    with pytest.raises(RuntimeError):
+        list(dec.map([torch.tensor([5, 0])]))
+    dec.close()
+    shared = FakeGen()
+    other = FakeGen()
+    other.model = shared.model
+    with pytest.raises(AssertionError):
+        InFlightDecoder([shared, other], device=None)

@@ -23,14 +23,12 @@ bool pdl_enabled() {
     return on;
 }
 
-static long long g_alloc_gen = 0;  // bumped whenever a workspace buffer moves (invalidates captured graphs)
 
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
-        ++g_alloc_gen;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -143,6 +141,20 @@ struct ttb_engine {
 
     int E() const { return d.embedding_dim; }
     int HD() const { return d.embedding_dim / d.num_heads; }
+
+    // Fingerprint of this engine's workspace (address and capacity of every buffer): part of the key of the captured
+    // graph, so a buffer that moved invalidates the graph of THIS engine only (several engines decode concurrently from
+    // different host threads, translation_transformer_b200/pipeline.py)
+    long long alloc_signature() const {
+        const DevBuf* bufs[] = {&x, &xh, &y, &qkv, &att, &q2, &hid, &logits, &tok32, &keytok32, &pred, &src32, &srclen, &desc, &memory, &memh,
+                                &crosskv, &kcache, &vcache, &kcache2, &vcache2, &drafts, &gen, &front, &active, &ctrl, &sel, &out64, &beam, &hist};
+        unsigned long long h = 1469598103934665603ull;
+        for (const DevBuf* b : bufs) {
+            h = (h ^ (unsigned long long)reinterpret_cast<uintptr_t>(b->p)) * 1099511628211ull;
+            h = (h ^ (unsigned long long)b->cap) * 1099511628211ull;
+        }
+        return (long long)(h >> 1);
+    }
 };
 
 namespace ttb {
@@ -663,7 +675,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     static const int graph_iters = [] { const char* v = getenv("TTB_GRAPH_ITERS"); const int k = v ? atoi(v) : 4; return k < 1 ? 1 : (k > 16 ? 16 : k); }();
     const int K_it = use_graph ? graph_iters : 1;
     if (use_graph) {
-        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, g_alloc_gen, (long long)sizeof(ActT) + 16 * K_it, replace};
+        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, e->alloc_signature(), (long long)sizeof(ActT) + 16 * K_it, replace};
         if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
             const long long l0 = e->launches;

@@ -28,7 +28,8 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
                  activation: str = "relu", share_embeddings: bool = False, generation: str = "greedy_speculative",
                  beam_size: int = 0, max_len: int = 0, n_drafts: int = 0, draft_len: int = 0, smart_drafts_mode: bool = True,
                  report_prediction_time: bool = True, report_prediction_file: str | None = None,
-                 state_dict: dict | None = None, precision: str = "bf16", device: int = 0, seed: int = 0, **_unused):
+                 state_dict: dict | None = None, precision: str = "bf16", device: int = 0, seed: int = 0,
+                 batches_in_flight: int = 1, **_unused):
         if _Base is not object:
             super().__init__()
         assert src_tokenizer is not None, "source tokenizer not provided"
@@ -45,33 +46,41 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
                           num_encoder_layers=num_encoder_layers, num_decoder_layers=num_decoder_layers,
                           num_heads=num_heads, share_embeddings=share_embeddings,
                           src_pad_token_idx=self.src_pad_token_i, tgt_pad_token_idx=self.tgt_pad_token_i)
-        self.model = B200Transformer(cfg, state_dict if state_dict is not None else random_init_state_dict(cfg, seed),
-                                     precision=precision, device=device)
-        self.generator = self._create_generator()
+        weights = state_dict if state_dict is not None else random_init_state_dict(cfg, seed)
+        # `batches_in_flight` > 1: one engine (weights, workspace, stream, CUDA graphs) per batch decoded concurrently by
+        # `predict_batches` (pipeline.py); `model` / `generator` stay the first pair, which `predict_step` uses
+        self.models = [B200Transformer(cfg, weights, precision=precision, device=device) for _ in range(max(1, batches_in_flight))]
+        self.model = self.models[0]
+        self.generators = [self._create_generator(m) for m in self.models]
+        self.generator = self.generators[0]
+        self._in_flight = None
+        self.device_index = device
         self.prediction_start_time = None
         self.batch_size = None
 
     def load_checkpoint_state_dict(self, state_dict: dict) -> None:
         """Accepts the `state_dict` of a reference Lightning checkpoint (keys prefixed `model.`)."""
-        self.model.load_state_dict({k: v for k, v in state_dict.items() if "positional_encoding" not in k})
+        for m in self.models:
+            m.load_state_dict({k: v for k, v in state_dict.items() if "positional_encoding" not in k})
 
-    def _create_generator(self):
+    def _create_generator(self, model=None):
+        model = self.model if model is None else model
         if self.generation == "greedy":
-            return TranslationInferenceGreedy(self.model, max_len=self.max_len, pad_token=self.tgt_pad_token_i,
+            return TranslationInferenceGreedy(model, max_len=self.max_len, pad_token=self.tgt_pad_token_i,
                                               bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i)
         if self.generation == "beam_search":
-            return TranslationInferenceBeamSearch(self.model, beam_size=self.beam_size, max_len=self.max_len,
+            return TranslationInferenceBeamSearch(model, beam_size=self.beam_size, max_len=self.max_len,
                                                   pad_token=self.tgt_pad_token_i, bos_token=self.tgt_bos_token_i,
                                                   eos_token=self.tgt_eos_token_i)
         if self.generation == "greedy_speculative":
             assert self.draft_len > 0, "Number of speculative tokens must be a positive integer."
             return TranslationInferenceGreedySpeculative(
-                self.model, max_len=self.max_len, draft_len=self.draft_len, n_drafts=self.n_drafts,
+                model, max_len=self.max_len, draft_len=self.draft_len, n_drafts=self.n_drafts,
                 pad_token=self.tgt_pad_token_i, bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
                 replace_token=self.tgt_tokenizer.encoder_dict["c"])
         if self.generation == "beam_search_speculative":
             return TranslationInferenceBeamSearchSpeculative(
-                self.model, vocab_size=self.tgt_tokenizer.n_tokens, max_len=self.max_len, n_best=self.beam_size,
+                model, vocab_size=self.tgt_tokenizer.n_tokens, max_len=self.max_len, n_best=self.beam_size,
                 draft_len=self.draft_len, n_drafts=self.n_drafts, pad_token=self.tgt_pad_token_i,
                 bos_token=self.tgt_bos_token_i, eos_token=self.tgt_eos_token_i,
                 C_token=self.tgt_tokenizer.encoder_dict["c"], smart_drafts_mode=self.smart_drafts_mode)
@@ -82,6 +91,21 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         self.batch_size = batch["src_tokens"].shape[0] if self.batch_size is None else self.batch_size
         return self.generator.generate(batch["src_tokens"])
 
+    def predict_batches(self, batches, on_error=None):
+        """Predictions of `batches` (dicts with "src_tokens", like `predict_step` gets) in order, with up to
+        `batches_in_flight` batches decoded concurrently (pipeline.py).  Same results as calling `predict_step` on each."""
+        from .pipeline import InFlightDecoder
+        if self._in_flight is None:
+            self._in_flight = InFlightDecoder(self.generators, device=self.device_index)
+        batches = list(batches)
+        if batches and self.batch_size is None:
+            self.batch_size = batches[0]["src_tokens"].shape[0]
+        dev = self.model.device
+        return self._in_flight.map((b["src_tokens"] for b in batches), pre=lambda s: s.to(dev, non_blocking=True), on_error=on_error)
+
+    def _counter(self, name: str):
+        return sum(getattr(g, name) for g in self.generators)
+
     def on_predict_start(self) -> None:
         if self.report_prediction_time:
             self.prediction_start_time = timer()
@@ -90,9 +114,10 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         if not self.report_prediction_time:
             return
         elapsed = datetime.timedelta(seconds=timer() - self.prediction_start_time)
-        calls = max(self.generator.model_calls_num, 1)
+        n_calls = self._counter("model_calls_num")
+        calls = max(n_calls, 1)
         report = {"algorithm": self.generation, "batch_size": self.batch_size, "max_len": self.max_len,
-                  "total_seconds": round(elapsed.total_seconds(), 4), "model_calls": self.generator.model_calls_num,
+                  "total_seconds": round(elapsed.total_seconds(), 4), "model_calls": n_calls,
                   "seconds_per_model_call": round(elapsed.total_seconds() / calls, 4)}
         if self.generation in ("greedy_speculative", "beam_search_speculative"):
             report["n_drafts"], report["draft_len"] = self.n_drafts, self.draft_len

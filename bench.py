@@ -223,6 +223,11 @@ def run_reference(args, rank, world):
         return
     from oracle.greedy_speculative import GreedySpeculativeOracle
     from oracle.transformer import OracleTransformer
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make this a one-thread baseline
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(os.cpu_count() or 1)
     cfg, sd = build_weights(args)
     model = OracleTransformer(sd, cfg.num_heads)
     nq = args.cpu_queries if args.warmup + args.steps <= 8 else 1    # ~6.5 s of host time per query: keep the run to minutes
@@ -267,8 +272,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL logs to stdout (its version banner at VERSION and at WARN level)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd = build_weights(args)
     n_fly = max(1, args.in_flight)

@@ -112,6 +112,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL logs (version banner) off stdout
         dist.init_process_group("nccl", device_id=dev)
 
     tk, batches = load_batches(args)

@@ -6,7 +6,7 @@
 
 One "step" = one batch of `--batch-size` synthetic USPTO-MIT-shape queries decoded to completion
 through `TranslationInferenceGreedySpeculative.generate` (BASELINE.json configs[1]).  The K timed steps are
-decoded with `--in-flight` (default 2) batches at a time per GPU, each on its own engine and stream
+decoded with `--in-flight` (default 3) batches at a time per GPU, each on its own engine and stream
 (pipeline.py; same predictions, batches are independent); the strictly sequential figure is reported
 beside it as `one_batch_in_flight`.  Multi-GPU runs
 shard the queries (each rank decodes its own batches, weak scaling) and all-gather the predictions.
@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-insitu", action="store_true", help="skip the extra CUPTI-profiled step (kernels_in_situ)")
     ap.add_argument("--tie-break", default="torch_cpu", choices=["torch_cpu", "lowest_index"])
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="bs=32 batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
                          "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")

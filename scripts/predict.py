@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--output", help="prediction CSV (reference format); omitted -> predictions are not saved")
     ap.add_argument("--report-file")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="batches decoded concurrently per GPU (one engine each, pipeline.py); 1 = the reference's sequential loop")
     return ap.parse_args()
 

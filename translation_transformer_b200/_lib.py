@@ -6,9 +6,11 @@ if the shared object is missing or no B200 is visible, using the package raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libttb200.so"
+# TTB_LIB: file name (inside the package) of an experimental build of the same sources, for A/B runs (scripts/build_variant.sh)
+LIB_PATH = Path(__file__).resolve().parent / os.environ.get("TTB_LIB", "libttb200.so")
 
 ABI_VERSION = 2
 PRECISION = {"fp32": 0, "bf16": 1}

@@ -476,8 +476,9 @@ def main():
             # BASELINE.json configs[2] beside the headline (same weights): speculative beam search bs=4, n_best=5
             try:
                 from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
-                bgen = TranslationInferenceBeamSearchSpeculative(eng, args.max_len, 5, args.draft_len, args.n_drafts, args.vocab, False,
-                                                                 PAD, BOS, EOS, REPLACE)
+                bgens = [TranslationInferenceBeamSearchSpeculative(e_, args.max_len, 5, args.draft_len, args.n_drafts, args.vocab, False,
+                                                                   PAD, BOS, EOS, REPLACE) for e_ in engs]
+                bgen = bgens[0]
                 bsrc = [batch_for(args, 0, i)[:4].to(dev) for i in range(3)]
                 bgen.generate(bsrc[0])
                 torch.cuda.synchronize()
@@ -489,7 +490,19 @@ def main():
                 line["beam_speculative"] = {"workload": "product prediction beam-search speculative bs=4 n_best=5 draft_len=10 n_drafts=23 "
                                                         "(BASELINE.json configs[2]), same weights and sources, KV-cached",
                                             "value": 8 / dt, "unit": "SMILES/s", "ms_per_batch": 1000 * dt / 2,
-                                            "decoder_calls_per_batch": (bgen.model_calls_num - c0) / 2}
+                                            "decoder_calls_per_batch": (bgen.model_calls_num - c0) / 2, "batches_in_flight": 1}
+                if n_fly > 1:    # the same search with `n_fly` batches in flight (one engine each)
+                    bfly = InFlightDecoder(bgens, device=local_rank)
+                    many = [batch_for(args, 0, i % 3)[:4] for i in range(3 * n_fly)]
+                    list(bfly.map(many[:n_fly], pre=lambda t: t.to(dev), on_error=lambda i, ex: None))
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    list(bfly.map(many, pre=lambda t: t.to(dev), on_error=lambda i, ex: None))
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    line["beam_speculative"]["in_flight"] = {"batches_in_flight": n_fly, "value": 4 * len(many) / dt, "unit": "SMILES/s",
+                                                             "ms_per_batch": 1000 * dt / len(many)}
+                    bfly.close()
             except (RuntimeError, AssertionError) as ex:   # reference-faithful failure modes
                 line["beam_speculative"] = {"error": str(ex)[:120]}
         if world == 1 and not args.no_cpu_baseline:

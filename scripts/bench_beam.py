@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--eos-bias", type=float, default=2.0, help="random-init models never stop on their own; bias EOS so "
                                                                   "that hypotheses finish at USPTO-like lengths")
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--profile", action="store_true", help="per kernel class CUDA-event times of one batch")
+    ap.add_argument("--in-flight", type=int, nargs="+", default=[1],
+                    help="batches decoded concurrently (one engine + host thread each, pipeline.py); several values are run in turn")
     a = ap.parse_args()
     c = CONFIGS[a.config]
     cfg = ModelConfig(src_vocab_size=a.vocab, tgt_vocab_size=a.vocab, embedding_dim=256, feedforward_dim=2048,
@@ -60,7 +63,46 @@ def main():
             calls.append(gen.model_calls_num - c0)
     print(json.dumps({"config": a.config, "precision": a.precision, "smiles_per_s": c["bs"] * len(times) / sum(times),
                       "ms_per_batch": 1000 * sum(times) / len(times), "decoder_calls_per_batch": sum(calls) / len(calls),
-                      "accepted_tokens": gen.accepted_tokens_num, "reference_failures": errs}))
+                      "accepted_tokens": gen.accepted_tokens_num, "reference_failures": errs}), flush=True)
+    if a.profile:   # CUDA-event time of every kernel class in one more (eagerly launched, serialised) batch
+        import ctypes as C
+        lib = eng.lib
+        n_cls = lib.ttb_kernel_class_count()
+        names = [lib.ttb_kernel_class_name(i).decode() for i in range(n_cls)]
+        lib.ttb_engine_set_profiling(eng._h, (1 << n_cls) - 1)
+        gen.generate(synthetic_sources(c["bs"], a.vocab, seed=7000 + a.warmup).to(dev))
+        ms_arr, n_arr = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
+        lib.ttb_engine_get_profile(eng._h, n_cls, ms_arr, n_arr)
+        lib.ttb_engine_set_profiling(eng._h, 0)
+        tot = sum(ms_arr) or 1.0
+        for i in range(n_cls):
+            if n_arr[i]:
+                print(f"  {names[i]:18s} {ms_arr[i]:8.3f} ms {n_arr[i]:6d} launches {1000 * ms_arr[i] / n_arr[i]:7.2f} us  {ms_arr[i] / tot:5.3f}", flush=True)
+    # ---- several batches in flight: these searches keep only a few hundred token rows busy (2-8 row blocks of the GEMM
+    # kernels on 148 SMs), so independent batches overlap almost freely
+    from translation_transformer_b200.pipeline import InFlightDecoder
+    kmax = max(a.in_flight)
+    if kmax > 1:
+        gens = [gen] + [TranslationInferenceBeamSearchSpeculative(B200Transformer(cfg, sd, precision=a.precision, device=0), a.max_len, c["nbest"],
+                                                                  c["draft_len"], c["n_drafts"], a.vocab, False, 0, 1, 2, 7) for _ in range(kmax - 1)]
+        ref = None
+        for k in a.in_flight:
+            if k < 2:
+                continue
+            fly = InFlightDecoder(gens[:k], device=0)
+            n = max(a.steps, 2) * k
+            srcs = [synthetic_sources(c["bs"], a.vocab, seed=7000 + a.warmup + (i % a.steps)) for i in range(n)]
+            list(fly.map(srcs[:k], pre=lambda s: s.to(dev), on_error=lambda i, ex: None))     # warm-up of every engine
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            outs = [o.cpu() if o is not None else None for o in fly.map(srcs, pre=lambda s: s.to(dev), on_error=lambda i, ex: None)]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            same = all((x is None and y is None) or (x is not None and y is not None and torch.equal(x, y))
+                       for x, y in zip(outs[:a.steps], outs[a.steps:2 * a.steps]))   # the same sources decoded by different engines
+            print(json.dumps({"config": a.config, "in_flight": k, "smiles_per_s": c["bs"] * n / dt, "ms_per_batch": 1000 * dt / n,
+                              "batches": n, "repeat_identical": same}), flush=True)
+            fly.close()
 
 
 if __name__ == "__main__":

@@ -17,6 +17,13 @@
 #include "topk_emul.cuh"
 
 namespace ttb {
+// Accumulators of the loop control behind the BC_COUNT control words (reset by the CTA that finalises an iteration), and the
+// loop state the device carries itself so that an iteration's kernel arguments do not change from one iteration to the next
+// (the iteration is replayed as a CUDA graph): width of the token matrix and number of the CURRENT iteration, advanced by
+// the CTA that closes the iteration with the same rule the host applies (engine.cu:beam_api, speculative_decoding.py:452-470)
+constexpr int BCX_ALL_FIN = BC_COUNT, BCX_MIN_PAD = BC_COUNT + 1, BCX_ACC = BC_COUNT + 2, BCX_CNT = BC_COUNT + 3, BCX_TICKET = BC_COUNT + 4,
+              BCX_W = BC_COUNT + 5, BCX_ITER = BC_COUNT + 6;
+
 
 // drafts of candidate c (query q): all N source drafts, or in smart mode the library windows keyed by its last token
 __device__ __forceinline__ int cand_n_drafts(const BeamState& st, int c) { return st.smart ? st.c_cnt[c] : st.N; }
@@ -52,7 +59,8 @@ void launch_beam_build_lib(const BeamState& st, cudaStream_t s) {
 }
 
 // ---- prepare ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int W, int dl) {
+__global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int dl) {
+    const int W = st.ctrl[BCX_W];
     // one warp per candidate row, coalesced scan: first PAD column, EOS anywhere, a real token behind the first PAD
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     for (int c = warp; c < C; c += n_warps) {
@@ -130,8 +138,8 @@ __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C,
         }
     }
 }
-void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s) {
-    beam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, beam, W, dl);
+void launch_beam_prepare(const BeamState& st, int C, int beam, int dl, cudaStream_t s) {
+    beam_prepare_kernel<<<1, 1024, 0, s>>>(st, C, beam, dl);
 }
 
 // ---- KV-cached decoder pass ---------------------------------------------------------------------------------
@@ -346,8 +354,9 @@ void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, i
 // One CTA per candidate.  "Is draft token a of draft n inside the truncated support of its position?" is evaluated for all
 // (draft, position) pairs in parallel (two dependent global loads each instead of a chain of up to 2 dl per draft); the
 // accepted length of a draft is the length of its leading run of hits.
-__global__ void __launch_bounds__(256) beam_choose_kernel(BeamState st, int C, int beam, int dl, int iter, int par) {
+__global__ void __launch_bounds__(256) beam_choose_kernel(BeamState st, int C, int beam, int dl, int par) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
+    const int iter = st.ctrl[BCX_ITER];
     const int c = blockIdx.x;
     __shared__ int s_nacc[64];
     extern __shared__ unsigned char s_hit[];                 // [m][dl] when par
@@ -395,19 +404,18 @@ __global__ void __launch_bounds__(256) beam_choose_kernel(BeamState st, int C, i
         if (st.trace_pick) st.trace_pick[(long long)iter * st.B * K + c] = pick;
     }
 }
-void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s) {
+void launch_beam_choose(const BeamState& st, int C, int beam, int dl, cudaStream_t s) {
     const size_t smem = (size_t)st.N * (dl > 0 ? dl : 1);
     const int par = smem <= 40 * 1024 ? 1 : 0;
-    launch_pdl(beam_choose_kernel, dim3(C), dim3(256), par ? smem : 0, s, st, C, beam, dl, iter, par);
+    launch_pdl(beam_choose_kernel, dim3(C), dim3(256), par ? smem : 0, s, st, C, beam, dl, par);
 }
 
 // ---- leaves of the continuation trees, n_best best per query, loop control ---------------------------------------
 // Accumulators of the loop control behind the BC_COUNT control words (reset by the CTA that finalises an iteration)
-constexpr int BCX_ALL_FIN = BC_COUNT, BCX_MIN_PAD = BC_COUNT + 1, BCX_ACC = BC_COUNT + 2, BCX_CNT = BC_COUNT + 3, BCX_TICKET = BC_COUNT + 4;
 // log softmax exactly as the reference evaluates it: log(exp(x - max) / sum)   (:378)
 __device__ __forceinline__ float ref_logprob(float logit, float mx, float sum) { return logf(expf(logit - mx) / sum); }
 
-__global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam, int W, int dl, const float* __restrict__ logits) {
+__global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam, int dl, const float* __restrict__ logits) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
     extern __shared__ float s_score[];                 // [beam][(dl+1)][K] leaf scores, -inf when absent
     __shared__ float s_red_v[256];
@@ -415,6 +423,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
     __shared__ int s_sel[64];
     __shared__ int s_valid;
     const int q = blockIdx.x, K = st.K, V = st.V, N = st.N;
+    const int W = st.ctrl[BCX_W];                      // rewritten only by the CTA that closes the iteration, after every CTA has arrived
     const int per_c = (dl + 1) * K, total = beam * per_c;
     float* s_pre = s_score + total;                    // [beam][dl+2] running log-prob of the accepted path
     if (threadIdx.x == 0) s_valid = 0;
@@ -558,11 +567,19 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             st.ctrl[BC_ACCEPTED] += acc;
             st.ctrl[BC_PRODUCED] += acc + cnt;
             st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
+            // width of the next iteration's token matrix (speculative_decoding.py:452-470, mirrored by the host loop)
+            const int seq = st.ctrl[BCX_ITER] + 1;
+            {
+                const int empty = st.ctrl[BC_EMPTY_COLS], filled = W - empty, budget = st.max_len - filled - 1;
+                const int grow = min(budget, dl) + 1 - empty;
+                st.ctrl[BCX_W] = W + max(grow, 0);
+                st.ctrl[BCX_ITER] = seq;
+            }
             if (st.host_ctrl) {
                 // what the host needs per iteration, packed into ONE 64-bit word of its own (pinned, mapped) memory:
                 // sequence number | error | all finished | empty columns.  One posted store: no copy engine, no stream
                 // synchronisation, no system-scope fence between this kernel and the cache update that follows it.
-                const unsigned long long word = ((unsigned long long)(unsigned)st.host_seq << 32) |
+                const unsigned long long word = ((unsigned long long)(unsigned)seq << 32) |
                                                 ((unsigned long long)(atomicAdd(&st.ctrl[BC_ERROR], 0) & 0xff) << 24) |
                                                 ((unsigned long long)(st.ctrl[BC_ALL_FINISHED] & 0xff) << 16) |
                                                 (unsigned long long)(st.ctrl[BC_EMPTY_COLS] & 0xffff);
@@ -571,14 +588,14 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
         }
     }
 }
-void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s) {
+void launch_beam_expand(const BeamState& st, int beam, int dl, const float* logits, cudaStream_t s) {
     const size_t smem = ((size_t)beam * (dl + 1) * st.K + (size_t)beam * (dl + 2)) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(beam_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    launch_pdl(beam_expand_kernel, dim3(st.B), dim3(256), smem, s, st, beam, W, dl, logits);
+    launch_pdl(beam_expand_kernel, dim3(st.B), dim3(256), smem, s, st, beam, dl, logits);
 }
 
 __global__ void beam_init_kernel(BeamState st) {
@@ -590,7 +607,10 @@ __global__ void beam_init_kernel(BeamState st) {
     if (blockIdx.x == 0) {
         for (int b = threadIdx.x; b < st.B * st.K; b += blockDim.x) { st.logp_cur[b] = 0.f; st.logp_next[b] = 0.f; }
         if (threadIdx.x < BC_COUNT) st.ctrl[threadIdx.x] = 0;
-        if (threadIdx.x == 0) { st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0; }
+        if (threadIdx.x == 0) {
+            st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
+            st.ctrl[BCX_W] = st.w0; st.ctrl[BCX_ITER] = 0;
+        }
     }
 }
 void launch_beam_init(const BeamState& st, cudaStream_t s) { beam_init_kernel<<<64, 256, 0, s>>>(st); }

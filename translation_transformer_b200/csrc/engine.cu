@@ -135,6 +135,9 @@ struct ttb_engine {
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_key[12] = {};
     long long graph_launches = 0;
+    cudaGraphExec_t beam_graph[2] = {nullptr, nullptr};   // steady-state iteration of the speculative beam search, per ping-pong parity
+    long long beam_graph_key[20] = {};
+    long long beam_graph_launches = 0;
     DevBuf beam;                 // arena of the beam-search state
     DevBuf hist;                 // per-iteration live-query count of the last generate()
     std::vector<int> h_hist;
@@ -825,6 +828,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
 
     BeamState st{};
     st.B = B; st.K = K; st.N = N; st.dl0 = smart ? D_lib : D0; st.V = V; st.smart = smart ? 1 : 0; st.n_lib = n_lib; st.pad = pad; st.bos = bos; st.eos = eos; st.ldw = ldw; st.tie_break = tie_break;
+    st.max_len = max_len;
+    {   // width of the token matrix in the first iteration (the loop below applies the same rule)
+        const int dl_first = std::min(max_len - 2, smart ? D_lib - 1 : D0);
+        st.w0 = 1 + std::max(dl_first + 1, 0);
+    }
     st.cand_cur = (int*)(base + o_cand0); st.cand_next = (int*)(base + o_cand1);
     st.logp_cur = (float*)(base + o_lp0); st.logp_next = (float*)(base + o_lp1);
     st.drafts = e->drafts.as<int>();
@@ -866,6 +874,21 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     ActT* xh = Prec<ActT>::lowp ? e->xh.as<ActT>() : nullptr;
     const int* n_live = st.ctrl + BC_NLIVE_ROWS;
     int W = 1, empty_cols = 0, filled = 1, budget = max_len - filled - 1, dl = smart ? D_lib - 1 : D0, C = B, beam = 1, iters = 0;
+    // CUDA graphs of the steady-state iteration (one per parity), kept across calls while nothing they bake in changes
+    const int dl_steady = dl;
+    // Opt-in (TTB_BEAM_GRAPH=1, read per call): measured neutral on one B200 -- the search is bound by the GPU work of its
+    // 5-20 k token rows, not by the ~33 launches per iteration (63.8 ms per batch launched directly, 64.5 ms replayed, the
+    // graphs being re-captured whenever the padded source length changes), see DESIGN.md §2b.
+    const char* ng = getenv("TTB_BEAM_GRAPH");
+    const bool use_graph = cached && st.host_ctrl && !trace_nacc && !trace_pick && e->prof.mask == 0 && ng && ng[0] == '1';
+    if (use_graph) {
+        const long long key[20] = {B, K, N, D0, Ls, max_len, V, smart ? 1 : 0, pad, bos, eos, c_token, tie_break, e->alloc_signature(),
+                                   (long long)sizeof(ActT), (long long)reinterpret_cast<uintptr_t>(st.host_ctrl), n_dec, 0, 0, 0};
+        if (memcmp(key, e->beam_graph_key, sizeof(key)) != 0) {
+            for (int p = 0; p < 2; ++p) if (e->beam_graph[p]) { cudaGraphExecDestroy(e->beam_graph[p]); e->beam_graph[p] = nullptr; }
+            memcpy(e->beam_graph_key, key, sizeof(key));
+        }
+    }
     int* hc = e->h_ctrl;
     hc[BC_ERROR] = 0;
     while (budget >= 1 && filled <= max_len) {
@@ -873,8 +896,12 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         const int grow = dl + 1 - empty_cols;
         if (grow > 0) W += grow;
         TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
+        // One iteration = a fixed kernel sequence whose arguments depend on (C, beam, dl) and on the ping-pong parity of the
+        // hypothesis / cache buffers only: the width of the token matrix and the iteration number live in device memory
+        // (beam.cu: BCX_W, BCX_ITER), so the steady state (C = B K, full draft length) is replayed as a CUDA graph.
+        auto enqueue_iteration = [&]() -> int {
         const int R = C * N;
-        { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, W, dl, s); }
+        { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, dl, s); }
         if (cached) {
             RowCount rows(R * (dl + 1), n_live, dl + 1);
             { Scope sc(e, KC_EMBED, s); launch_beam_embed_cached<ActT>(st, beam, R, dl, e->tgt_emb, e->pe, E, x, xh, s); }
@@ -912,16 +939,42 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
         }
         { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
-        { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, iters, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, s); }
         // the expand kernel also closes the iteration: its last CTA writes the control words and, last, the iteration's
         // sequence number into pinned host memory; the host reads them while the caches are still being re-parented and
         // enqueues the next iteration behind that
-        st.host_seq = iters + 1;
-        { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, W, dl, logits, s); }
+        { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, dl, logits, s); }
         if (cached) {
             Scope sc(e, KC_CACHE_APPEND, s);
             launch_beam_cache_update<ActT>(st, dl, e->qkv.as<ActT>(), Tc * 3 * E, n_dec, 3 * E, E, kc_cur, vc_cur, kc_next, vc_next,
                                            cache_l_stride, cache_c_stride, s);
+        }
+        return 0;
+        };   // enqueue_iteration
+        const int parity = iters & 1;     // the ping-pong buffers have been swapped `iters` times
+        if (use_graph && C == B * K && beam == K && dl == dl_steady) {
+            if (!e->beam_graph[parity]) {
+                const long long l0 = e->launches;
+                cudaGraph_t graph = nullptr;
+                TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+                const int rc = enqueue_iteration();
+                const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                if (rc || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    if (!rc) set_last_error(std::string("CUDA graph capture of the beam-search iteration failed: ") + cudaGetErrorString(ce));
+                    return 1;
+                }
+                TTB_CUDA_OK(cudaGraphInstantiate(&e->beam_graph[parity], graph, 0));
+                cudaGraphDestroy(graph);
+                e->beam_graph_launches = e->launches - l0;
+                e->launches = l0;   // capturing did not launch anything
+            }
+            TTB_CUDA_OK(cudaGraphLaunch(e->beam_graph[parity], s));
+            e->launches += e->beam_graph_launches;
+        } else if (enqueue_iteration()) {
+            return 1;
+        }
+        if (cached) {
             std::swap(kc_cur, kc_next);
             std::swap(vc_cur, vc_next);
         }
@@ -1165,6 +1218,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->prof.pool) cudaEventDestroy(ev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (int p = 0; p < 2; ++p) if (e->beam_graph[p]) cudaGraphExecDestroy(e->beam_graph[p]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->join_ev) cudaEventDestroy(e->join_ev);
     if (e->t0) cudaEventDestroy(e->t0);

@@ -143,6 +143,7 @@ void launch_greedy_std_step(const GreedyState& st, cudaStream_t s);
 // ---- beam.cu --------------------------------------------------------------------------------------
 struct BeamState {
     int B, K, N, dl0, V, pad, bos, eos, ldw, tie_break;
+    int max_len, w0;                      // length budget of the loop; width of the token matrix in the first iteration
     int* cand_cur; int* cand_next;        // [B*K][ldw] hypotheses (query-major), ping-pong
     float* logp_cur; float* logp_next;    // [B*K]
     const int* drafts;                    // [B][N][dl0]
@@ -152,7 +153,6 @@ struct BeamState {
     // of the chain live list -> front -> token, and everything the attention kernels may read ahead of their dependency wait
     int4* desc_self; int4* desc_cross; const int* src_len;
     int* host_ctrl;   // pinned host mirror of ctrl (device-accessible): BC_COUNT words + a sequence word written last
-    int host_seq;     // value of the sequence word for this iteration
     int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows
     float* topv; int* topi; int* nkeep; float* lmax; float* lsum;      // per (row, position) statistics
     int* trace_nacc; int* trace_pick;     // optional [iter][B*K][N] / [iter][B*K]
@@ -169,7 +169,7 @@ struct BeamState {
 };
 void launch_beam_build_lib(const BeamState& st, cudaStream_t s);
 void launch_beam_init(const BeamState& st, cudaStream_t s);
-void launch_beam_prepare(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
+void launch_beam_prepare(const BeamState& st, int C, int beam, int dl, cudaStream_t s);
 void launch_beam_fill_rows(const BeamState& st, int C, int beam, int W, int dl, cudaStream_t s);
 template <typename ActT>
 void launch_beam_gather(const BeamState& st, const float* x, const ActT* xh, int max_rows, int W, int dl, int E,
@@ -184,8 +184,8 @@ void launch_beam_cache_update(const BeamState& st, int dl, const ActT* qkv_all, 
                               int E, const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
                               long long cache_cand_stride, cudaStream_t s);
 void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, int dl, cudaStream_t s);
-void launch_beam_choose(const BeamState& st, int C, int beam, int dl, int iter, cudaStream_t s);
-void launch_beam_expand(const BeamState& st, int beam, int W, int dl, const float* logits, cudaStream_t s);
+void launch_beam_choose(const BeamState& st, int C, int beam, int dl, cudaStream_t s);
+void launch_beam_expand(const BeamState& st, int beam, int dl, const float* logits, cudaStream_t s);
 void launch_beam_export(const int* cand, int ldw, int R, int W, long long* out, cudaStream_t s);
 // ---- std_beam.cu : standard beam search (standard_decoding.py:90-174) -------------------------------------------
 struct StdBeamState {

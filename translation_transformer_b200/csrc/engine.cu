@@ -1194,7 +1194,9 @@ int ttb_engine_create(const ttb_model_desc* desc, int device, ttb_engine** out) 
     e->device = device;
     if (register_params(e)) { ttb_engine_destroy(e); return 1; }
     TTB_CUDA_OK(cudaMallocHost(&e->h_ctrl, 4 * CTRL_COUNT * sizeof(int)));
-    for (auto& ev : e->poll_ev) TTB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // blocking sync: the decoding loop polls one graph (four iterations, ~1.2 ms) behind the GPU, so a sleeping host thread
+    // costs nothing, and several engines per GPU x several ranks per box do not each burn a core spinning
+    for (auto& ev : e->poll_ev) TTB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
     TTB_CUDA_OK(cudaEventCreate(&e->t0));
     TTB_CUDA_OK(cudaEventCreate(&e->t1));
     TTB_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

@@ -99,6 +99,22 @@ lo, hi = shard_bounds(n, rank, 2)
 all_preds = torch.arange(n * 2 * 5).reshape(n, 2, 5)      # (queries, n_best, max_len)
 out = gather_predictions(all_preds[lo:hi].clone())
 assert torch.equal(out, all_preds), (rank, out)
+# several batches in flight per rank (pipeline.py): worker threads decode, the main thread gathers in batch order,
+# so the collectives of the two ranks stay matched although the batches complete out of order
+import time
+from translation_transformer_b200.pipeline import InFlightDecoder
+class Eng: pass
+class Gen:
+    def __init__(self): self.model = Eng()
+    def generate(self, src):
+        time.sleep(0.001 * int((src[0, 0, 0] * 7 + rank * 3) % 5))
+        return src + 1
+fly = InFlightDecoder([Gen(), Gen(), Gen()], device=None)
+batches = [all_preds[lo:hi].clone() + 100 * i for i in range(9)]
+got = [gather_predictions(o) for o in fly.map(batches)]
+for i, g in enumerate(got):
+    assert torch.equal(g, all_preds + 100 * i + 1), (rank, i)
+fly.close()
 dist.destroy_process_group()
 print("ok", rank)
 """

@@ -34,8 +34,8 @@ from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
 # (kernel class -> bytes); classes without a capture report null
-NCU_TRAFFIC = {"gemm_ffn1": 14.8e6, "gemm_self_out": 12.8e6, "self_attn": 12.9e6, "cross_attn": 7.0e6,
-               "gemm_qkv": 4.6e6}   # profiles/r1i_top_kernels_ncu_full.txt (cold-cache replays: mostly the weight fetch)
+NCU_TRAFFIC = {"gemm_ffn1": 14.76e6, "gemm_self_out": 12.76e6, "self_attn": 13.50e6, "cross_attn": 7.03e6,
+               "gemm_qkv": 4.57e6, "gemm_classifier": 4.32e6}   # profiles/r1k_top_kernels_ncu_full.txt (cold-cache replays: mostly the weight fetch)
 
 PAD, BOS, EOS, REPLACE = 0, 1, 2, 7   # REPLACE plays the role of the "c" token (lightning_model.py:117)
 METRIC = "SMILES/sec (greedy speculative, product prediction)"

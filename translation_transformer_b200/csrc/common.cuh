@@ -57,8 +57,15 @@ constexpr int kNumSMs = 148;  // B200
 // allocation, descriptor prefetch) and then blocks in pdl_wait() until the predecessor has completed
 // and its writes are visible.  Rule: no global-memory access that depends on (or could disturb) an
 // earlier kernel before pdl_wait().  Both instructions are no-ops for a plain launch.
+#ifdef TTB_PDL_AFTER_WAIT
+// A/B build (scripts/build_variant.sh): a kernel releases its dependents only once its own dependency is satisfied, so at
+// most ONE successor waits on the SMs instead of the whole downstream chain cascading ahead
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 bool pdl_enabled();   // engine.cu: TTB_NO_PDL=1 switches the attribute off (A/B comparisons)
 
 template <typename... KArgs, typename... Args>

@@ -42,6 +42,25 @@ def test_make_drafts_matches_reference_golden(dev):
         assert np.array_equal(d.cpu().numpy(), dz[f"d{c['id']}"].astype(np.int64)), c
 
 
+def test_make_drafts_reference_test_grid_vs_oracle(dev):
+    """All 1008 size combinations of the reference's own test (tests/test_drafting.py:19-61) on its source file: requested
+    shape (what the reference asserts) and bit-exact agreement with the oracle."""
+    from oracle.drafting import make_drafts as oracle_drafts
+    from test_oracle_golden import REF_GRID_AMOUNTS, REF_GRID_BATCHES, REF_GRID_LENGTHS
+    from translation_transformer_b200.utils.drafting import make_drafts
+    meta = load_json("model_forward.json")
+    tk, src, _ = test_file_sources(meta["vocab"])
+    src_d = src.to(dev)
+    eos, pad, rep = tk.eos_token_idx, tk.pad_token_idx, tk.encoder_dict["c"]
+    for B in REF_GRID_BATCHES:
+        for n_drafts in REF_GRID_LENGTHS:
+            for draft_len in REF_GRID_AMOUNTS:
+                got = make_drafts(src_d[:B], draft_len, n_drafts, 1, 200, eos, pad, rep)
+                assert tuple(got.shape) == (min(B, src.shape[0]), n_drafts, draft_len)
+                ref = oracle_drafts(src[:B].numpy(), draft_len, n_drafts, 1, 200, eos, pad, rep)
+                assert np.array_equal(got.cpu().numpy(), ref), (B, n_drafts, draft_len)
+
+
 def test_make_drafts_argument_checks(dev):
     from translation_transformer_b200.utils.drafting import make_drafts
     s = torch.tensor([[5, 6, 7, 2, 0]], device=dev)

@@ -53,6 +53,27 @@ def test_make_drafts_matches_reference():
         assert np.array_equal(d, dz[f"d{c['id']}"].astype(np.int64)), c
 
 
+# the reference's own test of this function (tests/test_drafting.py:19-61): every combination of these sizes on the
+# sources of tests/product_prediction_src_test.txt must give drafts of the requested shape
+REF_GRID_LENGTHS = [1, 2, 3, 4, 5, 8, 10, 15, 25, 35, 50, 80, 100, 200]
+REF_GRID_AMOUNTS = [1, 2, 3, 5, 10, 15, 25, 35, 50, 80, 100, 200]
+REF_GRID_BATCHES = [1, 2, 3, 4, 5, 10]
+
+
+def test_make_drafts_reference_test_grid():
+    meta = load_json("model_forward.json")
+    tk, src, _ = test_file_sources(meta["vocab"])
+    src = src.numpy()
+    n = 0
+    for B in REF_GRID_BATCHES:
+        for n_drafts in REF_GRID_LENGTHS:         # the reference unpacks its product as (batch, n_drafts, draft_len)
+            for draft_len in REF_GRID_AMOUNTS:
+                d = make_drafts(src[:B], draft_len, n_drafts, 1, 200, tk.eos_token_idx, tk.pad_token_idx, tk.encoder_dict["c"])
+                assert d.shape == (min(B, src.shape[0]), n_drafts, draft_len)
+                n += 1
+    assert n == 1008
+
+
 def test_make_drafts_argument_checks():
     s = np.array([[5, 6, 7, 2, 0]])
     with pytest.raises(AssertionError):

@@ -422,15 +422,9 @@ attn_mma_kernel(Params p) {
 
 static void launch(const Params& p, int heads, int head_dim, int n_groups_max, cudaStream_t s) {
     dim3 grid(heads, n_groups_max, (p.Lq + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-    static const bool attr_ok = [] {
-        return cudaFuncSetAttribute(attn_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16>()) == cudaSuccess &&
-               cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32>()) == cudaSuccess &&
-               cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()) == cudaSuccess;
-    }();
-    (void)attr_ok;
-    if (head_dim == 16) launch_pdl(attn_mma_kernel<16>, grid, dim3(THREADS), smem_bytes<16>(), s, p);
-    else if (head_dim == 32) launch_pdl(attn_mma_kernel<32>, grid, dim3(THREADS), smem_bytes<32>(), s, p);
-    else if (head_dim == 64) launch_pdl(attn_mma_kernel<64>, grid, dim3(THREADS), smem_bytes<64>(), s, p);
+    if (head_dim == 16) { if (!ensure_dyn_smem(attn_mma_kernel<16>, (int)smem_bytes<16>())) launch_pdl(attn_mma_kernel<16>, grid, dim3(THREADS), smem_bytes<16>(), s, p); }
+    else if (head_dim == 32) { if (!ensure_dyn_smem(attn_mma_kernel<32>, (int)smem_bytes<32>())) launch_pdl(attn_mma_kernel<32>, grid, dim3(THREADS), smem_bytes<32>(), s, p); }
+    else if (head_dim == 64) { if (!ensure_dyn_smem(attn_mma_kernel<64>, (int)smem_bytes<64>())) launch_pdl(attn_mma_kernel<64>, grid, dim3(THREADS), smem_bytes<64>(), s, p); }
 }
 }  // namespace amma
 

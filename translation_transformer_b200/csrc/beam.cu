@@ -590,11 +590,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
 }
 void launch_beam_expand(const BeamState& st, int beam, int dl, const float* logits, cudaStream_t s) {
     const size_t smem = ((size_t)beam * (dl + 1) * st.K + (size_t)beam * (dl + 2)) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(beam_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (ensure_dyn_smem(beam_expand_kernel, (int)smem)) return;   // error recorded; the launch below fails and cudaGetLastError reports it
     launch_pdl(beam_expand_kernel, dim3(st.B), dim3(256), smem, s, st, beam, dl, logits);
 }
 

@@ -68,6 +68,14 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 #endif
 bool pdl_enabled();   // engine.cu: TTB_NO_PDL=1 switches the attribute off (A/B comparisons)
 
+// Opt-in of `kernel` to `bytes` of dynamic shared memory on the CURRENT device, once per (device, kernel) and for the
+// largest size asked so far.  The attribute is per device and engines of several devices / host threads share the
+// process, so the bookkeeping is a mutex-protected table keyed by (device, kernel) (engine.cu).  Returns 0 or an error
+// code after set_last_error().
+int ensure_dyn_smem(const void* kernel, int bytes);
+template <typename... KArgs>
+inline int ensure_dyn_smem(void (*kernel)(KArgs...), int bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg{};

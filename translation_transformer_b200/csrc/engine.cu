@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,25 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
+
+int ensure_dyn_smem(const void* kernel, int bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> granted;
+    int dev = 0;
+    TTB_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int& have = granted[{dev, kernel}];
+    if (bytes <= have) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_last_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize, ") + std::to_string(bytes) + ") failed on device " +
+                       std::to_string(dev) + ": " + cudaGetErrorString(e));
+        return 1;
+    }
+    have = bytes;
+    return 0;
+}
 
 bool pdl_enabled() {
     static const bool on = [] { const char* v = getenv("TTB_NO_PDL"); return !(v && v[0] == '1'); }();
@@ -1326,6 +1346,18 @@ int ttb_make_drafts(const int64_t* src_dev, int64_t src_ld, int32_t B, int32_t L
 
 #define TTB_DISPATCH(e, call_f32, call_bf16) ((e)->d.precision == TTB_PRECISION_FP32 ? (call_f32) : (call_bf16))
 
+// Every exit of a decoding loop leaves the engine's stream drained: kernels still queued there write to the caller's
+// `out` / `trace` buffers, which the caller is free to release as soon as the call returns (error exits included).
+static int drained(ttb_engine* e, int rc) {
+    if (rc != 0 && e->stream) {
+        const std::string keep = g_last_error;
+        cudaStreamSynchronize(e->stream);
+        (void)cudaGetLastError();
+        g_last_error = keep;
+    }
+    return rc;
+}
+
 int ttb_encode_src(ttb_engine* e, const int64_t* src_dev, const uint8_t* src_pad_mask_dev, int32_t B,
                    int32_t Ls, float* memory_out_dev, void* stream) {
     TTB_CHECK(e && e->finalized, "engine not finalized");
@@ -1362,10 +1394,10 @@ int ttb_greedy_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32
     TTB_CHECK(Ls <= e->d.max_positions && max_len + draft_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
     TTB_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
+    return drained(e, TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
                                              replace_token, tie_break, out_dev, trace_dev, stats, s),
                         greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, draft_len, n_drafts, pad_token, bos_token, eos_token,
-                                                  replace_token, tie_break, out_dev, trace_dev, stats, s));
+                                                  replace_token, tie_break, out_dev, trace_dev, stats, s)));
 }
 
 int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t pad_token,
@@ -1375,8 +1407,8 @@ int ttb_greedy_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_
     TTB_CHECK(Ls <= e->d.max_positions && max_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
     TTB_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true),
-                        greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true));
+    return drained(e, TTB_DISPATCH(e, greedy_api<float>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true),
+                        greedy_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, 0, 1, pad_token, bos_token, eos_token, -1, 1, out_dev, nullptr, stats, s, true)));
 }
 
 int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len, int32_t beam_size,
@@ -1389,8 +1421,8 @@ int ttb_beam_search_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, i
     TTB_CHECK(Ls <= e->d.max_positions && max_len + 2 <= e->d.max_positions, "sequence longer than the positional table");
     TTB_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return TTB_DISPATCH(e, std_beam_api<float>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s),
-                        std_beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s));
+    return drained(e, TTB_DISPATCH(e, std_beam_api<float>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s),
+                        std_beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, beam_size, pad_token, bos_token, eos_token, out_dev, out_width, stats, s)));
 }
 
 int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t B, int32_t Ls, int32_t max_len,
@@ -1409,12 +1441,12 @@ int ttb_beam_speculative_generate(ttb_engine* e, const int64_t* src_dev, int32_t
     TTB_CHECK(e->d.tgt_vocab_size <= 1024, "vocabularies above 1024 tokens are not supported by the beam statistics kernel");
     TTB_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return TTB_DISPATCH(e, beam_api<float>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token, eos_token,
+    return drained(e, TTB_DISPATCH(e, beam_api<float>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token, eos_token,
                                            c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s,
                                            smart_drafts_mode != 0),
                         beam_api<__nv_bfloat16>(e, src_dev, B, Ls, max_len, n_best, draft_len, n_drafts, pad_token, bos_token,
                                                 eos_token, c_token, tie_break, out_dev, out_width, trace_nacc_dev, trace_pick_dev, stats, s,
-                                                smart_drafts_mode != 0));
+                                                smart_drafts_mode != 0)));
 }
 
 int ttb_kernel_class_count(void) { return KC_COUNT; }

@@ -14,6 +14,7 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -2198,15 +2199,7 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
         static const bool pair_off = [] { const char* v = getenv("TTB_GEMM_PAIR"); return v && v[0] == '0'; }();
         const int chunks = N % 384 == 0 ? 3 : (N % 256 == 0 && N >= 512 ? 2 : 0);
         if (!pair_off && K == 256 && chunks && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && rows.max_rows >= 1024) {
-            static bool attr = false;
-            if (!attr) {
-                cudaError_t e = cudaFuncSetAttribute(gemm_pair_k256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pgk::SMEM);
-                if (e != cudaSuccess) {
-                    set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-                    return 1;
-                }
-                attr = true;
-            }
+            if (int rc = ensure_dyn_smem(gemm_pair_k256_kernel, pgk::SMEM)) return rc;
             CUtensorMap tmWh, tmC;
             if (int rc = get_tensor_map(W, N, K, K, 64, &tmWh)) return rc;
             if (int rc = get_tensor_map(C, rows.max_rows, N, ldc, BM, &tmC)) return rc;
@@ -2218,7 +2211,6 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
     }
     if (int rc = get_tensor_map(W, N, K, K, BN, &tmB)) return rc;
     static const bool use_v1 = [] { const char* v = getenv("TTB_GEMM_V1"); return v && v[0] == '1'; }();
-    constexpr int which = std::is_same<OutT, float>::value ? 0 : 1;
     if (!use_v1) {
         // narrow GEMMs (N <= 256 at full batch) get 64-column tiles so that every SM owns more than one
         // tile and the epilogue/main-loop overlap of the persistent kernel has something to overlap
@@ -2228,31 +2220,15 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
         if (int rc = get_tensor_map(W, N, K, K, bn, &tmB)) return rc;
         const int max_tiles = ((N + bn - 1) / bn) * ((rows.max_rows + BM - 1) / BM);
         const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-        static bool pattr_set[2][2] = {{false, false}, {false, false}};
-        auto launch = [&](auto kernel, int smem, bool& flag) -> int {
-            if (!flag) {
-                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (e != cudaSuccess) {
-                    set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-                    return 1;
-                }
-                flag = true;
-            }
+        auto launch = [&](auto kernel, int smem) -> int {
+            if (int rc = ensure_dyn_smem(kernel, smem)) return rc;
             launch_pdl(kernel, dim3(grid), dim3(pers::THREADS), (size_t)smem, s, tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
             return 0;
         };
-        if (narrow) return launch(gemm_bf16_tc_persistent_kernel<OutT, 64>, pers::smem_bytes<OutT, 64>(), pattr_set[which][0]);
-        return launch(gemm_bf16_tc_persistent_kernel<OutT, 128>, pers::smem_bytes<OutT, 128>(), pattr_set[which][1]);
+        if (narrow) return launch(gemm_bf16_tc_persistent_kernel<OutT, 64>, pers::smem_bytes<OutT, 64>());
+        return launch(gemm_bf16_tc_persistent_kernel<OutT, 128>, pers::smem_bytes<OutT, 128>());
     }
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[which]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set[which] = true;
-    }
+    if (int rc = ensure_dyn_smem(gemm_bf16_tc_kernel<OutT>, SMEM_BYTES)) return rc;
     dim3 grid((N + BN - 1) / BN, (rows.max_rows + BM - 1) / BM);
     gemm_bf16_tc_kernel<OutT><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, bias, C, ldc, rows, N, K, relu ? 1 : 0);
     return 0;
@@ -2272,15 +2248,7 @@ int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat1
     const int tail_rows = V_pad % 128 ? V_pad % 128 : 128;
     if (int rc = get_tensor_map(W, V, K, K, V_pad >= 128 ? 128 : tail_rows, &tmW)) return rc;
     if (int rc = get_tensor_map(W, V, K, K, tail_rows, &tmWtail)) return rc;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(classifier_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) {
-            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-            return 1;
-        }
-        attr_smem = smem;
-    }
+    if (int rc = ensure_dyn_smem(classifier_argmax_kernel, smem)) return rc;
     const int tiles = (rows.max_rows + BM - 1) / BM;
     launch_pdl(classifier_argmax_kernel, dim3(tiles), dim3(cls::THREADS), (size_t)smem, s, tmA, tmW, tmWtail, bias, pred, rows, V, V_pad, KB);
     return 0;
@@ -2288,9 +2256,15 @@ int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat1
 
 // Number of co-resident clusters of the CTA-pair kernel (0: not usable); TTB_FFN_PAIR=0/1 forces the choice.
 static int ffn_pair_clusters() {
-    static int max_clusters = -1;
+    // per device (the opt-in and the occupancy answer are properties of the device); slots are written once each
+    static std::atomic<int> per_device[64];
+    static std::once_flag init;
+    std::call_once(init, [] { for (auto& v : per_device) v.store(-1); });
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    int max_clusters = per_device[dev].load();
     if (max_clusters < 0) {
-        cudaError_t e = cudaFuncSetAttribute(tc::ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ffn::SMEM);
+        cudaError_t e = ensure_dyn_smem(tc::ffn_pair_kernel, tc::ffn::SMEM) ? cudaErrorInvalidValue : cudaSuccess;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(4 * kNumSMs);
         cfg.blockDim = dim3(tc::ffn::THREADS);
@@ -2299,7 +2273,8 @@ static int ffn_pair_clusters() {
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, tc::ffn_pair_kernel, &cfg);
         max_clusters = e == cudaSuccess ? n : 0;
         (void)cudaGetLastError();
-        if (getenv("TTB_DEBUG")) fprintf(stderr, "[ttb] ffn_pair_kernel: %d co-resident clusters of 4 (%s)\n", max_clusters, cudaGetErrorString(e));
+        if (getenv("TTB_DEBUG")) fprintf(stderr, "[ttb] ffn_pair_kernel: %d co-resident clusters of 4 on device %d (%s)\n", max_clusters, dev, cudaGetErrorString(e));
+        per_device[dev].store(max_clusters);
     }
     return max_clusters;
 }
@@ -2334,15 +2309,7 @@ int launch_ffn_fused(__nv_bfloat16* xh, const __nv_bfloat16* W1, const float* bi
     if (int rc = get_tensor_map(W1, F, 256, 256, 128, &tmW1)) return rc;
     if (int rc = get_tensor_map(W2, 256, F, F, 128, &tmW2)) return rc;
     if (int rc = get_tensor_map(x, rows.max_rows, 256, 256, BM, &tmX, true)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn::SMEM);
-        if (e != cudaSuccess) {
-            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem(ffn_fused_kernel, ffn::SMEM)) return rc;
     const int tiles = (rows.max_rows + BM - 1) / BM;
 #ifdef TTB_FFN_TIMELINE
     {
@@ -2409,15 +2376,7 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
         if (int rc = get_tensor_map(W2, 256, 256, 256, lnk::BNL, &tmW2)) return rc;
         if (int rc = get_tensor_map(q2, rows.max_rows, 256, 256, BM, &tmQ)) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_resid_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lnk::SMEM);
-        if (e != cudaSuccess) {
-            set_last_error(std::string("cudaFuncSetAttribute(smem) failed: ") + cudaGetErrorString(e));
-            return 1;
-        }
-        attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem(gemm_resid_ln_kernel, lnk::SMEM)) return rc;
     const int tiles = (rows.max_rows + BM - 1) / BM;
 #ifdef TTB_LNK_TIMELINE
     {

@@ -342,11 +342,7 @@ void launch_greedy_accept(const GreedyState& st, cudaStream_t s) {
     const size_t gen_ints = (size_t)st.B * st.gen_ld;
     const int stage_gen = base_ints + gen_ints <= (size_t)ACCEPT_MAX_SMEM_INTS ? 1 : 0;
     const size_t smem = (base_ints + (stage_gen ? gen_ints : 0)) * sizeof(int);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-        cudaFuncSetAttribute(greedy_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ACCEPT_MAX_SMEM_INTS * sizeof(int)));
-        attr_smem = ACCEPT_MAX_SMEM_INTS * sizeof(int);
-    }
+    if (smem > 48 * 1024 && ensure_dyn_smem(greedy_accept_kernel, (int)(ACCEPT_MAX_SMEM_INTS * sizeof(int)))) return;   // the launch below then fails loudly
 #ifdef TTB_ACC_TIMELINE
     {
         static int n_launch = 0;

@@ -128,11 +128,7 @@ __global__ void __launch_bounds__(256) sbeam_select_kernel(StdBeamState st, int 
 int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s) {
     const size_t smem = (size_t)beam * st.V * sizeof(VF);
     if (smem > 200 * 1024) return -1;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(sbeam_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = 200 * 1024;
-    }
+    if (smem > 48 * 1024 && ensure_dyn_smem(sbeam_select_kernel, 200 * 1024)) return 1;
     sbeam_select_kernel<<<st.B, 256, smem, s>>>(st, beam, W);
     return 0;
 }

@@ -29,7 +29,7 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
                  beam_size: int = 0, max_len: int = 0, n_drafts: int = 0, draft_len: int = 0, smart_drafts_mode: bool = True,
                  report_prediction_time: bool = True, report_prediction_file: str | None = None,
                  state_dict: dict | None = None, precision: str = "bf16", device: int = 0, seed: int = 0,
-                 batches_in_flight: int = 1, **_unused):
+                 batches_in_flight: int = 1, tgt_test_path: str | None = None, **_unused):
         if _Base is not object:
             super().__init__()
         assert src_tokenizer is not None, "source tokenizer not provided"
@@ -57,6 +57,9 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         self.device_index = device
         self.prediction_start_time = None
         self.batch_size = None
+        # the reference reads both from `self.trainer.datamodule` (lightning_model.py:223-224); without a Lightning trainer
+        # they come from the constructor / the first batch
+        self.tgt_test_path = tgt_test_path
 
     def load_checkpoint_state_dict(self, state_dict: dict) -> None:
         """Accepts the `state_dict` of a reference Lightning checkpoint (keys prefixed `model.`)."""
@@ -116,11 +119,21 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         elapsed = datetime.timedelta(seconds=timer() - self.prediction_start_time)
         n_calls = self._counter("model_calls_num")
         calls = max(n_calls, 1)
-        report = {"algorithm": self.generation, "batch_size": self.batch_size, "max_len": self.max_len,
+        batch_size, tgt_test_path = self.batch_size, self.tgt_test_path
+        dm = getattr(getattr(self, "_trainer", None), "datamodule", None)   # under a Lightning trainer: same sources as the reference
+        if dm is not None:
+            batch_size = getattr(dm, "batch_size", batch_size)
+            tgt_test_path = getattr(dm, "tgt_test_path", tgt_test_path)
+        # keys and their order as in lightning_model.py:221-235
+        report = {"algorithm": self.generation, "batch_size": batch_size, "tgt_test_path": str(tgt_test_path), "max_len": self.max_len,
                   "total_seconds": round(elapsed.total_seconds(), 4), "model_calls": n_calls,
                   "seconds_per_model_call": round(elapsed.total_seconds() / calls, 4)}
         if self.generation in ("greedy_speculative", "beam_search_speculative"):
             report["n_drafts"], report["draft_len"] = self.n_drafts, self.draft_len
+            if self.generation == "beam_search_speculative":
+                accepted = self._counter("accepted_tokens_num")
+                report["accepted_tokens"] = accepted
+                report["acceptance_rate"] = round(accepted / max(self._counter("produced_non_pad_tokens"), 1), 4)
         report = json.dumps(report)
         print(report)
         if self.report_prediction_file is not None:

@@ -55,6 +55,12 @@ class InFlightDecoder:
                 if post is not None:
                     out = post(out)
                 s.synchronize()
+            # the result was allocated on this worker's side stream but is consumed on the caller's stream: tell the
+            # caching allocator, so that the block is not handed to the next generate() of this worker while kernels
+            # of the consumer that read it are still queued
+            for t in (out if isinstance(out, (tuple, list)) else (out,)):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(torch.cuda.current_stream(self.device))
             return out
         finally:
             self._free.put((g, s))

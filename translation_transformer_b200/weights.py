@@ -121,6 +121,80 @@ def random_init_state_dict(cfg: ModelConfig, seed: int) -> dict:
     return sd
 
 
+def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.04, damp: float = 0.05, sharpness: float = 60.0,
+                         gain: float = 8.0, alpha: float = 0.05, pad_bias: float = -5.0) -> dict:
+    """Synthetic stand-in for a TRAINED reaction model (checkpoints are not available offline): the random-init weights
+    of `random_init_state_dict(cfg, seed)` with a deterministic "copy circuit" laid over them, so that the model behaves
+    like the trained Molecular Transformer does on USPTO data in the respects that drive the decoding loops:
+
+    * the prediction is (mostly) a copy of the source: position p of the target attends to source position p + 1 through
+      a purely positional cross-attention in the last decoder layer (queries = the sinusoidal code rotated by one
+      position, keys = the code itself, read from the first `head_dim` embedding dimensions, which the token embedding
+      leaves free) and the classifier reads the copied token embedding.  Source windows therefore make good drafts
+      (several accepted tokens per decoder call) and a query ends when the copy reaches the source's EOS, i.e. target
+      lengths follow the source lengths (ragged finish times, retirement and compaction of the batch);
+    * it is imperfect in a deterministic way: a fraction `mismatch` of the vocabulary is predicted as a different token
+      (a fixed permutation) and the positional attention is off by one for a few percent of the positions, so drafts
+      are rejected at realistic rates; the logit margins stay healthy (like a trained model's), so a bf16 forward pass
+      reproduces the fp32 token sequence except at genuine near-ties;
+    * every other matrix keeps its random-init values (the sub-layer output projections scaled by `damp`, so that the
+      residual stream carries token + position through the stack); the arithmetic per decoder call is exactly that of
+      any other weight set of the architecture.
+
+    The state dict loads into the reference's `VanillaTransformer` unchanged (tests/golden/make_golden_bench.py)."""
+    sd = {k: v.clone() for k, v in random_init_state_dict(cfg, seed).items()}
+    g = torch.Generator().manual_seed(seed + 77)
+    E, H, V = cfg.embedding_dim, cfg.num_heads, cfg.tgt_vocab_size
+    HD = E // H
+    assert cfg.share_embeddings and cfg.src_vocab_size == V and H >= 2 and HD % 2 == 0
+    emb = sd["src_token_featurizer.embedding.weight"]
+    emb[:, :HD] = 0                                   # dimensions [0, HD) carry the positional code alone
+    sd["tgt_token_featurizer.embedding.weight"] = emb
+    for k in sd:
+        if k.endswith("out_proj.weight") or k.endswith("linear2.weight") or k.endswith("linear2.bias"):
+            sd[k] *= damp
+    perm = torch.arange(V)                            # token the model emits for a copied source token
+    body = torch.arange(4, V)
+    n_mis = int(round(mismatch * len(body)))
+    if n_mis >= 2:
+        pick = body[torch.randperm(len(body), generator=g)[:n_mis]]
+        perm[pick] = pick.roll(1)
+    Wc = torch.zeros(V, E)
+    Wc[perm] = alpha * emb
+    sd["next_token_classifier.weight"] = Wc
+    sd["next_token_classifier.bias"][cfg.tgt_pad_token_idx] += pad_bias
+    sd["next_token_classifier.bias"][1] += 2.0 * pad_bias    # BOS is never predicted (a trained model does not either)
+    p = f"transformer.decoder.layers.{cfg.num_decoder_layers - 1}.multihead_attn"
+    Win = torch.zeros(3 * E, E)
+    omega = torch.exp(torch.arange(0, E, 2).float() * (-math.log(10000.0) / E))[:HD // 2]
+    R = torch.zeros(HD, HD)                           # code(p + 1) = R code(p)
+    for i in range(HD // 2):
+        c, s_ = math.cos(float(omega[i])), math.sin(float(omega[i]))
+        R[2 * i, 2 * i], R[2 * i, 2 * i + 1] = c, s_
+        R[2 * i + 1, 2 * i], R[2 * i + 1, 2 * i + 1] = -s_, c
+    # LayerNorm subtracts the mean over all E dimensions, which the slow (nearly constant) cosine dimensions of the code
+    # push to mu0 > 0; the projection biases add it back so that queries and keys see the plain sinusoidal code
+    pe_mid = [math.sin(40.0 * float(w)) for w in torch.exp(torch.arange(0, E, 2).double() * (-math.log(10000.0) / E))] + \
+             [math.cos(40.0 * float(w)) for w in torch.exp(torch.arange(0, E, 2).double() * (-math.log(10000.0) / E))]
+    mu0 = sum(pe_mid) / E
+    sigma0 = math.sqrt((E - HD) / E + sum(v * v for v in pe_mid) / E - mu0 * mu0)
+    shift = torch.full((HD,), mu0 / sigma0)
+    Bin = torch.zeros(3 * E)
+    Wo = torch.zeros(E, E)
+    for h in range(H):
+        Win[h * HD:(h + 1) * HD, :HD] = sharpness * R
+        Bin[h * HD:(h + 1) * HD] = sharpness * (R @ shift)
+        Win[E + h * HD:E + (h + 1) * HD, :HD] = torch.eye(HD)
+        Bin[E + h * HD:E + (h + 1) * HD] = shift
+        if h < H - 1:                                 # head h carries embedding dimensions [HD (h + 1), HD (h + 2))
+            Win[2 * E + h * HD:2 * E + (h + 1) * HD, HD * (h + 1):HD * (h + 2)] = torch.eye(HD)
+            Wo[HD * (h + 1):HD * (h + 2), h * HD:(h + 1) * HD] = gain * torch.eye(HD)
+    sd[p + ".in_proj_weight"] = Win
+    sd[p + ".in_proj_bias"] = Bin
+    sd[p + ".out_proj.weight"] = Wo
+    return sd
+
+
 def state_dict_checksum(sd: dict) -> float:
     """Order-independent fingerprint used by the golden fixtures to detect RNG drift."""
     tot = 0.0

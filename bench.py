@@ -1,15 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: speculative greedy decoding, product-prediction Molecular Transformer.
+"""Benchmark of the hot path: the Molecular Transformer driven by the speculative decoding loops.
 
-    python bench.py --gpus N --steps K --warmup W            (our arm: libttb200 on B200)
-    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU port of the reference)
+    python bench.py --gpus N --steps K --warmup W              our arm: libttb200 on B200 (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...    reference arm: the reference's own PyTorch code on the host cores
 
-One "step" = one batch of `--batch-size` synthetic USPTO-MIT-shape queries decoded to completion
-through `TranslationInferenceGreedySpeculative.generate` (BASELINE.json configs[1]).  The K timed steps are
-decoded with `--in-flight` (default 3) batches at a time per GPU, each on its own engine and stream
-(pipeline.py; same predictions, batches are independent); the strictly sequential figure is reported
-beside it as `one_batch_in_flight`.  Multi-GPU runs
-shard the queries (each rank decodes its own batches, weak scaling) and all-gather the predictions.
+Workloads (`--workload`, BASELINE.json configs[1..3]); one "step" = one batch of synthetic queries decoded to completion
+through the public generator classes (`TranslationInferenceGreedySpeculative.generate` / `...BeamSearchSpeculative.generate`):
+
+    greedy  product prediction, greedy speculative, bs 32, draft_len 10, n_drafts 23, max_len 200        (configs[1], default)
+    beam    product prediction, speculative beam search, bs 4, n_best 5, draft_len 10, n_drafts 23       (configs[2])
+    retro   single-step retrosynthesis (6+6 layers), speculative beam search, bs 8, n_best 10, draft_len 10, n_drafts 2
+            (configs[3]; scripts/single_step_retrosynthesis.sh:166-174), USPTO-50k-shape sources
+
+Weights (`--weights`): `copy` (default) = random-init weights with the deterministic copy circuit of
+`weights.copy_task_state_dict` laid over them, a stand-in for a TRAINED model (no checkpoints offline): predictions
+follow the source, drafts are accepted at realistic rates, every query ends with EOS at its own length, so batches
+retire query by query; `random` = plain random init (round-1 headline: nothing ever finishes, every batch decodes 32
+queries to the width limit and returns all-PAD rows: the worst case).  The default line reports both (the second as
+`random_init_worst_case`) and, on one GPU, the beam / retro workloads as `workloads`.
+
+The timed batches are drawn from ONE queue shared by all ranks and in-flight engines (`distributed.BatchQueue`): nobody
+owns a static shard.  `--scaling weak` (default) times N*K batches on N GPUs, `--scaling strong` a fixed set of
+`--queries` queries whatever N is.  Every GPU output is checked: against the reference goldens of the same batch
+(tests/golden/bench_configs.npz) and against the reference run live on the host for a few queries (`parity`).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -24,21 +37,32 @@ import threading
 import time
 from pathlib import Path
 
+import numpy as np
 import torch
 
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
 from translation_transformer_b200.synthetic import synthetic_sources  # noqa: E402
-from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, random_init_state_dict  # noqa: E402
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-# (kernel class -> bytes); classes without a capture report null
-NCU_TRAFFIC = {"gemm_ffn1": 14.76e6, "gemm_self_out": 12.76e6, "self_attn": 13.50e6, "cross_attn": 7.03e6,
-               "gemm_qkv": 4.57e6, "gemm_classifier": 4.32e6}   # profiles/r1k_top_kernels_ncu_full.txt (cold-cache replays: mostly the weight fetch)
+from translation_transformer_b200.weights import (ModelConfig, PRODUCT_PREDICTION, SINGLE_STEP_RETRO, copy_task_state_dict,  # noqa: E402
+                                                  random_init_state_dict)
 
 PAD, BOS, EOS, REPLACE = 0, 1, 2, 7   # REPLACE plays the role of the "c" token (lightning_model.py:117)
-METRIC = "SMILES/sec (greedy speculative, product prediction)"
+RETRO_SRC = dict(mean_len=45.0, std_len=15.0, min_len=12, max_len=150)
+WORKLOADS = {
+    "greedy": dict(kind="greedy", arch="product", bs=32, draft_len=10, n_drafts=23, src_seed=100003, src_kw={}, draw=32,
+                   golden={"copy": "cfg1_copy", "random": "cfg1_random"},
+                   metric="SMILES/sec (greedy speculative, product prediction)",
+                   name="product-prediction greedy speculative bs=32 draft_len=10 n_drafts=23 (BASELINE.json configs[1])"),
+    "beam": dict(kind="beam", arch="product", bs=4, n_best=5, draft_len=10, n_drafts=23, src_seed=100003, src_kw={}, draw=32,
+                 golden={"copy": "cfg2_copy"}, metric="SMILES/sec (beam-search speculative, product prediction)",
+                 name="product-prediction speculative beam search bs=4 n_best=5 draft_len=10 n_drafts=23 (BASELINE.json configs[2])"),
+    "retro": dict(kind="beam", arch="retro", bs=8, n_best=10, draft_len=10, n_drafts=2, src_seed=200003, src_kw=RETRO_SRC, draw=8,
+                  golden={"copy": "cfg3_copy"}, metric="SMILES/sec (beam-search speculative, single-step retrosynthesis)",
+                  name="single-step retrosynthesis (6+6 layers) speculative beam search bs=8 n_best=10 draft_len=10 n_drafts=2 "
+                       "(BASELINE.json configs[3]; scripts/single_step_retrosynthesis.sh:166-174)"),
+}
+ARCH = {"product": PRODUCT_PREDICTION, "retro": SINGLE_STEP_RETRO}
 
 
 def parse():
@@ -47,48 +71,96 @@ def parse():
     ap.add_argument("--steps", type=int, default=18)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="greedy", choices=list(WORKLOADS))
+    ap.add_argument("--weights", default="copy", choices=["copy", "random"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--queries", type=int, default=4096, help="size of the fixed query set of --scaling strong")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch-size", type=int, default=32)
-    ap.add_argument("--draft-len", type=int, default=10)
-    ap.add_argument("--n-drafts", type=int, default=23)
     ap.add_argument("--max-len", type=int, default=200)
     ap.add_argument("--vocab", type=int, default=288)
     ap.add_argument("--seed", type=int, default=1234)
-    ap.add_argument("--eos-bias", type=float, default=0.0, help="added to the classifier bias of EOS (0 = plain random init)")
-    ap.add_argument("--pad-bias", type=float, default=0.0)
-    ap.add_argument("--cpu-queries", type=int, default=2, help="queries per CPU-baseline sample (about 6 s of host time each)")
+    ap.add_argument("--cpu-queries", type=int, default=2, help="queries of the live CPU parity / baseline sample; --impl reference: > 2 fixes the per-step sample, otherwise it is sized to a ~3 minute run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-insitu", action="store_true", help="skip the extra CUPTI-profiled step (kernels_in_situ)")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="only the selected workload (no random-init / beam / retro side figures)")
     ap.add_argument("--tie-break", default="torch_cpu", choices=["torch_cpu", "lowest_index"])
     ap.add_argument("--in-flight", type=int, default=3,
-                    help="bs=32 batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
+                    help="batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
                          "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
 
 
-def build_weights(args):
-    cfg = ModelConfig(src_vocab_size=args.vocab, tgt_vocab_size=args.vocab, **PRODUCT_PREDICTION)
-    sd = {k: v.clone() for k, v in random_init_state_dict(cfg, args.seed).items()}
-    sd["tgt_token_featurizer.embedding.weight"] = sd["src_token_featurizer.embedding.weight"]
-    sd["next_token_classifier.bias"][EOS] += args.eos_bias
-    sd["next_token_classifier.bias"][PAD] += args.pad_bias
-    return cfg, sd
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """One of WORKLOADS with a weight set: configuration, weights and the synthetic batches."""
+
+    def __init__(self, key, weights, args):
+        self.key, self.weights, self.args = key, weights, args
+        self.w = WORKLOADS[key]
+        self.kind, self.bs = self.w["kind"], self.w["bs"]
+        self.cfg = ModelConfig(src_vocab_size=args.vocab, tgt_vocab_size=args.vocab, **ARCH[self.w["arch"]])
+        if weights == "copy":
+            self.sd = copy_task_state_dict(self.cfg, args.seed)
+        else:
+            self.sd = {k: v.clone() for k, v in random_init_state_dict(self.cfg, args.seed).items()}
+            self.sd["tgt_token_featurizer.embedding.weight"] = self.sd["src_token_featurizer.embedding.weight"]
+        self.out_width = args.max_len if self.kind == "greedy" else args.max_len + max(5, self.w["draft_len"]) + 4
+        self.n_best = 1 if self.kind == "greedy" else self.w["n_best"]
+        self.golden_id = self.w["golden"].get(weights) if (args.vocab, args.seed, args.max_len) == (288, 1234, 200) else None
+
+    def batch(self, j):
+        """Synthetic batch number j of the job (j = 0 is the batch the reference goldens were recorded on)."""
+        return synthetic_sources(self.w["draw"], self.args.vocab, seed=self.w["src_seed"] + j, **self.w["src_kw"])[:self.bs]
+
+    def describe(self):
+        a = self.cfg
+        wt = ("trained-like copy-circuit weights over random init (weights.copy_task_state_dict" if self.weights == "copy" else "random-init weights (")
+        src = "USPTO-50k-shape sources (12..150 tokens, mean 45)" if self.w["arch"] == "retro" else "USPTO-MIT-shape sources (20..198 tokens, mean 80)"
+        return (f"{self.w['name']}, max_len={self.args.max_len}; Molecular Transformer {a.embedding_dim}/{a.feedforward_dim}/"
+                f"{a.num_encoder_layers}+{a.num_decoder_layers}/{a.num_heads}, {wt}, seed {self.args.seed}), vocab {self.args.vocab}; synthetic {src}")
+
+    def generator(self, eng, keep_trace=False):
+        from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative, TranslationInferenceGreedySpeculative
+        a, w = self.args, self.w
+        if self.kind == "greedy":
+            return TranslationInferenceGreedySpeculative(eng, a.max_len, w["draft_len"], w["n_drafts"], PAD, BOS, EOS, REPLACE,
+                                                         tie_break=a.tie_break, keep_trace=keep_trace)
+        return TranslationInferenceBeamSearchSpeculative(eng, a.max_len, w["n_best"], w["draft_len"], w["n_drafts"], a.vocab, False,
+                                                         PAD, BOS, EOS, REPLACE, tie_break=a.tie_break, keep_trace=keep_trace)
+
+    def pad_out(self, out):
+        """(B, n_best, W) prediction -> fixed width (the beam search returns the width it reached)."""
+        if out.shape[-1] == self.out_width:
+            return out
+        res = torch.zeros(out.shape[:-1] + (self.out_width,), dtype=out.dtype, device=out.device)
+        res[..., :out.shape[-1]] = out
+        return res
+
+    # ---- the reference itself (oracle/_ref) or its port (oracle/), on `device` -----------------------------------
+    def reference_generator(self, device="cpu"):
+        from oracle import ref_runner
+        a, w = self.args, self.w
+        if ref_runner.available():
+            m = ref_runner.build_model(self.cfg, self.sd, device)
+            if self.kind == "greedy":
+                return ref_runner.greedy_speculative(m, a.max_len, w["draft_len"], w["n_drafts"], PAD, BOS, EOS, REPLACE), "reference"
+            return ref_runner.beam_speculative(m, a.max_len, w["n_best"], w["draft_len"], w["n_drafts"], a.vocab, False, PAD, BOS, EOS, REPLACE), "reference"
+        assert device == "cpu", "the oracle port is a CPU restatement"
+        from oracle.transformer import OracleTransformer
+        m = OracleTransformer(self.sd, self.cfg.num_heads)
+        if self.kind == "greedy":
+            from oracle.greedy_speculative import GreedySpeculativeOracle
+            return GreedySpeculativeOracle(m, a.max_len, w["draft_len"], w["n_drafts"], PAD, BOS, EOS, REPLACE), "port"
+        from oracle.beam_speculative import BeamSearchSpeculativeOracle
+        return BeamSearchSpeculativeOracle(m, a.max_len, w["n_best"], w["draft_len"], w["n_drafts"], a.vocab, False, PAD, BOS, EOS, REPLACE), "port"
 
 
-def workload_name(args):
-    return (f"product-prediction greedy speculative bs={args.batch_size} draft_len={args.draft_len} "
-            f"n_drafts={args.n_drafts} max_len={args.max_len}; Molecular Transformer 256/2048/4+4/8 random-init "
-            f"(seed {args.seed}, eos_bias {args.eos_bias}, pad_bias {args.pad_bias}), vocab {args.vocab}; "
-            f"synthetic USPTO-MIT-shape sources (20..198 tokens, mean 80)")
-
-
-def batch_for(args, rank, step):
-    """Synthetic batch of step `step`.  Weak scaling: per-GPU work is fixed as N grows, so every rank decodes the SAME
-    queries of the step (rotated by its rank); with rank-specific random batches the step time would be the slowest
-    rank's batch, i.e. the maximum of N samples of the batch-to-batch spread (about +-12 % with these sources), which
-    measures the data rather than the system."""
-    return torch.roll(synthetic_sources(args.batch_size, args.vocab, seed=100003 + step), shifts=rank, dims=0)
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -142,19 +214,33 @@ def measured_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "tflops_burst": d["bf16_tflops"],
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=True, chained_ffn=False):
-    """Algorithmic (flops, bytes) of ALL launches of a kernel class over the iterations in `hist`
-    (live queries per iteration); per-unit figures are in DESIGN.md §4.  With the fused kernels the
-    sub-layer tails (bias + residual + LayerNorm, fp32 and bf16 copies of the residual stream) are part
-    of the GEMM classes and the whole feed-forward block is the class `gemm_ffn1`."""
+def ncu_kernel_table():
+    """Per-kernel counters of the committed `ncu --set full` capture (profiles/*_ncu_kernels.json, written by
+    scripts/ncu_summary.py from the .ncu-rep): DRAM bytes per launch, tensor-pipe activity."""
+    files = sorted((REPO / "profiles").glob("*_ncu_kernels.json"))
+    if not files:
+        return None, {}
+    try:
+        return files[-1].name, json.load(open(files[-1]))["kernels"]
+    except Exception:
+        return None, {}
+
+
+def class_work(name, wl, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=True, chained_ffn=False, precision="bf16"):
+    """Algorithmic (flops, bytes) of ALL launches of a kernel class over the greedy iterations in `hist` (live queries per
+    iteration); per-unit figures are in DESIGN.md §4.  With the fused kernels the sub-layer tails (bias + residual +
+    LayerNorm, fp32 and bf16 copies of the residual stream) are part of the GEMM classes and the whole feed-forward
+    block is the class `gemm_ffn1`."""
     E, F, V, L = cfg.embedding_dim, cfg.feedforward_dim, cfg.tgt_vocab_size, cfg.num_decoder_layers
-    per_q = args.n_drafts * (args.draft_len + 1)
+    D, N = wl["draft_len"], wl["n_drafts"]
+    per_q = N * (D + 1)
     rows = sum(h * per_q for h in hist)           # token rows summed over iterations
-    ab = 2 if args.precision == "bf16" else 4      # activation bytes
+    ab = 2 if precision == "bf16" else 4           # activation bytes
     n_it = len(hist)
     ln_flops = 8.0 * rows * E
     stream_bytes = rows * E * (4 + 4 + ab)          # residual in, residual out (fp32), low-precision copy out
@@ -165,22 +251,25 @@ def class_work(name, args, cfg, hist, src_lens_mean, fused_ln=True, fused_ffn=Tr
             b += (rows * E * ab + rows * E * 8) * L + E * E * ab * L * n_it
         return f, b
     if name in ("gemm_self_out", "gemm_cross_out") and fused_ln:
-        return (2.0 * rows * E * E + ln_flops) * L, (rows * E * ab + stream_bytes) * L + E * E * ab * L * n_it
+        f = (2.0 * rows * E * E + ln_flops) * L
+        if name == "gemm_self_out":
+            f += 2.0 * rows * E * E * L               # chained cross-attention query projection
+        return f, (rows * E * ab + stream_bytes) * L + E * E * ab * L * n_it
     if name == "gemm_ffn2" and fused_ln:
         return (2.0 * rows * E * F + ln_flops) * L, (rows * F * ab + stream_bytes) * L + E * F * ab * L * n_it
     gemm = {"gemm_qkv": (E, 3 * E, ab), "gemm_self_out": (E, E, 4), "gemm_cross_q": (E, E, ab), "gemm_cross_out": (E, E, 4),
             "gemm_ffn1": (E, F, ab), "gemm_ffn2": (F, E, 4)}
     if name in gemm:
-        K, N, ob = gemm[name]
-        return 2.0 * rows * K * N * L, (rows * K * ab + rows * N * ob) * L + K * N * ab * L * n_it
+        K, Nn, ob = gemm[name]
+        return 2.0 * rows * K * Nn * L, (rows * K * ab + rows * Nn * ob) * L + K * Nn * ab * L * n_it
     if name == "gemm_classifier":
-        return 2.0 * rows * E * V, rows * E * ab + rows * V * 4 + E * V * ab * n_it
+        return 2.0 * rows * E * V, rows * E * ab + rows * 4 + E * V * ab * n_it
     if name == "cross_attn":
         lk = src_lens_mean
         return 4.0 * rows * lk * E * L, (rows * E * ab * 2 + sum(hist) * lk * 2 * E * ab) * L
     if name == "self_attn":
-        # keys: accepted prefix (grows ~1 token/iteration on average) + causal half of the draft row
-        flops = sum(4.0 * h * per_q * (it + 1 + (args.draft_len + 2) / 2.0) * E for it, h in enumerate(hist)) * L
+        # keys: accepted prefix (grows while decoding) + causal half of the draft row
+        flops = sum(4.0 * h * per_q * (it + 1 + (D + 2) / 2.0) * E for it, h in enumerate(hist)) * L
         byts = sum(h * (per_q * 4 * E * ab + (it + 1) * 2 * E * ab) for it, h in enumerate(hist)) * L
         return flops, byts
     if name == "add_layernorm":
@@ -210,46 +299,375 @@ def insitu_kernel_times(fn):
     return {k: {"launches": n, "avg_us": round(d / n, 2), "avg_added_us": round(g / n, 2)} for k, (n, d, g) in agg.items()}
 
 
-CLASS_KERNEL = {"gemm_ffn1": ("ffn_pair_kernel", "ffn_fused_kernel"), "self_attn": ("attn_mma_kernel",), "cross_attn": ("attn_mma_kernel",),
+CLASS_KERNEL = {"gemm_ffn1": ("ffn_pair_kernel", "ffn_fused_kernel"), "self_attn": ("attn_tc_kernel", "attn_mma_kernel"),
+                "cross_attn": ("attn_tc_kernel", "attn_mma_kernel"),
                 "gemm_qkv": ("gemm_pair_k256_kernel", "gemm_bf16_tc_persistent_kernel"), "gemm_self_out": ("gemm_resid_ln_kernel",),
-                "gemm_cross_out": ("gemm_resid_ln_kernel",)}
+                "gemm_cross_out": ("gemm_resid_ln_kernel",), "gemm_classifier": ("classifier_argmax_kernel",)}
+
+
+# ------------------------------------------------------------------------------------------------
+def compare_with_golden(wl, out):
+    """GPU prediction of batch 0 against the UNMODIFIED reference's output for the same batch (committed fixture)."""
+    if wl.golden_id is None or not (REPO / "tests/golden/bench_configs.npz").exists():
+        return None
+    z = np.load(REPO / "tests/golden/bench_configs.npz")
+    if wl.golden_id + "_out" not in z.files:
+        return None
+    ref = z[wl.golden_id + "_out"].astype(np.int64)
+    src = z[wl.golden_id + "_src"].astype(np.int64)
+    if not np.array_equal(src, wl.batch(0).numpy()):
+        return {"checked": False, "why": "the fixture's batch is not this run's batch 0"}
+    o = out.cpu().numpy()
+    W = max(o.shape[-1], ref.shape[-1])
+    po = np.zeros(o.shape[:-1] + (W,), np.int64); po[..., :o.shape[-1]] = o
+    pr = np.zeros(ref.shape[:-1] + (W,), np.int64); pr[..., :ref.shape[-1]] = ref
+    same_top1 = (po[:, 0] == pr[:, 0]).all(-1)
+    res = {"checked": True, "against": f"unmodified reference, tests/golden/bench_configs.npz:{wl.golden_id}", "queries": int(len(same_top1)),
+           "top1_identical": int(same_top1.sum()), "non_pad_tokens_in_reference": int((pr != PAD).sum())}
+    if wl.kind == "beam":
+        res["hypotheses_identical"] = int((po == pr).all(-1).sum())
+        res["hypotheses"] = int(po.shape[0] * po.shape[1])
+    return res
+
+
+def compare_with_live_reference(wl, out, nq):
+    """The reference (oracle/_ref, else the oracle port) decodes the first `nq` queries of batch 0 on the host now; the
+    GPU rows for the same queries must carry the same tokens.  Returns (parity dict, cpu_baseline dict).  Greedy queries
+    are independent of their batch mates; the beam search is run on the sub-batch by both sides."""
+    gen, kind = wl.reference_generator("cpu")
+    src = wl.batch(0)[:nq].clone()
+    torch.set_num_threads(host_threads())
+    t0 = time.perf_counter()
+    err = None
+    with torch.inference_mode():
+        try:
+            ref = gen.generate(src)
+        except (RuntimeError, AssertionError) as ex:
+            ref, err = None, str(ex)[:80]
+    dt = time.perf_counter() - t0
+    base = {"value": nq / dt, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"first {nq} queries of batch 0, full decode, {gen.model_calls_num} decoder calls, {dt:.1f} s"}
+    if ref is None:
+        return {"checked": False, "why": f"the reference raised: {err}"}, base
+    o, r = out.cpu().numpy(), ref.cpu().numpy()
+    W = max(o.shape[-1], r.shape[-1])
+    po = np.zeros(o.shape[:-1] + (W,), np.int64); po[..., :o.shape[-1]] = o
+    pr = np.zeros(r.shape[:-1] + (W,), np.int64); pr[..., :r.shape[-1]] = r
+    same = (po[:, 0] == pr[:, 0]).all(-1)
+    return {"checked": True, "against": f"{kind} run on the host in this process", "queries": int(nq), "top1_identical": int(same.sum()),
+            "non_pad_tokens_in_reference": int((pr != PAD).sum())}, base
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """Reference arm: the CPU port of the reference's algorithm (oracle/), all host threads.
-    Each step decodes a bounded sample (`--cpu-queries` queries) of the step's batch."""
+    """Reference arm: the reference's own CPU implementation (oracle/_ref; the oracle port when that copy is absent) with
+    all host threads.  Each step decodes a bounded sample (`--cpu-queries` queries) of the step's batch; plus, once, the
+    same unmodified code on cuda:0 (`reference_gpu_eager`, context for "over the reference's PyTorch path")."""
     if rank != 0:
         return
-    from oracle.greedy_speculative import GreedySpeculativeOracle
-    from oracle.transformer import OracleTransformer
-    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make this a one-thread baseline
-    try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except (AttributeError, RuntimeError):
-        torch.set_num_threads(os.cpu_count() or 1)
-    cfg, sd = build_weights(args)
-    model = OracleTransformer(sd, cfg.num_heads)
-    nq = args.cpu_queries if args.warmup + args.steps <= 8 else 1    # ~6.5 s of host time per query: keep the run to minutes
-    times = []
-    for i in range(args.warmup + args.steps):
-        src = batch_for(args, 0, i)[:nq]
-        gen = GreedySpeculativeOracle(model, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
+    torch.set_num_threads(host_threads())   # torchrun exports OMP_NUM_THREADS=1 to its workers
+    wl = Workload(args.workload, args.weights, args)
+    gen, kind = wl.reference_generator("cpu")
+
+    def decode(src):
         t0 = time.perf_counter()
-        gen.generate(src)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
+        with torch.inference_mode():
+            try:
+                gen.generate(src)
+            except (RuntimeError, AssertionError):
+                pass
+        return time.perf_counter() - t0
+
+    # sample size: as many queries of the step's batch as keep the whole run within ~3 minutes (calibrated on 2 queries)
+    t_cal = decode(wl.batch(0)[:min(2, wl.bs)]) / min(2, wl.bs)
+    n_steps = args.warmup + args.steps
+    nq = args.cpu_queries if args.cpu_queries > 0 else 0
+    nq = max(1, min(wl.bs, nq if nq > 2 else int(180.0 / n_steps / max(t_cal, 1e-3))))
+    times = [decode(wl.batch(i)[:nq]) for i in range(n_steps)][args.warmup:]
     total = sum(times)
     value = nq * len(times) / total
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "SMILES/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": wl.w["metric"], "value": value, "unit": "SMILES/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample": f"{nq} of {args.batch_size} queries per step"},
-            "cpu_baseline": {"value": value, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{nq} query per step, {len(times)} steps, full decode (max_len {args.max_len})"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.describe(), "sample": f"{nq} of {wl.bs} queries per step"},
+            "cpu_baseline": {"value": value, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": f"{nq} of {wl.bs} queries per step, {len(times)} steps, full decode (max_len {args.max_len})"},
             "e2e": {"value": value, "unit": "SMILES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if nq < wl.bs and t_cal * wl.bs * 0.6 < 150.0:
+        # one WHOLE batch as the reference's predict loop decodes it (batched GEMMs are cheaper per query than the sample's)
+        dt = decode(wl.batch(args.warmup))
+        line["full_batch"] = {"value": wl.bs / dt, "unit": "SMILES/s", "seconds": round(dt, 1), "batch_size": wl.bs,
+                              "what": "batch `warmup` of the job decoded whole, once (same configuration as the GPU arm's step)"}
+    if torch.cuda.is_available() and kind == "reference":
+        try:   # informational: the reference's normal deployment is eager PyTorch on a GPU
+            g2, _ = wl.reference_generator("cuda:0")
+            with torch.inference_mode():
+                g2.generate(wl.batch(0).cuda())
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nb = 2
+                for i in range(1, 1 + nb):
+                    try:
+                        g2.generate(wl.batch(i).cuda())
+                    except (RuntimeError, AssertionError):
+                        pass
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            line["reference_gpu_eager"] = {"value": nb * wl.bs / dt, "unit": "SMILES/s", "batches": nb, "batch_size": wl.bs,
+                                           "what": "the unmodified reference (oracle/_ref) in eager fp32 PyTorch on cuda:0, whole batches"}
+        except Exception as ex:
+            line["reference_gpu_eager"] = {"error": str(ex)[:120]}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class Runner:
+    """Engines + generators of one workload on this rank, and the timed regions over a shared batch queue."""
+
+    def __init__(self, wl, args, local_rank, world, n_fly):
+        from translation_transformer_b200.model import B200Transformer
+        from translation_transformer_b200.pipeline import InFlightDecoder
+        self.wl, self.args, self.world, self.local_rank = wl, args, world, local_rank
+        self.dev = torch.device("cuda", local_rank)
+        self.engs = [B200Transformer(wl.cfg, wl.sd, precision=args.precision, device=local_rank) for _ in range(n_fly)]
+        self.gens = [wl.generator(e) for e in self.engs]
+        self.fly = InFlightDecoder(self.gens, device=local_rank)
+        self.one = InFlightDecoder(self.gens[:1], device=local_rank)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        self.errors = []
+        self.cache = {}
+
+    def host_batch(self, j):
+        if j not in self.cache:
+            self.cache[j] = self.wl.batch(j).pin_memory()
+        return self.cache[j]
+
+    def counters(self):
+        names = ("model_calls_num", "gpu_launches", "accepted_tokens_num") + (("produced_tokens_num",) if self.wl.kind == "greedy" else ("produced_non_pad_tokens",))
+        return [sum(getattr(g, n) for g in self.gens) for n in names]
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def decode_one(self, j):
+        """Batch j on the first engine, synchronously (warm-up, parity)."""
+        src = self.host_batch(j).to(self.dev, non_blocking=True)
+        return self.gens[0].generate(src)
+
+    def timed(self, first, n_batches, e2e, decoder=None, resident=None):
+        """Decode batches first .. first+n_batches-1 of the job; every rank and every in-flight engine pulls the next index
+        from one shared queue.  e2e: inputs start in pinned host memory, each prediction is copied back to pinned host
+        memory inside the region.  Returns (ms as max over ranks, batches decoded by this rank, failed batches)."""
+        import torch.distributed as dist
+        from translation_transformer_b200.distributed import BatchQueue, gather_indexed_predictions
+        decoder = decoder or self.fly
+        wl = self.wl
+        for j in range(first, first + n_batches):
+            self.host_batch(j)
+        if not e2e:
+            resident = resident if resident is not None else {j: self.host_batch(j).to(self.dev) for j in range(first, first + n_batches)}
+        out_hosts = {}
+        if e2e:
+            out_hosts = {j: torch.empty(wl.bs, wl.n_best, wl.out_width, dtype=torch.int64).pin_memory() for j in range(first, first + n_batches)}
+        q = BatchQueue(n_batches)
+        failed = []
+
+        def next_item():
+            i = q.next()
+            return None if i is None else (first + i, first + i)
+
+        def pre(j):
+            self.flush.zero_()                                   # on the worker's stream, like everything of its step
+            return self.host_batch(j).to(self.dev, non_blocking=True) if e2e else resident[j]
+
+        def post(o):
+            return wl.pad_out(o)
+
+        def on_error(j, ex):   # reference-faithful failure modes (oracle/greedy_speculative.py); not counted as throughput
+            failed.append(j)
+            self.errors.append(str(ex)[:80])
+            return None
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        if e2e:
+            def post_e2e(o, _oh=out_hosts):
+                return wl.pad_out(o)
+            done = decoder.drain(next_item, pre=pre, post=post_e2e, on_error=on_error)
+            for j, o in done:
+                if o is not None:
+                    out_hosts[j].copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            done = decoder.drain(next_item, pre=pre, post=post, on_error=on_error)
+        good = [(j, o) for j, o in done if o is not None]
+        # predictions of every rank collected once, in batch order (NCCL all-gather; identity on one GPU)
+        gathered = gather_indexed_predictions([j - first for j, _ in good], [o for _, o in good], n_batches, device=self.dev)
+        ev1.record()
+        self.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev)
+        nfail = torch.tensor([len(failed)], device=self.dev, dtype=torch.int64)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nfail)
+        self.last_gathered = gathered
+        return float(ms.item()), len(done), int(nfail.item())
+
+    def close(self):
+        self.fly.close()
+        self.one.close()
+        for e in self.engs:
+            e.close()
+        self.flush = None
+
+
+def measure_workload(wl, args, local_rank, world, rank, n_fly, steps, warmup, n_timed_batches, full):
+    """Warm-up, parity, timed regions (resident, end to end, strictly sequential) of one workload.  `full` adds the
+    instrumented step (per-class CUDA events -> roofline) and the CUPTI in-situ step."""
+    R = Runner(wl, args, local_rank, world, n_fly)
+    res = {}
+    # ---- warm-up (also sizes every workspace) + parity of batch 0 ---------------------------------------------------
+    out0 = None
+    for g_i, g in enumerate(R.gens):
+        for i in range(warmup):
+            try:
+                o = g.generate(R.host_batch(i).to(R.dev))
+                if g_i == 0 and i == 0:
+                    out0 = o.clone()
+            except RuntimeError as ex:
+                R.errors.append(str(ex)[:80])
+    if n_fly > 1:    # and W more through the worker threads, `n_fly` at a time (thread start-up, per-thread CUDA state)
+        from translation_transformer_b200.distributed import BatchQueue
+        q = BatchQueue(warmup * n_fly, local=True)
+        R.fly.drain(lambda: (lambda i: None if i is None else (i, i % warmup))(q.next()), pre=lambda j: R.host_batch(j).to(R.dev),
+                    on_error=lambda j, ex: None)
+    torch.cuda.synchronize()
+    parity = {}
+    if rank == 0 and out0 is not None:
+        parity["golden"] = compare_with_golden(wl, out0)
+    res["_out0"] = out0
+    first = warmup
+    lib, eng, gen = R.engs[0].lib, R.engs[0], R.gens[0]
+    shares, hist, n_cls, names = {}, [], 0, []
+    if full and wl.kind == "greedy":
+        # ---- one instrumented step: CUDA-event time of every kernel class -> dominant kernel ---------
+        n_cls = lib.ttb_kernel_class_count()
+        names = [lib.ttb_kernel_class_name(i).decode() for i in range(n_cls)]
+        lib.ttb_engine_set_profiling(eng._h, (1 << n_cls) - 1)
+        R.flush.zero_()
+        try:
+            gen.generate(R.host_batch(first).to(R.dev))
+        except RuntimeError as ex:
+            R.errors.append(str(ex)[:80])
+        ms_arr, n_arr = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
+        lib.ttb_engine_get_profile(eng._h, n_cls, ms_arr, n_arr)
+        shares = {names[i]: {"ms": round(ms_arr[i], 3), "launches": int(n_arr[i])} for i in range(n_cls) if n_arr[i]}
+        tot_ms = sum(v["ms"] for v in shares.values()) or 1.0
+        for v in shares.values():
+            v["share"] = round(v["ms"] / tot_ms, 4)
+        buf = (C.c_int32 * (args.max_len + 2))()
+        n_hist = lib.ttb_engine_get_history(eng._h, buf, args.max_len + 2)
+        hist = list(buf[:n_hist])
+        lib.ttb_engine_set_profiling(eng._h, 0)
+    # ---- timed regions ----------------------------------------------------------------------------------------------
+    one_n = max(1, min(n_timed_batches, steps))
+    one_ms, _, one_fail = R.timed(first, one_n, False, decoder=R.one) if (n_fly > 1 and world == 1) else (None, 0, 0)
+    c0 = R.counters()
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
+    if rank == 0 and full:
+        sampler.start()
+    ms, mine, nfail = R.timed(first, n_timed_batches, False)
+    clocks = sampler.stop() if (rank == 0 and full) else None
+    c1 = R.counters()
+    e2e_ms, _, e2e_fail = R.timed(first, n_timed_batches, True)
+    insitu = None
+    if full and rank == 0 and not args.no_insitu:
+        try:
+            src_d = R.host_batch(first).to(R.dev)
+            insitu = insitu_kernel_times(lambda: gen.generate(src_d))   # rank-local: no collective in here
+        except Exception as ex:   # CUPTI not available: the event-bracket figures stand alone
+            insitu = {"error": str(ex)[:120]}
+    delta = torch.tensor([b - a for a, b in zip(c0, c1)], dtype=torch.int64, device=R.dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(delta)
+    calls, launches, accepted, produced = [int(x) for x in delta.tolist()]
+    q_ok = (n_timed_batches - nfail) * wl.bs
+    res.update({"value": q_ok / (ms / 1000.0), "ms": ms, "batches": n_timed_batches, "failed_batches": nfail, "batches_this_rank": mine,
+                "e2e_value": (n_timed_batches - e2e_fail) * wl.bs / (e2e_ms / 1000.0), "e2e_ms": e2e_ms,
+                "one_value": (one_n - one_fail) * wl.bs / (one_ms / 1000.0) if one_ms else None, "one_ms": one_ms, "one_batches": one_n,
+                "calls": calls, "launches": launches, "accepted": accepted, "produced": produced, "clocks": clocks, "shares": shares,
+                "hist": hist, "insitu": insitu, "parity": parity, "errors": R.errors[:3],
+                "h2d": int(R.host_batch(first).numel() * 8), "d2h": int(wl.bs * wl.n_best * wl.out_width * 8),
+                "src_len_mean": float((R.host_batch(first) != PAD).sum().item()) / wl.bs})
+    R.close()
+    return res
+
+
+def roofline_tables(wl, args, m, peaks):
+    """`roofline` (dominant class) and `roofline_all` (every decoder class) from the instrumented step of a greedy workload."""
+    shares, hist, insitu = m["shares"], m["hist"], m["insitu"]
+    if not shares or not hist:
+        return None, None
+    fused_ln = "add_layernorm" not in shares
+    fused_ffn = "gemm_ffn2" not in shares
+    chained_ffn = fused_ffn and "gemm_cross_out" not in shares
+    ncu_file, ncu = ncu_kernel_table()
+    balance = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    table = {}
+    for cls, sh in shares.items():
+        if cls in ("encoder", "misc"):
+            continue
+        f, b = class_work(cls, wl.w, wl.cfg, hist, m["src_len_mean"], fused_ln, fused_ffn, chained_ffn, args.precision)
+        n = max(sh["launches"], 1)
+        us = 1000.0 * sh["ms"] / n
+        tensor = f / max(b, 1.0) >= balance
+        row = {"launches": sh["launches"], "share_of_step": sh["share"], "avg_us_event_bracket": round(us, 2),
+               "flops_per_launch": f / n, "bytes_per_launch": b / n, "bound": "tensor" if tensor else "hbm"}
+        per = (f if tensor else b) / n
+        unit = 1e12 if tensor else 1e9
+        peak = peaks["tflops"] if tensor else peaks["hbm_gbs"]
+        row["frac_event_bracket"] = round(per / (us * 1e-6) / unit / peak, 4) if us > 0 else None
+        k = next((kn for kn in CLASS_KERNEL.get(cls, ()) if insitu and kn in insitu), None) if insitu and "error" not in insitu else None
+        # several classes can share one kernel name (self / cross attention; the two out-projections): in-situ figures are per name
+        if k:
+            row["kernel"] = k
+            row["in_situ_us"] = insitu[k]["avg_added_us"]
+            shared = [c for c in shares if k in CLASS_KERNEL.get(c, ())]
+            if len(shared) == 1:
+                row["frac_in_situ"] = round(per / (insitu[k]["avg_added_us"] * 1e-6) / unit / peak, 4)
+        kn = next((kn for kn in CLASS_KERNEL.get(cls, ()) if kn in ncu), None)
+        if kn:
+            row["ncu"] = ncu[kn]
+        table[cls] = row
+    dominant = max(table, key=lambda c: shares[c]["ms"])
+    d = table[dominant]
+    tensor = d["bound"] == "tensor"
+    per = d["flops_per_launch"] if tensor else d["bytes_per_launch"]
+    ach = per / (d["avg_us_event_bracket"] * 1e-6) / (1e12 if tensor else 1e9)
+    label = {"gemm_ffn1": ("ffn_pair_kernel (cross out-proj+LayerNorm2 + FFN1+ReLU+FFN2+residual+LayerNorm3, cta_group::2)" if chained_ffn else
+                           "ffn_fused_kernel (FFN1+ReLU+FFN2+residual+LayerNorm)") if fused_ffn else "gemm_ffn1"}.get(dominant, d.get("kernel", dominant))
+    traffic = d.get("ncu", {}).get("dram_bytes_per_launch")
+    roof = {"bound": d["bound"], "achieved": ach, "peak": peaks["tflops"] if tensor else peaks["hbm_gbs"], "unit": "TFLOP/s" if tensor else "GB/s",
+            "frac": ach / (peaks["tflops"] if tensor else peaks["hbm_gbs"]), "traffic": traffic,
+            "traffic_source": f"profiles/{ncu_file} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
+            "kernel": label, "kernel_class": dominant, "launches": d["launches"], "avg_launch_us": d["avg_us_event_bracket"],
+            "algorithmic_flops_per_launch": d["flops_per_launch"], "algorithmic_bytes_per_launch": d["bytes_per_launch"],
+            "peak_source": peaks["source"], "share_of_step": d["share_of_step"],
+            "event_bracket_us_of_a_trivial_kernel": 1000.0 * shares["misc"]["ms"] / shares["misc"]["launches"] if "misc" in shares else None,
+            "live_queries_per_iteration": {"first": hist[0], "mean": round(sum(hist) / len(hist), 2), "iterations": len(hist)},
+            "timing": "CUDA events around every launch of the class on the launching stream, one extra instrumented step of the same "
+                      "workload right before the timed region (bracketing every launch inside the timed region costs ~2x step time); "
+                      "flops / bytes per launch follow the live queries of each iteration"}
+    if "frac_in_situ" in d:
+        roof["in_situ"] = {"kernel": d["kernel"], "avg_added_us": d["in_situ_us"], "frac": d["frac_in_situ"],
+                           "how": "CUPTI activity records of one extra step run like the timed ones (CUDA graph + programmatic dependent "
+                                  "launch): avg_added_us = end of the kernel minus end of the preceding kernel"}
+    return roof, table
 
 
 def main():
@@ -262,12 +680,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from translation_transformer_b200 import _lib
-    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
-    from translation_transformer_b200.distributed import gather_predictions
-    from translation_transformer_b200.model import B200Transformer
-    from translation_transformer_b200.pipeline import InFlightDecoder
-
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -277,247 +689,84 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
-    cfg, sd = build_weights(args)
     n_fly = max(1, args.in_flight)
-    engs = [B200Transformer(cfg, sd, precision=args.precision, device=local_rank) for _ in range(n_fly)]
-    gens = [TranslationInferenceGreedySpeculative(e, args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE,
-                                                  tie_break=args.tie_break) for e in engs]
-    eng, gen = engs[0], gens[0]          # the instrumented / profiled steps run on the first engine alone
-    fly = InFlightDecoder(gens, device=local_rank) if n_fly > 1 else None
-    lib = eng.lib
-    n_total = args.warmup + args.steps + 1
-    host = [batch_for(args, rank, i).pin_memory() for i in range(n_total)]
-    devb = [h.to(dev) for h in host]
-    out_host = torch.empty(args.batch_size, 1, args.max_len, dtype=torch.int64).pin_memory()
-    out_hosts = [torch.empty_like(out_host).pin_memory() for _ in range(args.steps)] if fly else None
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    errors = []
+    wl = Workload(args.workload, args.weights, args)
+    if args.scaling == "strong":
+        n_batches = max(1, args.queries // wl.bs)
+    else:
+        n_batches = world * args.steps
+    m = measure_workload(wl, args, local_rank, world, rank, n_fly, args.steps, args.warmup, n_batches, full=True)
+    peaks = measured_peaks()
 
-    def one_step(i, e2e, g=None):
-        flush.zero_()
-        src = host[i].to(dev, non_blocking=True) if e2e else devb[i]
-        try:
-            out = (g or gen).generate(src)
-        except RuntimeError as ex:   # reference-faithful failure modes (see oracle/greedy_speculative.py)
-            errors.append(str(ex)[:80])
-            out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
-        if world > 1:
-            gather_predictions(out, counts=[args.batch_size] * world)   # NCCL all-gather of the predictions
-        if e2e:
-            out_host.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def pre_resident(i):
-        flush.zero_()                                   # on the worker's stream, like everything of its step
-        return devb[i]
-
-    def pre_host(i):
-        flush.zero_()
-        return host[i].to(dev, non_blocking=True)
-
-    def timed(e2e, first, pipelined=True):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        if fly and pipelined:
-            # all K steps are submitted at once; `n_fly` of them are decoded at any time, each on its own engine and stream
-            # (flush, input copy, decoding loop, result copy); this thread collects them in step order
-            futs = [fly.submit(first + k, pre=pre_host if e2e else pre_resident,
-                               post=(lambda o, k=k: (out_hosts[k].copy_(o, non_blocking=True), o)[1]) if e2e else None) for k in range(args.steps)]
-            for f in futs:
-                try:
-                    out = f.result()
-                except RuntimeError as ex:   # reference-faithful failure modes (see oracle/greedy_speculative.py)
-                    errors.append(str(ex)[:80])
-                    out = torch.zeros(args.batch_size, 1, args.max_len, dtype=torch.int64, device=dev)
-                if world > 1:
-                    gather_predictions(out, counts=[args.batch_size] * world)   # NCCL all-gather of the predictions
-        else:
-            for k in range(args.steps):
-                one_step(first + k, e2e)
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # ---- warm-up (also sizes every workspace) -------------------------------------------------
-    for g in gens:
-        for i in range(args.warmup):
-            one_step(i, False, g)
-    if fly:   # and W more through the worker threads, `n_fly` at a time (thread start-up, per-thread CUDA state)
-        for f in [fly.submit(i % args.warmup, pre=pre_resident) for i in range(args.warmup * n_fly)]:
-            try:
-                f.result()
-            except RuntimeError:
-                pass
-    # ---- one instrumented step: CUDA-event time of every kernel class -> dominant kernel ---------
-    n_cls = lib.ttb_kernel_class_count()
-    names = [lib.ttb_kernel_class_name(i).decode() for i in range(n_cls)]
-    lib.ttb_engine_set_profiling(eng._h, (1 << n_cls) - 1)
-    one_step(args.warmup + args.steps, False)
-    ms_arr, n_arr = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
-    lib.ttb_engine_get_profile(eng._h, n_cls, ms_arr, n_arr)
-    shares = {names[i]: {"ms": round(ms_arr[i], 3), "launches": int(n_arr[i])} for i in range(n_cls) if n_arr[i]}
-    tot_ms = sum(v["ms"] for v in shares.values()) or 1.0
-    for v in shares.values():
-        v["share"] = round(v["ms"] / tot_ms, 4)
-    dominant = max((n for n in shares if n not in ("encoder", "misc")), key=lambda n: shares[n]["ms"])
-    dom_id = names.index(dominant)
-
-    # per-iteration live-query history of the instrumented step (for the algorithmic work of the kernel)
-    buf = (C.c_int32 * (args.max_len + 2))()
-    n_hist = lib.ttb_engine_get_history(eng._h, buf, args.max_len + 2)
-    hists = [list(buf[:n_hist])]
-    dom_ms, dom_launches = ms_arr[dom_id], int(n_arr[dom_id])
-    lib.ttb_engine_set_profiling(eng._h, 0)
-
-    # ---- timed region 1: inputs resident in HBM, no instrumentation -------------------------------
-    def counters():
-        return [sum(getattr(g, n) for g in gens) for n in ("model_calls_num", "gpu_launches", "accepted_tokens_num", "produced_tokens_num")]
-
-    one_ms = timed(False, args.warmup, pipelined=False) if fly else None    # strictly one batch after the other
-    calls0, launches0, acc0, tok0 = counters()
-    sampler = ClockSampler(local_rank, args.clock_period_ms)
+    line = None
     if rank == 0:
-        sampler.start()
-    timed_ms = timed(False, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    calls1, launches1, acc1, tok1 = counters()
-    calls, launches, accepted, produced = calls1 - calls0, launches1 - launches0, acc1 - acc0, tok1 - tok0
-
-    # ---- timed region 2: end to end through the public API with host buffers ---------------------
-    e2e_ms = timed(True, args.warmup)
-
-    insitu = None
-    if rank == 0 and not args.no_insitu:
-        try:
-            insitu = insitu_kernel_times(lambda: gen.generate(devb[args.warmup]))   # rank-local: no collective in here
-        except Exception as ex:   # CUPTI not available: the event-bracket figures stand alone
-            insitu = {"error": str(ex)[:120]}
-
-    lt = torch.tensor([launches, calls, accepted, produced], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(lt)
-    launches, calls, accepted, produced = [int(x) for x in lt.tolist()]
-
-    if rank == 0:
-        queries = world * args.steps * args.batch_size
-        value = queries / (timed_ms / 1000.0)
-        e2e_value = queries / (e2e_ms / 1000.0)
-        peaks = measured_peaks()
-        src_lens_mean = float((host[args.warmup + args.steps] != PAD).sum().item()) / args.batch_size
-        flops = byts = 0.0
-        fused_ln = "add_layernorm" not in shares
-        fused_ffn = "gemm_ffn2" not in shares
-        chained_ffn = fused_ffn and "gemm_cross_out" not in shares
-        for h in hists:
-            f, b = class_work(dominant, args, cfg, h, src_lens_mean, fused_ln, fused_ffn, chained_ffn)
-            flops += f
-            byts += b
-        intensity = flops / max(byts, 1.0)
-        balance = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-        dom_s = max(dom_ms, 1e-9) / 1000.0
-        if intensity >= balance:
-            roof = {"bound": "tensor", "achieved": flops / dom_s / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
-        else:
-            roof = {"bound": "hbm", "achieved": byts / dom_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-        label = {"gemm_ffn1": ("ffn_pair_kernel (cross out-proj+LayerNorm2 + FFN1+ReLU+FFN2+residual+LayerNorm3, cta_group::2)" if chained_ffn else
-                               "ffn_fused_kernel (FFN1+ReLU+FFN2+residual+LayerNorm)") if fused_ffn else "gemm_ffn1",
-                 "gemm_self_out": "gemm_resid_ln_kernel (self out-proj)" if fused_ln else "gemm_self_out",
-                 "gemm_cross_out": "gemm_resid_ln_kernel (cross out-proj)" if fused_ln else "gemm_cross_out"}.get(dominant, dominant)
-        overhead_us = 1000.0 * shares["misc"]["ms"] / shares["misc"]["launches"] if "misc" in shares else None
-        roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": NCU_TRAFFIC.get(dominant), "kernel": label, "kernel_class": dominant,
-                     "event_bracket_us_of_a_trivial_kernel": overhead_us,
-                     "launches": dom_launches, "avg_launch_us": 1000.0 * dom_ms / max(dom_launches, 1),
-                     "algorithmic_flops_per_launch": flops / max(dom_launches, 1), "algorithmic_bytes_per_launch": byts / max(dom_launches, 1),
-                     "peak_source": peaks["source"], "share_of_step": shares[dominant]["share"],
-                     "timing": "CUDA events around every launch of the class on the launching stream, one extra "
-                               "instrumented step of the same workload right before the timed region "
-                               "(bracketing every launch inside the timed region costs ~2x step time)"})
-        if insitu and "error" not in insitu:
-            k = next((n for n in CLASS_KERNEL.get(dominant, ()) if n in insitu), None)
-            if k:
-                us = insitu[k]["avg_added_us"]
-                per_launch = (flops if roof["bound"] == "tensor" else byts) / max(dom_launches, 1)
-                ach = per_launch / (us * 1e-6) / (1e12 if roof["bound"] == "tensor" else 1e9)
-                roof["in_situ"] = {"kernel": k, "launches": insitu[k]["launches"], "avg_us": insitu[k]["avg_us"], "avg_added_us": us,
-                                   "achieved": ach, "frac": ach / roof["peak"],
-                                   "how": "CUPTI activity records of one extra step run like the timed ones (CUDA graph + programmatic "
-                                          "dependent launch): avg_added_us = end of the kernel minus end of the preceding kernel"}
-        line = {"metric": METRIC, "value": value, "unit": "SMILES/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        roof, table = roofline_tables(wl, args, m, peaks) if wl.kind == "greedy" else (None, None)
+        steps_equiv = n_batches / world
+        line = {"metric": wl.w["metric"], "value": m["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": m["ms"] / steps_equiv, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": workload_name(args), "global_batch": world * args.batch_size,
-                           "parallelism": f"dp{world} (one batch per rank and step: the step's queries rotated by the rank, so "
-                                          f"per-GPU work is identical; predictions all-gathered over NCCL)" if world > 1 else "single GPU",
-                           "batches_in_flight": n_fly,
-                           "l2": "256 MiB buffer written before every step (L2 flush)"},
-                "e2e": {"value": e2e_value, "unit": "SMILES/s", "ms_per_step": e2e_ms / args.steps,
-                        "h2d_bytes_per_step": int(host[args.warmup].numel() * 8),
-                        "d2h_bytes_per_step": int(out_host.numel() * 8)},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_shares": shares,
-                "decoder_calls": calls, "accepted_tokens_per_call": accepted / max(calls, 1),
-                "produced_tokens": produced, "reference_failures": errors[:3]}
-        if one_ms is not None:
-            line["one_batch_in_flight"] = {"value": queries / (one_ms / 1000.0), "unit": "SMILES/s", "ms_per_step": one_ms / args.steps,
-                                           "what": "the same K steps strictly one after the other on one engine (the kernel-level "
-                                                   "figures of `roofline` / `kernels_in_situ` are measured in this mode)"}
-        if insitu:
-            line["kernels_in_situ"] = insitu
-        if world == 1:
-            # BASELINE.json configs[2] beside the headline (same weights): speculative beam search bs=4, n_best=5
+                "config": {"workload": wl.describe(), "global_batch": world * wl.bs, "batches_timed": n_batches,
+                           "parallelism": (f"dp{world}: the {n_batches} batches of the job are drawn from one queue shared by all ranks and "
+                                           f"in-flight engines (no static shards); predictions all-gathered once over NCCL") if world > 1 else "single GPU",
+                           "batches_in_flight": n_fly, "l2": "256 MiB buffer written before every step (L2 flush)"},
+                "e2e": {"value": m["e2e_value"], "unit": "SMILES/s", "ms_per_step": m["e2e_ms"] / steps_equiv,
+                        "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+                "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roof, "roofline_all": table, "kernel_shares": m["shares"],
+                "decoder_calls": m["calls"], "accepted_tokens_per_call": m["accepted"] / max(m["calls"], 1),
+                "produced_tokens": m["produced"], "failed_batches": m["failed_batches"], "reference_failures": m["errors"]}
+        if m["one_value"] is not None:
+            line["one_batch_in_flight"] = {"value": m["one_value"], "unit": "SMILES/s", "ms_per_step": m["one_ms"] / m["one_batches"],
+                                           "what": "batches strictly one after the other on one engine (the kernel-level figures of `roofline` / "
+                                                   "`kernels_in_situ` are measured in this mode)"}
+        if m["insitu"]:
+            line["kernels_in_situ"] = m["insitu"]
+        parity = m["parity"]
+        if world == 1 and not args.no_cpu_baseline and m["_out0"] is not None:
+            nq = min(wl.bs, args.cpu_queries)
+            out_sub = m["_out0"][:nq]
+            if wl.kind == "beam":   # the search couples the queries of a batch (width bookkeeping): decode the sub-batch on the GPU too
+                from translation_transformer_b200.model import B200Transformer
+                e_ = B200Transformer(wl.cfg, wl.sd, precision=args.precision, device=local_rank)
+                out_sub = wl.generator(e_).generate(wl.batch(0)[:nq].to(dev))
+                e_.close()
+            parity["live"], line["cpu_baseline"] = compare_with_live_reference(wl, out_sub, nq)
+        checks = [p for p in parity.values() if p and p.get("checked")]
+        line["parity"] = parity
+        line["parity_checked"] = bool(checks)
+        line["parity_ok"] = bool(checks) and all(p["top1_identical"] == p["queries"] for p in checks)
+
+    # ---- side figures on one GPU: random-init worst case (round-1 headline) and the beam workloads ------------------------
+    if world == 1 and not args.no_extra_workloads and args.scaling == "weak":
+        extra = {}
+        todo = []
+        if args.workload == "greedy" and args.weights == "copy":
+            todo.append(("random_init_worst_case", Workload("greedy", "random", args), 6, True))
+        if args.workload == "greedy":
+            todo += [("beam", Workload("beam", "copy", args), 6, False), ("retro", Workload("retro", "copy", args), 6, False)]
+        for key, w2, k2, full in todo:
             try:
-                from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
-                bgens = [TranslationInferenceBeamSearchSpeculative(e_, args.max_len, 5, args.draft_len, args.n_drafts, args.vocab, False,
-                                                                   PAD, BOS, EOS, REPLACE) for e_ in engs]
-                bgen = bgens[0]
-                bsrc = [batch_for(args, 0, i)[:4].to(dev) for i in range(3)]
-                bgen.generate(bsrc[0])
-                torch.cuda.synchronize()
-                c0, t0 = bgen.model_calls_num, time.perf_counter()
-                for b in bsrc[1:]:
-                    bgen.generate(b)
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                line["beam_speculative"] = {"workload": "product prediction beam-search speculative bs=4 n_best=5 draft_len=10 n_drafts=23 "
-                                                        "(BASELINE.json configs[2]), same weights and sources, KV-cached",
-                                            "value": 8 / dt, "unit": "SMILES/s", "ms_per_batch": 1000 * dt / 2,
-                                            "decoder_calls_per_batch": (bgen.model_calls_num - c0) / 2, "batches_in_flight": 1}
-                if n_fly > 1:    # the same search with `n_fly` batches in flight (one engine each)
-                    bfly = InFlightDecoder(bgens, device=local_rank)
-                    many = [batch_for(args, 0, i % 3)[:4] for i in range(3 * n_fly)]
-                    list(bfly.map(many[:n_fly], pre=lambda t: t.to(dev), on_error=lambda i, ex: None))
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    list(bfly.map(many, pre=lambda t: t.to(dev), on_error=lambda i, ex: None))
-                    torch.cuda.synchronize()
-                    dt = time.perf_counter() - t0
-                    line["beam_speculative"]["in_flight"] = {"batches_in_flight": n_fly, "value": 4 * len(many) / dt, "unit": "SMILES/s",
-                                                             "ms_per_batch": 1000 * dt / len(many)}
-                    bfly.close()
-            except (RuntimeError, AssertionError) as ex:   # reference-faithful failure modes
-                line["beam_speculative"] = {"error": str(ex)[:120]}
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle.greedy_speculative import GreedySpeculativeOracle
-            from oracle.transformer import OracleTransformer
-            nq = args.cpu_queries
-            o = GreedySpeculativeOracle(OracleTransformer(sd, cfg.num_heads), args.max_len, args.draft_len, args.n_drafts, PAD, BOS, EOS, REPLACE)
-            t0 = time.perf_counter()
-            try:
-                o.generate(host[args.warmup][:nq].clone())
-            except RuntimeError:
-                pass
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": nq / dt, "unit": "SMILES/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"first {nq} queries of the first timed batch, full decode, {o.model_calls_num} decoder calls, {dt:.1f} s"}
+                m2 = measure_workload(w2, args, local_rank, 1, 0, n_fly, k2, 2, k2, full=full)
+                blk = {"workload": w2.describe(), "metric": w2.w["metric"], "value": m2["value"], "unit": "SMILES/s", "steps": k2,
+                       "ms_per_step": m2["ms"] / k2, "batches_in_flight": n_fly,
+                       "e2e": {"value": m2["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": m2["h2d"], "d2h_bytes_per_step": m2["d2h"]},
+                       "one_batch_in_flight": {"value": m2["one_value"], "ms_per_step": m2["one_ms"] / m2["one_batches"]} if m2["one_value"] else None,
+                       "decoder_calls_per_batch": m2["calls"] / k2, "accepted_tokens_per_call": m2["accepted"] / max(m2["calls"], 1),
+                       "gpu_launches": m2["launches"], "failed_batches": m2["failed_batches"], "parity": m2["parity"]}
+                if full:
+                    blk["roofline"], blk["roofline_all"] = roofline_tables(w2, args, m2, peaks)
+                extra[key] = blk
+            except (RuntimeError, AssertionError) as ex:
+                extra[key] = {"error": str(ex)[:160]}
+        if line is not None:
+            if "random_init_worst_case" in extra:
+                line["random_init_worst_case"] = extra.pop("random_init_worst_case")
+            if extra:
+                line["workloads"] = extra
+            for blk in [line.get("random_init_worst_case")] + list(line.get("workloads", {}).values()):
+                g = (blk or {}).get("parity", {}).get("golden") if blk else None
+                if g and g.get("checked") and blk.get("workload", "").find("copy-circuit") >= 0 and g["top1_identical"] != g["queries"]:
+                    line["parity_ok"] = False
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

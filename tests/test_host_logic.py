@@ -115,6 +115,33 @@ got = [gather_predictions(o) for o in fly.map(batches)]
 for i, g in enumerate(got):
     assert torch.equal(g, all_preds + 100 * i + 1), (rank, i)
 fly.close()
+# dynamic batch queue shared by both ranks (distributed.BatchQueue) + ONE indexed gather at the end: every batch index is
+# handed out exactly once whoever asks, a slow rank simply draws fewer batches, every rank ends with all predictions in order
+from translation_transformer_b200.distributed import BatchQueue, gather_indexed_predictions
+n_b = 13
+q = BatchQueue(n_b)
+fly = InFlightDecoder([Gen(), Gen()], device=None)
+def next_item():
+    i = q.next()
+    if i is not None and rank == 1:
+        time.sleep(0.004)                # rank 1 is the slow one
+    return None if i is None else (i, all_preds[:4] + 1000 * i)
+done = fly.drain(next_item)
+mine = sorted(i for i, _ in done)
+counts = [torch.zeros(1, dtype=torch.int64) for _ in range(2)]
+dist.all_gather(counts, torch.tensor([len(mine)]))
+assert sum(int(c) for c in counts) == n_b, counts
+everything = gather_indexed_predictions([i for i, _ in done], [o for _, o in done], n_b)
+for i, o in enumerate(everything):
+    assert o is not None and torch.equal(o, all_preds[:4] + 1000 * i + 1), (rank, i)
+q2 = BatchQueue(3)                        # a second queue of the job gets its own counter
+got2 = []
+while (i := q2.next()) is not None:
+    got2.append(i)
+tot = [torch.zeros(1, dtype=torch.int64) for _ in range(2)]
+dist.all_gather(tot, torch.tensor([len(got2)]))
+assert sum(int(c) for c in tot) == 3
+fly.close()
 dist.destroy_process_group()
 print("ok", rank)
 """
@@ -203,3 +230,86 @@ def test_in_flight_decoder_keeps_submission_order_and_bounds_concurrency():
     other.model = shared.model
     with pytest.raises(AssertionError):
         InFlightDecoder([shared, other], device=None)
+
+
+def test_batch_queue_and_drain_single_process():
+    """Without a process group the queue is a local counter; `InFlightDecoder.drain` decodes every item exactly once."""
+    from translation_transformer_b200.distributed import BatchQueue, gather_indexed_predictions
+    from translation_transformer_b200.pipeline import InFlightDecoder
+
+    class E:
+        pass
+
+    class G:
+        def __init__(self):
+            self.model = E()
+
+        def generate(self, src):
+            if int(src[0]) == 4:
+                raise RuntimeError("reference failure mode")
+            return src * 3
+
+    q = BatchQueue(9)
+    dec = InFlightDecoder([G(), G(), G()], device=None)
+    failed = []
+    done = dec.drain(lambda: (lambda i: None if i is None else (i, torch.tensor([i, 1])))(q.next()),
+                     post=lambda o: o + 1, on_error=lambda k, ex: failed.append(k))
+    assert sorted(k for k, _ in done) == list(range(9)) and failed == [4]
+    good = [(k, o) for k, o in done if o is not None]
+    ordered = gather_indexed_predictions([k for k, _ in good], [o for _, o in good], 9)
+    assert ordered[4] is None and all(ordered[i].tolist() == [3 * i + 1, 4] for i in range(9) if i != 4)
+    assert q.next() is None
+    dec.close()
+
+
+def test_on_predict_end_report_has_the_reference_keys(capsys, tmp_path):
+    """lightning_model.py:218-235 of the reference: key set and order of the report, acceptance rate of the beam search."""
+    import json
+    from translation_transformer_b200.lightning_model import VanillaEncoderDecoderTransformerLightning as M
+    m = M.__new__(M)
+
+    class Gen:
+        model_calls_num, accepted_tokens_num, produced_non_pad_tokens = 40, 300, 400
+
+    m.generators, m.generation, m.batch_size, m.max_len, m.n_drafts, m.draft_len = [Gen(), Gen()], "beam_search_speculative", 4, 200, 23, 10
+    m.report_prediction_time, m.report_prediction_file, m.tgt_test_path = True, str(tmp_path / "r" / "report.txt"), "data/tgt-test.txt"
+    m.on_predict_start()
+    m.on_predict_end()
+    rep = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert list(rep) == ["algorithm", "batch_size", "tgt_test_path", "max_len", "total_seconds", "model_calls", "seconds_per_model_call",
+                         "n_drafts", "draft_len", "accepted_tokens", "acceptance_rate"]
+    assert rep["model_calls"] == 80 and rep["accepted_tokens"] == 600 and rep["acceptance_rate"] == 0.75 and rep["tgt_test_path"] == "data/tgt-test.txt"
+    assert json.loads(open(m.report_prediction_file).read()) == rep
+    m.generation = "greedy_speculative"
+    m.on_predict_end()
+    rep = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert "accepted_tokens" not in rep and rep["n_drafts"] == 23
+    m.generation = "greedy"
+    m.on_predict_end()
+    assert "n_drafts" not in json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+
+def test_copy_task_weights_behave_like_a_trained_copier():
+    """weights.copy_task_state_dict (bench.py --weights copy): teacher-forced, the ORACLE transformer with these weights predicts
+    the permuted source token at (almost) every position with a healthy margin, and EOS where the source ends."""
+    from oracle.transformer import OracleTransformer
+    from translation_transformer_b200.synthetic import synthetic_sources
+    from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, copy_task_state_dict
+    cfg = ModelConfig(src_vocab_size=288, tgt_vocab_size=288, **PRODUCT_PREDICTION)
+    sd = copy_task_state_dict(cfg, 1234)
+    again = copy_task_state_dict(cfg, 1234)
+    assert all(torch.equal(sd[k], again[k]) for k in sd)           # deterministic
+    src = synthetic_sources(6, 288, seed=100003)
+    Wc = sd["next_token_classifier.weight"]
+    emb = sd["src_token_featurizer.embedding.weight"]
+    # the token emitted for a copied source token t: the classifier row that reads emb[t]
+    perm = (Wc @ emb.t()).argmax(0)
+    assert int((perm != torch.arange(288)).sum()) == round(0.08 * 284)
+    logits = OracleTransformer(sd, cfg.num_heads)(src, src[:, :-1])
+    mask = src[:, 1:] != 0
+    ok = (logits.argmax(-1) == perm[src[:, 1:]]) & mask
+    assert ok.sum() >= 0.99 * mask.sum()
+    top2 = logits.topk(2, -1).values
+    assert torch.quantile((top2[..., 0] - top2[..., 1])[mask], 0.02) > 3.0   # trained-like margins: bf16 keeps the arg-max
+    eos_pos = (src == 2).float().argmax(-1) - 1
+    assert (logits.argmax(-1)[torch.arange(6), eos_pos] == 2).all()

@@ -82,6 +82,34 @@ class InFlightDecoder:
                     raise
                 yield on_error(i, ex)
 
+    def drain(self, next_item: Callable, pre: Callable | None = None, post: Callable | None = None,
+              on_error: Callable | None = None) -> list:
+        """Dynamic batch queue: every worker keeps pulling `(key, src)` pairs from `next_item()` (which must be thread-safe and
+        return None once the queue is empty — e.g. a counter shared by all ranks of a job, distributed.BatchQueue) and
+        decodes them on its own engine; returns the `(key, result)` pairs this decoder processed, in completion order.
+        No static assignment of batches to workers or ranks: a slow batch never holds back the rest of a shard."""
+        done: list = []
+
+        def worker():
+            while True:
+                item = next_item()
+                if item is None:
+                    return
+                key, src = item
+                try:
+                    res = self._job(src, pre, post)
+                except RuntimeError as ex:
+                    if on_error is None:
+                        raise
+                    res = on_error(key, ex)
+                with self._lock:
+                    done.append((key, res))
+
+        futures = [self._pool.submit(worker) for _ in self.generators]
+        for f in futures:
+            f.result()
+        return done
+
     def counter(self, name: str):
         """Sum of a per-generator counter (`model_calls_num`, `accepted_tokens_num`, ...)."""
         return sum(getattr(g, name) for g in self.generators)

@@ -121,7 +121,7 @@ def random_init_state_dict(cfg: ModelConfig, seed: int) -> dict:
     return sd
 
 
-def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.04, damp: float = 0.05, sharpness: float = 60.0,
+def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.08, damp: float = 0.05, sharpness: float = 60.0,
                          gain: float = 8.0, alpha: float = 0.05, pad_bias: float = -5.0) -> dict:
     """Synthetic stand-in for a TRAINED reaction model (checkpoints are not available offline): the random-init weights
     of `random_init_state_dict(cfg, seed)` with a deterministic "copy circuit" laid over them, so that the model behaves
@@ -149,6 +149,7 @@ def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.04, da
     assert cfg.share_embeddings and cfg.src_vocab_size == V and H >= 2 and HD % 2 == 0
     emb = sd["src_token_featurizer.embedding.weight"]
     emb[:, :HD] = 0                                   # dimensions [0, HD) carry the positional code alone
+    emb[:, E - 2] = 0                                 # ... and so does dimension E - 2 (see below)
     sd["tgt_token_featurizer.embedding.weight"] = emb
     for k in sd:
         if k.endswith("out_proj.weight") or k.endswith("linear2.weight") or k.endswith("linear2.bias"):
@@ -163,7 +164,7 @@ def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.04, da
     Wc[perm] = alpha * emb
     sd["next_token_classifier.weight"] = Wc
     sd["next_token_classifier.bias"][cfg.tgt_pad_token_idx] += pad_bias
-    sd["next_token_classifier.bias"][1] += 2.0 * pad_bias    # BOS is never predicted (a trained model does not either)
+    sd["next_token_classifier.bias"][1] += 8.0 * pad_bias    # BOS is never predicted (a trained model does not either)
     p = f"transformer.decoder.layers.{cfg.num_decoder_layers - 1}.multihead_attn"
     Win = torch.zeros(3 * E, E)
     omega = torch.exp(torch.arange(0, E, 2).float() * (-math.log(10000.0) / E))[:HD // 2]
@@ -172,20 +173,17 @@ def copy_task_state_dict(cfg: ModelConfig, seed: int, mismatch: float = 0.04, da
         c, s_ = math.cos(float(omega[i])), math.sin(float(omega[i]))
         R[2 * i, 2 * i], R[2 * i, 2 * i + 1] = c, s_
         R[2 * i + 1, 2 * i], R[2 * i + 1, 2 * i + 1] = -s_, c
-    # LayerNorm subtracts the mean over all E dimensions, which the slow (nearly constant) cosine dimensions of the code
-    # push to mu0 > 0; the projection biases add it back so that queries and keys see the plain sinusoidal code
-    pe_mid = [math.sin(40.0 * float(w)) for w in torch.exp(torch.arange(0, E, 2).double() * (-math.log(10000.0) / E))] + \
-             [math.cos(40.0 * float(w)) for w in torch.exp(torch.arange(0, E, 2).double() * (-math.log(10000.0) / E))]
-    mu0 = sum(pe_mid) / E
-    sigma0 = math.sqrt((E - HD) / E + sum(v * v for v in pe_mid) / E - mu0 * mu0)
-    shift = torch.full((HD,), mu0 / sigma0)
+    # LayerNorm subtracts the mean mu over all E dimensions from the code (and divides by sigma).  Dimension E - 2 holds
+    # sin(position x slowest frequency) ~ 0 and no token embedding, so after LayerNorm it reads -mu / sigma: subtracting
+    # it from every code dimension inside the projections restores the plain sinusoidal code (scaled by 1 / sigma)
     Bin = torch.zeros(3 * E)
     Wo = torch.zeros(E, E)
+    ones = torch.ones(HD)
     for h in range(H):
         Win[h * HD:(h + 1) * HD, :HD] = sharpness * R
-        Bin[h * HD:(h + 1) * HD] = sharpness * (R @ shift)
+        Win[h * HD:(h + 1) * HD, E - 2] = -sharpness * (R @ ones)
         Win[E + h * HD:E + (h + 1) * HD, :HD] = torch.eye(HD)
-        Bin[E + h * HD:E + (h + 1) * HD] = shift
+        Win[E + h * HD:E + (h + 1) * HD, E - 2] = -ones
         if h < H - 1:                                 # head h carries embedding dimensions [HD (h + 1), HD (h + 2))
             Win[2 * E + h * HD:2 * E + (h + 1) * HD, HD * (h + 1):HD * (h + 2)] = torch.eye(HD)
             Wo[HD * (h + 1):HD * (h + 2), h * HD:(h + 1) * HD] = gain * torch.eye(HD)

@@ -12,12 +12,13 @@ through the public generator classes (`TranslationInferenceGreedySpeculative.gen
     retro   single-step retrosynthesis (6+6 layers), speculative beam search, bs 8, n_best 10, draft_len 10, n_drafts 2
             (configs[3]; scripts/single_step_retrosynthesis.sh:166-174), USPTO-50k-shape sources
 
-Weights (`--weights`): `copy` (default) = random-init weights with the deterministic copy circuit of
+Weights (`--weights`): `random` (default, what BASELINE.json's north_star names) = plain random init: nothing ever emits EOS,
+every batch decodes all its queries to the width limit and the reference returns all-PAD rows -- the worst case and a
+fixed amount of work per step; `copy` = the same random-init weights with the deterministic copy circuit of
 `weights.copy_task_state_dict` laid over them, a stand-in for a TRAINED model (no checkpoints offline): predictions
 follow the source, drafts are accepted at realistic rates, every query ends with EOS at its own length, so batches
-retire query by query; `random` = plain random init (round-1 headline: nothing ever finishes, every batch decodes 32
-queries to the width limit and returns all-PAD rows: the worst case).  The default line reports both (the second as
-`random_init_worst_case`) and, on one GPU, the beam / retro workloads as `workloads`.
+retire query by query and the predictions are real token sequences.  The default line reports both (the second as
+`trained_like`) and, on one GPU, the beam / retro workloads (trained-like weights) as `workloads`.
 
 The timed batches are drawn from ONE queue shared by all ranks and in-flight engines (`distributed.BatchQueue`): nobody
 owns a static shard.  `--scaling weak` (default) times N*K batches on N GPUs, `--scaling strong` a fixed set of
@@ -72,7 +73,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="greedy", choices=list(WORKLOADS))
-    ap.add_argument("--weights", default="copy", choices=["copy", "random"])
+    ap.add_argument("--weights", default="random", choices=["random", "copy"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--queries", type=int, default=4096, help="size of the fixed query set of --scaling strong")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -330,6 +331,33 @@ def compare_with_golden(wl, out):
     return res
 
 
+def compare_trace_with_golden(wl, gen_traced, src_dev):
+    """All-PAD predictions say nothing (random-init weights never finish), so the loop itself is compared: the accepted length
+    and the chosen draft of every (iteration, live query) of a traced decode of batch 0 against what the unmodified reference
+    did on the same batch (recorded through hooks, tests/golden/make_golden_bench.py).  fp32 engines reproduce every cell
+    (tests/test_gpu_bench_configs.py); the bf16 engine follows the reference until the first near-tie of two logits flips."""
+    if wl.kind != "greedy" or wl.golden_id is None or not (REPO / "tests/golden/bench_configs.npz").exists():
+        return None
+    z = np.load(REPO / "tests/golden/bench_configs.npz")
+    if wl.golden_id + "_nacc" not in z.files:
+        return None
+    N = wl.w["n_drafts"]
+    ref_nacc = z[wl.golden_id + "_nacc"].astype(np.int64).reshape(-1, N)
+    ref_pick = z[wl.golden_id + "_pick"].astype(np.int64)
+    ref_acc = ref_nacc[np.arange(len(ref_pick)), ref_pick]
+    try:
+        gen_traced.generate(src_dev)
+    except RuntimeError:
+        pass
+    nacc = np.array([a for t in gen_traced.trace for a in t["n_accepted"]], dtype=np.int64)
+    pick = np.array([p_ for t in gen_traced.trace for p_ in t["draft_index"]], dtype=np.int64)
+    n = min(len(nacc), len(ref_acc))
+    eq = (nacc[:n] == ref_acc[:n]) & (pick[:n] == ref_pick[:n])
+    return {"cells": int(n), "reference_cells": int(len(ref_acc)), "cells_identical": int(eq.sum()),
+            "first_differing_cell": int(np.argmax(~eq)) if (~eq).any() else int(n),
+            "what": "(iteration, live query) cells of batch 0: accepted length and chosen draft index vs the unmodified reference"}
+
+
 def compare_with_live_reference(wl, out, nq):
     """The reference (oracle/_ref, else the oracle port) decodes the first `nq` queries of batch 0 on the host now; the
     GPU rows for the same queries must carry the same tokens.  Returns (parity dict, cpu_baseline dict).  Greedy queries
@@ -549,6 +577,8 @@ def measure_workload(wl, args, local_rank, world, rank, n_fly, steps, warmup, n_
     parity = {}
     if rank == 0 and out0 is not None:
         parity["golden"] = compare_with_golden(wl, out0)
+        if parity["golden"] is not None and wl.kind == "greedy":
+            parity["golden"]["trace"] = compare_trace_with_golden(wl, wl.generator(R.engs[0], keep_trace=True), R.host_batch(0).to(R.dev))
     res["_out0"] = out0
     first = warmup
     lib, eng, gen = R.engs[0].lib, R.engs[0], R.gens[0]
@@ -739,8 +769,9 @@ def main():
     if world == 1 and not args.no_extra_workloads and args.scaling == "weak":
         extra = {}
         todo = []
-        if args.workload == "greedy" and args.weights == "copy":
-            todo.append(("random_init_worst_case", Workload("greedy", "random", args), 6, True))
+        if args.workload == "greedy":
+            other = "copy" if args.weights == "random" else "random"
+            todo.append(("trained_like" if other == "copy" else "random_init_worst_case", Workload("greedy", other, args), 18 if other == "copy" else 6, True))
         if args.workload == "greedy":
             todo += [("beam", Workload("beam", "copy", args), 6, False), ("retro", Workload("retro", "copy", args), 6, False)]
         for key, w2, k2, full in todo:
@@ -754,18 +785,22 @@ def main():
                        "gpu_launches": m2["launches"], "failed_batches": m2["failed_batches"], "parity": m2["parity"]}
                 if full:
                     blk["roofline"], blk["roofline_all"] = roofline_tables(w2, args, m2, peaks)
+                if key == "trained_like" and not args.no_cpu_baseline and m2["_out0"] is not None:
+                    nq2 = min(w2.bs, max(4, args.cpu_queries))     # real token sequences: a few more queries cost a second
+                    blk["parity"]["live"], blk["cpu_baseline"] = compare_with_live_reference(w2, m2["_out0"][:nq2], nq2)
                 extra[key] = blk
             except (RuntimeError, AssertionError) as ex:
                 extra[key] = {"error": str(ex)[:160]}
         if line is not None:
-            if "random_init_worst_case" in extra:
-                line["random_init_worst_case"] = extra.pop("random_init_worst_case")
+            for key in ("trained_like", "random_init_worst_case"):
+                if key in extra:
+                    line[key] = extra.pop(key)
             if extra:
                 line["workloads"] = extra
-            for blk in [line.get("random_init_worst_case")] + list(line.get("workloads", {}).values()):
-                g = (blk or {}).get("parity", {}).get("golden") if blk else None
-                if g and g.get("checked") and blk.get("workload", "").find("copy-circuit") >= 0 and g["top1_identical"] != g["queries"]:
-                    line["parity_ok"] = False
+            for blk in [line.get("random_init_worst_case"), line.get("trained_like")] + list(line.get("workloads", {}).values()):
+                for g in ((blk or {}).get("parity") or {}).values():
+                    if g and g.get("checked") and g["top1_identical"] != g["queries"]:
+                        line["parity_ok"] = False
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -169,3 +169,35 @@ def test_beam_bench_config_bf16_vs_reference(dev, case, record_property):
     record_property("bf16_vs_reference", json.dumps(report))
     assert top1 >= 0.75 and set_frac >= 0.6, report
     eng.close()
+
+
+def test_tcgen05_attention_matches_mma_sync_attention(dev, monkeypatch):
+    """csrc/attention_tc.cu (S in tensor memory, transposed value caches) against csrc/attention_mma.cu inside the greedy loop:
+    trained-like weights -> identical tokens and accepted lengths; random-init weights -> the same trajectory until two
+    logits tie within bf16 noise (at least 32 (iteration, query) cells, as against the fp32 reference)."""
+    from translation_transformer_b200.decoding import TranslationInferenceGreedySpeculative
+    z = load_npz("bench_configs.npz")
+    for name in ("cfg1_copy", "cfg1_random"):
+        case = [c for c in _cases("greedy") if c["id"] == name][0]
+        cfg, sd = _weights(case)
+        src = _sources(case, z).to(dev)
+        runs = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("TTB_ATTN_TC", flag)
+            eng = _engine(cfg, sd, "bf16")
+            gen = TranslationInferenceGreedySpeculative(eng, case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2, 7, keep_trace=True)
+            out = gen.generate(src).cpu().numpy()
+            nacc = np.array([a for t in gen.trace for a in t["n_accepted"]], dtype=np.int64)
+            gen2 = TranslationInferenceGreedySpeculative(eng, case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2, 7)
+            assert np.array_equal(gen2.generate(src).cpu().numpy(), out)            # graph replay == eager
+            runs[flag] = (out, nacc, gen.model_calls_num)
+            eng.close()
+        (o0, n0, c0), (o1, n1, c1) = runs["0"], runs["1"]
+        n = min(len(n0), len(n1))
+        first = int(np.argmax(n0[:n] != n1[:n])) if (n0[:n] != n1[:n]).any() else n
+        print(f"{name}: tcgen05 vs mma.sync attention: first differing cell {first} of {n}, calls {c1} vs {c0}")
+        if name == "cfg1_copy":
+            assert np.array_equal(o0, o1) and first == n and c0 == c1
+            assert np.array_equal(o1, z[name + "_out"].astype(np.int64))
+        else:
+            assert first >= 32

@@ -143,7 +143,7 @@ struct ttb_engine {
     // forward workspace (typed by the precision's activation type at use)
     DevBuf x, xh, y, qkv, att, q2, hid, logits, tok32, keytok32, pred;
     // encoder products / decoding state
-    DevBuf src32, srclen, desc, memory, memh, crosskv, kcache, vcache, kcache2, vcache2, drafts, gen, front, active, ctrl, sel, out64;
+    DevBuf src32, srclen, desc, memory, memh, crosskv, crossvt, kcache, vcache, kcache2, vcache2, drafts, gen, front, active, ctrl, sel, out64;
     int* h_ctrl = nullptr;  // pinned snapshots of ctrl for lagged polling
     cudaEvent_t poll_ev[4]{};
     cudaEvent_t t0{}, t1{};
@@ -170,7 +170,7 @@ struct ttb_engine {
     // different host threads, translation_transformer_b200/pipeline.py)
     long long alloc_signature() const {
         const DevBuf* bufs[] = {&x, &xh, &y, &qkv, &att, &q2, &hid, &logits, &tok32, &keytok32, &pred, &src32, &srclen, &desc, &memory, &memh,
-                                &crosskv, &kcache, &vcache, &kcache2, &vcache2, &drafts, &gen, &front, &active, &ctrl, &sel, &out64, &beam, &hist};
+                                &crosskv, &crossvt, &kcache, &vcache, &kcache2, &vcache2, &drafts, &gen, &front, &active, &ctrl, &sel, &out64, &beam, &hist};
         unsigned long long h = 1469598103934665603ull;
         for (const DevBuf* b : bufs) {
             h = (h ^ (unsigned long long)reinterpret_cast<uintptr_t>(b->p)) * 1099511628211ull;
@@ -613,7 +613,13 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float)) || e->srclen.ensure((size_t)B * sizeof(int))) return 1;
     if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
     if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
-    if (e->kcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT)) || e->vcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT))) return 1;
+    // tcgen05 attention inside the loop (bf16, head_dim 32, key counts within its tensor-memory budget): the value caches
+    // are kept transposed ([dim][position], pitch VT_PITCH) so that both products read K-major operands
+    constexpr int VT_PITCH = 256;
+    const bool tc_attn = Prec<ActT>::lowp && !attn_simt_forced() && attention_tc_supported(HD, per_q, std::max(P, Ls), D + 1);
+    const size_t vcache_bytes = tc_attn ? (size_t)n_dec * B * E * VT_PITCH * sizeof(ActT) : (size_t)n_dec * B * P * E * sizeof(ActT);
+    if (e->kcache.ensure((size_t)n_dec * B * P * E * sizeof(ActT)) || e->vcache.ensure(vcache_bytes)) return 1;
+    if (tc_attn && e->crossvt.ensure((size_t)n_dec * B * E * VT_PITCH * sizeof(ActT))) return 1;
     if (e->drafts.ensure((size_t)B * N * D * sizeof(int)) || e->gen.ensure((size_t)B * gen_ld * sizeof(int))) return 1;
     if (e->front.ensure(B * sizeof(int)) || e->active.ensure(B * sizeof(int)) || e->ctrl.ensure(CTRL_COUNT * sizeof(int))) return 1;
     if (e->sel.ensure((size_t)B * 4 * sizeof(int)) || e->out64.ensure((size_t)B * max_len * sizeof(long long))) return 1;
@@ -631,6 +637,18 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
     ActT* crosskv = e->crosskv.as<ActT>();
     if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s, TS_cap * 2 * E)) return 1;
+    const long long vt_q_stride = (long long)E * VT_PITCH, vt_l_stride = (long long)B * E * VT_PITCH;
+    if constexpr (Prec<ActT>::lowp) {
+        if (tc_attn) {
+            // every position a product can touch must hold a finite number (masked keys get probability 0, and 0 x NaN = NaN)
+            TTB_CUDA_OK(cudaMemsetAsync(e->vcache.p, 0, vcache_bytes, s));
+            TTB_CUDA_OK(cudaMemsetAsync(e->crossvt.p, 0, (size_t)n_dec * B * E * VT_PITCH * sizeof(ActT), s));
+            for (int l = 0; l < n_dec; ++l) {
+                Scope sc(e, KC_ENCODER, s);
+                launch_transpose_v(crosskv + (long long)l * TS_cap * 2 * E + E, 2 * E, B, Ls, E, e->crossvt.as<ActT>() + (long long)l * vt_l_stride, VT_PITCH, s);
+            }
+        }
+    }
     // drafts from the source without its BOS column (speculative_decoding.py:64-73)
     if (!standard) { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D, N, eos, pad, replace, e->drafts.as<int>(), s); }
 
@@ -652,12 +670,28 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     RowCount rows((int)T, n_active, per_q);
 
     auto self_attn = [&](int l, ActT* qkv, ActT* att) {
+        if constexpr (Prec<ActT>::lowp) {
+            if (tc_attn) {
+                launch_spec_self_attention_tc(qkv, 3 * E, kc + l * cache_l_stride, cache_q_stride, E, vc + l * vt_l_stride, vt_q_stride, VT_PITCH, att, E,
+                                              B, n_active, st.gen, gen_ld, e->d.tgt_pad_token_idx, N, D, H, st.desc, s);
+                return;
+            }
+        }
         spec_attn(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
                                          att, E, B, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
                                          N, D, H, HD, P, s, st.desc);
     };
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
         const ActT* kv = crosskv + (long long)l * TS_cap * 2 * E;
+        if constexpr (Prec<ActT>::lowp) {
+            if (tc_attn) {
+                // the K/V rows of a query start at row query * Ls of the layer's block (the batch's own source length, read on the
+                // device by the kernel: the row stride of a group is Ls * 2E elements)
+                launch_cross_attention_tc(q2, E, kv, 2 * E, (long long)Ls * 2 * E, e->crossvt.as<ActT>() + (long long)l * vt_l_stride, vt_q_stride, VT_PITCH,
+                                          att, E, B, n_active, per_q, src32, Ls, e->d.src_pad_token_idx, st.ctrl + CTRL_LS, H, st.desc, s);
+                return;
+            }
+        }
         attn(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
              src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS, e->srclen.as<int>(), st.desc);
     };
@@ -666,7 +700,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
         {   // KV-cache append of the previous iteration's accepted tokens + embedding of this iteration's step tokens
             Scope sc(e, KC_EMBED, s);
             launch_greedy_advance<ActT>(st, e->tgt_emb, e->pe, E, x, xh, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, kc, vc,
-                                        cache_l_stride, cache_q_stride, E, s);
+                                        cache_l_stride, cache_q_stride, E, s, tc_attn ? vt_l_stride : 0, tc_attn ? vt_q_stride : 0, tc_attn ? VT_PITCH : 0);
         }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
         bool fused_cls = false;
@@ -698,7 +732,8 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     static const int graph_iters = [] { const char* v = getenv("TTB_GRAPH_ITERS"); const int k = v ? atoi(v) : 4; return k < 1 ? 1 : (k > 16 ? 16 : k); }();
     const int K_it = use_graph ? graph_iters : 1;
     if (use_graph) {
-        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, e->alloc_signature(), (long long)sizeof(ActT) + 16 * K_it, replace};
+        const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, e->alloc_signature(),
+                                   (long long)sizeof(ActT) + 16 * K_it + (tc_attn ? 1024 : 0), replace};
         if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
             const long long l0 = e->launches;
@@ -1234,7 +1269,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     }
     DevBuf* bufs[] = {&e->x, &e->xh, &e->y, &e->qkv, &e->att, &e->q2, &e->hid, &e->logits, &e->tok32, &e->keytok32, &e->pred,
                       &e->src32, &e->memory, &e->memh, &e->crosskv, &e->kcache, &e->vcache, &e->drafts, &e->gen, &e->front,
-                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam, &e->srclen, &e->desc, &e->kcache2, &e->vcache2};
+                      &e->active, &e->ctrl, &e->sel, &e->out64, &e->hist, &e->beam, &e->srclen, &e->desc, &e->kcache2, &e->vcache2, &e->crossvt};
     for (DevBuf* b : bufs) b->release();
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);

@@ -102,6 +102,19 @@ void launch_spec_self_attention_mma(const __nv_bfloat16* qkv, int qkv_ld, const 
                                     const int* gen, int gen_ld, int pad_id, int N, int D,
                                     int heads, int head_dim, cudaStream_t s, const int4* desc = nullptr);
 
+// ---- attention_tc.cu : tcgen05 attention of the decoding loops (head_dim 32, S in tensor memory, V caches kept transposed) ----
+bool attention_tc_supported(int head_dim, int Lq, int max_shared_keys, int row_len);
+// out[(g * E + c) * pitch + j] = in[(g * L + j) * ld + c]
+void launch_transpose_v(const __nv_bfloat16* in, int ld, int groups, int L, int E, __nv_bfloat16* out, int pitch, cudaStream_t s);
+int launch_cross_attention_tc(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* k, int k_ld, long long k_group_stride,
+                              const __nv_bfloat16* vt, long long vt_group_stride, int vt_pitch, __nv_bfloat16* out, int out_ld,
+                              int n_groups_max, const int* n_groups_dev, int Lq, const int* key_tok, int key_tok_stride, int pad_id,
+                              const int* lk_dev, int heads, const int4* desc, cudaStream_t s);
+int launch_spec_self_attention_tc(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* kcache, long long k_query_stride, int k_ld,
+                                  const __nv_bfloat16* vtcache, long long vt_query_stride, int vt_pitch, __nv_bfloat16* out, int out_ld,
+                                  int B_max, const int* n_active_dev, const int* gen, int gen_ld, int pad_id, int N, int D, int heads,
+                                  const int4* desc, cudaStream_t s);
+
 // ---- drafting.cu ------------------------------------------------------------------------------
 // Mirrors utils/drafting.py::make_drafts on device; src is (B, L) int32 with row stride src_ld (the
 // caller skips the BOS column by passing src + 1, L - 1).  out is (B, N, Deff) int32.
@@ -134,7 +147,9 @@ void launch_greedy_init(const GreedyState& st, cudaStream_t s);
 template <typename ActT>
 void launch_greedy_advance(const GreedyState& st, const float* table, const float* pe, int E, float* x, ActT* xh,
                            const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld, ActT* kcache, ActT* vcache,
-                           long long cache_layer_stride, long long cache_query_stride, int cache_ld, cudaStream_t s);
+                           long long cache_layer_stride, long long cache_query_stride, int cache_ld, cudaStream_t s,
+                           long long vt_layer_stride = 0, long long vt_query_stride = 0, int vt_pitch = 0);
+// vt_pitch > 0: `vcache` is the TRANSPOSED value cache [layer][query][E][vt_pitch] of the tcgen05 attention kernel
 // picks the best draft per live query, appends tokens, retires finished queries, plans next width
 void launch_greedy_accept(const GreedyState& st, cudaStream_t s);
 // standard greedy decoding (no drafts: N = 1, D = 0): appends the predicted token of every row, stop test

@@ -85,9 +85,11 @@ def parse():
     ap.add_argument("--no-insitu", action="store_true", help="skip the extra CUPTI-profiled step (kernels_in_situ)")
     ap.add_argument("--no-extra-workloads", action="store_true", help="only the selected workload (no random-init / beam / retro side figures)")
     ap.add_argument("--tie-break", default="torch_cpu", choices=["torch_cpu", "lowest_index"])
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=0,
                     help="batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
-                         "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`")
+                         "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`; 0 (default) = 3 "
+                         "for the random-init greedy workload (every batch keeps all its queries to the end) and 6 for workloads whose "
+                         "batches thin out while they decode (measured: DESIGN.md section 4c)")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
 
@@ -719,8 +721,12 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
-    n_fly = max(1, args.in_flight)
     wl = Workload(args.workload, args.weights, args)
+
+    def fly_for(w):
+        return args.in_flight if args.in_flight > 0 else (3 if (w.kind == "greedy" and w.weights == "random") else 6)
+
+    n_fly = fly_for(wl)
     if args.scaling == "strong":
         n_batches = max(1, args.queries // wl.bs)
     else:
@@ -773,12 +779,13 @@ def main():
             other = "copy" if args.weights == "random" else "random"
             todo.append(("trained_like" if other == "copy" else "random_init_worst_case", Workload("greedy", other, args), 18 if other == "copy" else 6, True))
         if args.workload == "greedy":
-            todo += [("beam", Workload("beam", "copy", args), 6, False), ("retro", Workload("retro", "copy", args), 6, False)]
+            todo += [("beam", Workload("beam", "copy", args), 12, False), ("retro", Workload("retro", "copy", args), 12, False)]
         for key, w2, k2, full in todo:
             try:
-                m2 = measure_workload(w2, args, local_rank, 1, 0, n_fly, k2, 2, k2, full=full)
+                n_fly2 = fly_for(w2)
+                m2 = measure_workload(w2, args, local_rank, 1, 0, n_fly2, k2, 2, k2, full=full)
                 blk = {"workload": w2.describe(), "metric": w2.w["metric"], "value": m2["value"], "unit": "SMILES/s", "steps": k2,
-                       "ms_per_step": m2["ms"] / k2, "batches_in_flight": n_fly,
+                       "ms_per_step": m2["ms"] / k2, "batches_in_flight": n_fly2,
                        "e2e": {"value": m2["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": m2["h2d"], "d2h_bytes_per_step": m2["d2h"]},
                        "one_batch_in_flight": {"value": m2["one_value"], "ms_per_step": m2["one_ms"] / m2["one_batches"]} if m2["one_value"] else None,
                        "decoder_calls_per_batch": m2["calls"] / k2, "accepted_tokens_per_call": m2["accepted"] / max(m2["calls"], 1),

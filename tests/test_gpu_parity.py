@@ -616,3 +616,31 @@ def test_batches_in_flight_give_the_sequential_predictions(dev, generation):
         assert a == b if isinstance(a, str) else torch.equal(a, b)
     for m in model.models:
         m.close()
+
+
+def test_lightning_checkpoint_state_dict_loads(dev):
+    """A reference Lightning checkpoint's `state_dict` (keys prefixed `model.`, plus the non-persistent positional buffer that
+    some exports carry) goes through `load_checkpoint_state_dict` (lightning_model.py:73 of the reference builds the same
+    prefix) and decodes like an engine built from the plain state dict."""
+    from translation_transformer_b200.data_handling import ChemSMILESTokenizer
+    from translation_transformer_b200.lightning_model import VanillaEncoderDecoderTransformerLightning
+    from translation_transformer_b200.model import sinusoid_table
+    from helpers import SMALL
+    meta = load_json("model_forward.json")
+    tk, src, _ = test_file_sources(meta["vocab"])
+    cfg = ModelConfig(src_vocab_size=tk.n_tokens, tgt_vocab_size=tk.n_tokens, **SMALL)
+    sd = {k: v.clone() for k, v in random_init_state_dict(cfg, 33).items()}
+    sd["next_token_classifier.bias"][2] += 0.5
+    sd["next_token_classifier.bias"][0] -= 5.0
+    kw = dict(src_tokenizer=tk, tgt_tokenizer=tk, generation="greedy_speculative", max_len=60, n_drafts=5, draft_len=6, precision="fp32",
+              share_embeddings=False, **SMALL)
+    a = VanillaEncoderDecoderTransformerLightning(state_dict=sd, **kw)
+    b = VanillaEncoderDecoderTransformerLightning(seed=5, **kw)                 # other weights first
+    ckpt = {"model." + k: v for k, v in sd.items()}
+    ckpt["model.positional_encoding.pe"] = sinusoid_table(SMALL["embedding_dim"], 5000)
+    b.load_checkpoint_state_dict(ckpt)
+    batch = {"src_tokens": src[:4].to(dev)}
+    ra, rb = a.predict_step(batch, 0), b.predict_step(batch, 0)
+    assert torch.equal(ra, rb) and (ra != 0).any()
+    for m in a.models + b.models:
+        m.close()

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "../../include/ttb200.h"
 
+#include <sched.h>
 #include <cmath>
 #include <cstdlib>
 #include <atomic>
@@ -36,6 +37,14 @@ int ensure_dyn_smem(const void* kernel, int bytes) {
     }
     have = bytes;
     return 0;
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
 }
 
 bool pdl_enabled() {
@@ -1040,6 +1049,9 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             for (long spin = 0; !seen; ++spin) {
                 w = *word;
                 seen = (unsigned)(w >> 32) == (unsigned)(iters + 1);
+                // the word normally arrives within a few microseconds of the last launch call; past that (long iterations,
+                // several engines per GPU and ranks per box sharing the cores) the thread gives its core away between polls
+                if (!seen) { if (spin < 256) cpu_relax(); else sched_yield(); }
                 if (!seen && (spin & 0x3FFF) == 0x3FFF) {
                     const cudaError_t q = cudaStreamQuery(s);
                     if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy

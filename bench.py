@@ -509,12 +509,18 @@ class Runner:
             i = q.next()
             return None if i is None else (first + i, first + i)
 
+        tls = threading.local()
+
         def pre(j):
+            tls.j = j
             self.flush.zero_()                                   # on the worker's stream, like everything of its step
             return self.host_batch(j).to(self.dev, non_blocking=True) if e2e else resident[j]
 
         def post(o):
-            return wl.pad_out(o)
+            o = wl.pad_out(o)
+            if e2e:                                              # device -> pinned host copy of the step's prediction, on the worker's stream
+                out_hosts[tls.j].copy_(o, non_blocking=True)
+            return o
 
         def on_error(j, ex):   # reference-faithful failure modes (oracle/greedy_speculative.py); not counted as throughput
             failed.append(j)
@@ -524,16 +530,7 @@ class Runner:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         ev0.record()
-        if e2e:
-            def post_e2e(o, _oh=out_hosts):
-                return wl.pad_out(o)
-            done = decoder.drain(next_item, pre=pre, post=post_e2e, on_error=on_error)
-            for j, o in done:
-                if o is not None:
-                    out_hosts[j].copy_(o, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        else:
-            done = decoder.drain(next_item, pre=pre, post=post, on_error=on_error)
+        done = decoder.drain(next_item, pre=pre, post=post, on_error=on_error)
         good = [(j, o) for j, o in done if o is not None]
         # predictions of every rank collected once, in batch order (NCCL all-gather; identity on one GPU)
         gathered = gather_indexed_predictions([j - first for j, _ in good], [o for _, o in good], n_batches, device=self.dev)

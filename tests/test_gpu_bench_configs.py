@@ -201,3 +201,32 @@ def test_tcgen05_attention_matches_mma_sync_attention(dev, monkeypatch):
             assert np.array_equal(o1, z[name + "_out"].astype(np.int64))
         else:
             assert first >= 32
+
+
+@pytest.mark.parametrize("case", [c for c in _cases("beam") if c["n_best"] <= 16], ids=lambda c: c["id"])
+def test_fused_classifier_statistics_match_the_unfused_kernels(dev, case, monkeypatch):
+    """csrc/gemm_tcgen05.cu:classifier_stats_kernel (vocabulary projection + soft-max statistics + n_best largest logits
+    straight from tensor memory) against the logits GEMM + beam.cu:beam_stats_kernel it replaces on the bf16 path: the same
+    hypotheses, decoder calls and acceptance counters (the two differ only in the order of the soft-max sum)."""
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    z = load_npz("bench_configs.npz")
+    cfg, sd = _weights(case)
+    src = _sources(case, z).to(dev)
+    res = {}
+    monkeypatch.setenv("TTB_FUSED_STATS_WIDE", "1")      # n_best > 8 runs unfused by default (slower fused); exercised here
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TTB_NO_FUSED_STATS", flag)
+        eng = _engine(cfg, sd, "bf16")
+        gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"], case["vocab"],
+                                                        False, 0, 1, 2, 7, keep_trace=True)
+        out = gen.generate(src).cpu().numpy()
+        res[flag] = (out, gen.model_calls_num, gen.accepted_tokens_num, gen.gpu_launches,
+                     np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace]))
+        eng.close()
+    (o_un, c_un, a_un, l_un, n_un), (o_fu, c_fu, a_fu, l_fu, n_fu) = res["1"], res["0"]
+    assert l_fu < l_un                                   # one launch less per iteration
+    same = o_un.shape == o_fu.shape and np.array_equal(o_un, o_fu)
+    print(f"{case['id']}: fused vs unfused statistics: identical={same}, calls {c_fu}/{c_un}, accepted {a_fu}/{a_un}, launches {l_fu}/{l_un}")
+    assert c_fu == c_un and np.array_equal(n_fu, n_un)   # accepted length of every draft in every iteration
+    assert o_un.shape == o_fu.shape and (o_un[:, 0] == o_fu[:, 0]).all()          # best hypothesis of every query
+    assert (o_un == o_fu).all(-1).mean() >= 0.95         # the rest up to swaps of hypotheses whose scores differ in the last bits

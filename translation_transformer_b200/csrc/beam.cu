@@ -165,6 +165,10 @@ __global__ void beam_embed_cached_kernel(BeamState st, int beam, int dl, const f
         f = st.c_front[c];
         tok = (i == 0) ? st.cand_cur[(long long)c * st.ldw + f] : st.drafts[((long long)(c / beam) * st.N + n) * st.dl0 + i - 1];
     }
+    if (lane == 0 && st.row_tok) {   // the draft token at input position i is the "next draft token" of scored position i - 1
+        if (i >= 1) st.row_tok[t - 1] = tok;
+        if (i == dl) st.row_tok[t] = -1;
+    }
     const float* e = table + (long long)tok * E;
     const float* p = pe + (long long)(f + i + 1) * E;
     for (int col = lane; col < E; col += 32) {
@@ -287,11 +291,13 @@ __global__ void __launch_bounds__(256) beam_stats_kernel(BeamState st, const flo
     const float* p = logits + (long long)rp * V;
     float v[VPL];
     float mx = -INFINITY;
+    const int want = st.row_tok ? st.row_tok[rp] : -1;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         const int c = lane + 32 * k;
         v[k] = c < V ? p[c] : -INFINITY;
         mx = fmaxf(mx, v[k]);
+        if (c == want) st.tokv[rp] = v[k];
     }
     mx = warp_max(mx);
     float sum = 0.f;
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                 float term = 0.f;
                 if (i0 + lane < a) {
                     const long long rp = (long long)r * (dl + 1) + i0 + lane;
-                    term = ref_logprob(logits[rp * V + dr[i0 + lane]], st.lmax[rp], st.lsum[rp]);
+                    term = ref_logprob(st.tokv ? st.tokv[rp] : logits[rp * V + dr[i0 + lane]], st.lmax[rp], st.lsum[rp]);
                 }
                 const int cnt = min(32, a - i0);
                 for (int i = 0; i < cnt; ++i) {

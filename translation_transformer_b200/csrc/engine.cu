@@ -872,7 +872,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t o_rows = take((size_t)Rmax * ldw * 4), o_rc = take(Rmax * 4), o_rq = take(Rmax * 4), o_rs = take(Rmax * 4);
     const size_t n_rp = (size_t)Rmax * (D0 + 1);
     const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
-    const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4);
+    const size_t o_xg = take(n_rp * E * 4), o_xgh = take(n_rp * E * 2), o_lg = take(n_rp * V * 4), o_rt = take(n_rp * 4), o_tv = take(n_rp * 4);
     const size_t o_lc = take(Rmax * 4), o_lq = take(Rmax * 4), o_cf = take(Cmax * 4), o_np = take(Cmax * 4), o_nk = take(Cmax * 4), o_nr = take(Cmax * 4);
     const size_t o_tc = take(smart ? (size_t)B * V * 4 : 4), o_tl = take(smart ? (size_t)B * V * N * 4 : 4), o_cc = take(Cmax * 4),
                  o_cl = take(Cmax * 4), o_rd = take(Rmax * 4), o_ds = take(Rmax * 16), o_dc = take(Rmax * 16);
@@ -912,6 +912,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         st.host_ctrl = cudaHostGetDevicePointer(&dp, e->h_ctrl + 16, 0) == cudaSuccess ? static_cast<int*>(dp) : nullptr;
         (void)cudaGetLastError();
     }
+    if (cached) { st.row_tok = (int*)(base + o_rt); st.tokv = (float*)(base + o_tv); }
     st.live_cand = (int*)(base + o_lc); st.live_query = (int*)(base + o_lq); st.c_front = (int*)(base + o_cf);
     st.n_parent = (int*)(base + o_np); st.n_keep = (int*)(base + o_nk); st.n_row = (int*)(base + o_nr);
     st.tok_cnt = (int*)(base + o_tc); st.tok_list = (int*)(base + o_tl); st.c_cnt = (int*)(base + o_cc); st.c_last = (int*)(base + o_cl);
@@ -965,6 +966,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         // (beam.cu: BCX_W, BCX_ITER), so the steady state (C = B K, full draft length) is replayed as a CUDA graph.
         auto enqueue_iteration = [&]() -> int {
         const int R = C * N;
+        bool fused_stats = false;
         { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, dl, s); }
         if (cached) {
             RowCount rows(R * (dl + 1), n_live, dl + 1);
@@ -982,8 +984,20 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                      src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, nullptr, nullptr, st.desc_cross);
             };
             if (decoder_stack<ActT>(e, rows, n_dec, Tc * 3 * E, self_attn, cross_attn, s)) return 1;
-            // every decoder row is a scored position: logits straight from the residual stream
-            if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits, V, rows, false, s)) return 1;
+            // every decoder row is a scored position.  bf16 path: the projection is fused with the statistics the search reads
+            // (logits stay in tensor memory); otherwise logits straight from the residual stream + beam_stats below
+            if constexpr (Prec<ActT>::lowp) {
+                const char* nf = getenv("TTB_NO_FUSED_STATS");
+                if (!(nf && nf[0] == '1')) {
+                    Scope sc(e, KC_GEMM_CLASSIFIER, s);
+                    const int rc = launch_classifier_stats(xh, E, e->classifier.wh, e->classifier.b, rows, V, E, K, st.row_tok, st.tokv, st.lmax, st.lsum,
+                                                           st.nkeep, st.topv, st.topi, s);
+                    if (rc > 0) return 1;
+                    fused_stats = rc == 0;
+                    if (!fused_stats) e->launches--;
+                }
+            }
+            if (!fused_stats && linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits, V, rows, false, s)) return 1;
         } else {
             { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, W, dl, s); }
             RowCount rows(R * W, n_live, W);
@@ -1002,7 +1016,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             RowCount rp_rows(R * (dl + 1), n_live, dl + 1);
             if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
         }
-        { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
+        if (!fused_stats) { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, s); }
         // the expand kernel also closes the iteration: its last CTA writes the control words and, last, the iteration's
         // sequence number into pinned host memory; the host reads them while the caches are still being re-parented and

@@ -2181,6 +2181,204 @@ classifier_argmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
+
+// =====================================================================================================
+// Vocabulary projection fused with the per-distribution statistics of the speculative beam search (bf16 path): the
+// logits of a 128-row tile stay in tensor memory (as in classifier_argmax_kernel) and the epilogue reduces every row to
+// what beam_choose / beam_expand read (beam.cu): soft-max maximum and sum, the K largest logits in descending order
+// (ties: lower token id first) with their token ids, the size of the nucleus-truncated support, and the logit of the
+// row's own next draft token.  The (rows x V) fp32 logits matrix never exists in memory.
+//   thread = (row, half of the columns): pass 1 streams its columns through a sorted KT-entry list held in registers
+//   (an element enters only when it beats the current KT-th best: ~KT (1 + ln(columns / KT)) insertions per thread),
+//   the two halves meet in shared memory (the A tiles are dead once the accumulator is complete), pass 2 adds
+//   exp(logit - max) over the same columns, the lower half merges the two lists and writes the results.
+template <int KT>
+__global__ void __launch_bounds__(cls::THREADS, 1)
+classifier_stats_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                        const __grid_constant__ CUtensorMap tmWtail, const float* __restrict__ bias, RowCount rows, int V, int V_pad, int KB,
+                        int K, const int* __restrict__ row_tok, float* __restrict__ tokv, float* __restrict__ lmax, float* __restrict__ lsum,
+                        int* __restrict__ nkeep, float* __restrict__ topv, int* __restrict__ topi) {
+    const int m0 = blockIdx.x * BM;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    const int w_kb_bytes = V_pad * 128;
+    const uint32_t w_base = base + KB * A_BYTES;
+    float* bias_sm = reinterpret_cast<float*>(gen + KB * A_BYTES + KB * w_kb_bytes);
+    const uint32_t bar_base = base + KB * A_BYTES + KB * w_kb_bytes + V_pad * 4 + BM * 8;
+    auto full_bar = [&](int kb) { return bar_base + 8u * kb; };
+    const uint32_t tfull_bar = bar_base + 8u * 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar_base - base) + 8 * 17);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_main = V_pad < 256 ? V_pad : 256, n_tail = V_pad - n_main;
+    // exchange area of the two column halves (aliases the A tiles): [2][128] {max, token logit, found, partial sum},
+    // [2][KT][128] list values, [2][KT][128] list token ids
+    float4* xinfo = reinterpret_cast<float4*>(gen);
+    float* xv = reinterpret_cast<float*>(gen + 4096);
+    int* xi = reinterpret_cast<int*>(gen + 4096 + 2 * KT * BM * 4);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWtail)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) mbar_init(full_bar(kb), 1);
+            mbar_init(tfull_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2)
+        for (int c = threadIdx.x - 64; c < V_pad; c += 256) bias_sm[c] = (bias && c < V) ? __ldg(bias + c) : 0.f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                  // the live row count of the beam search is written inside the iteration: read it behind the wait
+    const int M = rows.live();
+    const bool live = m0 < M;
+
+    if (warp == 0) {
+        if (lane == 0 && live) {  // ===== TMA producer: everything at once, one barrier per K-block =====
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_expect_tx(full_bar(kb), A_BYTES + w_kb_bytes);
+                tma_load_2d(base + kb * A_BYTES, &tmA, kb * BK, m0, full_bar(kb));
+                const uint32_t wdst = w_base + kb * w_kb_bytes;
+                int r0 = 0;
+                for (; r0 + 128 <= V_pad; r0 += 128) tma_load_2d(wdst + r0 * 128, &tmW, kb * BK, r0, full_bar(kb));
+                if (r0 < V_pad) tma_load_2d(wdst + r0 * 128, &tmWtail, kb * BK, r0, full_bar(kb));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && live) {  // ===== MMA issuer =====
+            const uint32_t idesc_main = umma_idesc_bf16(BM, n_main);
+            const uint32_t idesc_tail = umma_idesc_bf16(BM, n_tail > 0 ? n_tail : 16);
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(full_bar(kb), 0);
+                tcgen05_fence_after();
+                const uint32_t a_src = base + kb * A_BYTES, b_src = w_base + kb * w_kb_bytes;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(a_src + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, adesc, umma_desc_sw128(b_src + k * UMMA_K * 2), idesc_main, (kb | k) != 0 ? 1u : 0u);
+                    if (n_tail > 0)
+                        umma_bf16(tmem_base + 256u, adesc, umma_desc_sw128(b_src + 256 * 128 + k * UMMA_K * 2), idesc_tail, (kb | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else if (live) {  // ===== statistics: thread = (row, column half) =====
+        const int q = warp & 3, hh = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int grow = m0 + row;
+        const int n32 = V_pad / 32, c_half = (n32 + 1) / 2;
+        const int c_begin = hh == 0 ? 0 : c_half, c_end = hh == 0 ? c_half : n32;
+        const int tok = grow < M ? row_tok[grow] : -1;
+        float tv[KT];
+        int ti[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
+        float mx = -INFINITY, tokval = 0.f, found = 0.f;
+        mbar_wait(tfull_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_row + (uint32_t)(ch * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                const float v = __uint_as_float(r[j]) + bias_sm[col];
+                if (col < V) {
+                    mx = fmaxf(mx, v);
+                    if (col == tok) { tokval = v; found = 1.f; }
+                    if (v > tv[KT - 1]) {          // enters the list: sift down from the top (equal values stay behind earlier ones)
+                        float cv = v;
+                        int ci = col;
+#pragma unroll
+                        for (int i = 0; i < KT; ++i) {
+                            if (cv > tv[i]) {
+                                const float t0 = tv[i]; tv[i] = cv; cv = t0;
+                                const int t1 = ti[i]; ti[i] = ci; ci = t1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KT; ++i) { xv[(hh * KT + i) * BM + row] = tv[i]; xi[(hh * KT + i) * BM + row] = ti[i]; }
+        xinfo[hh * BM + row] = make_float4(mx, tokval, found, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 i0 = xinfo[row], i1 = xinfo[BM + row];
+        const float gmax = fmaxf(i0.x, i1.x);
+        float part = 0.f;
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm_row + (uint32_t)(ch * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                if (col < V) part += expf(__uint_as_float(r[j]) + bias_sm[col] - gmax);
+            }
+        }
+        if (hh == 1) xinfo[BM + row].w = part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (hh == 0 && grow < M) {
+            const float sum = part + xinfo[BM + row].w;
+            // merge of the two sorted lists (equal values: the lower column half first = lower token id)
+            int a = 0, b = 0;
+            float mv[KT];
+            int mi[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const float va = a < KT ? xv[a * BM + row] : -INFINITY;
+                const float vb = b < KT ? xv[(KT + b) * BM + row] : -INFINITY;
+                const int ia = a < KT ? xi[a * BM + row] : -1;
+                const int ib = b < KT ? xi[(KT + b) * BM + row] : -1;
+                const bool take_a = ia >= 0 && (ib < 0 || va >= vb);
+                mv[j] = take_a ? va : vb;
+                mi[j] = take_a ? ia : ib;
+                a += take_a ? 1 : 0;
+                b += take_a ? 0 : 1;
+            }
+            int keep = 1;
+            float cum = 0.f;
+            bool open = true;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                if (j < K) {
+                    topv[(long long)grow * K + j] = mv[j];
+                    topi[(long long)grow * K + j] = mi[j];
+                    // truncated support: entry j is kept while the exclusive cumulative probability of entries 0..j-1 is < 0.9975
+                    if (j >= 1 && open) {
+                        if (mi[j] < 0) {
+                            open = false;
+                        } else {
+                            cum += expf(mv[j - 1] - gmax) / sum;
+                            if (cum < 0.9975f) keep = j + 1; else open = false;
+                        }
+                    }
+                }
+            }
+            lmax[grow] = gmax;
+            lsum[grow] = sum;
+            nkeep[grow] = keep;
+            tokv[grow] = i0.z != 0.f ? i0.y : i1.y;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
 }  // namespace tc
 
 template <typename OutT>
@@ -2251,6 +2449,43 @@ int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat1
     if (int rc = ensure_dyn_smem(classifier_argmax_kernel, smem)) return rc;
     const int tiles = (rows.max_rows + BM - 1) / BM;
     launch_pdl(classifier_argmax_kernel, dim3(tiles), dim3(cls::THREADS), (size_t)smem, s, tmA, tmW, tmWtail, bias, pred, rows, V, V_pad, KB);
+    return 0;
+}
+
+
+// returns 0 on success, -1 when the shape does not fit the fused kernel (caller falls back to the logits GEMM + beam_stats)
+int launch_classifier_stats(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, RowCount rows, int V, int Kdim, int n_best,
+                            const int* row_tok, float* tokv, float* lmax, float* lsum, int* nkeep, float* topv, int* topi, cudaStream_t s) {
+    using namespace tc;
+    if (rows.max_rows <= 0) return 0;
+    const int V_pad = (V + 31) / 32 * 32, KB = Kdim / BK;
+    const int smem = KB * A_BYTES + KB * V_pad * 128 + V_pad * 4 + BM * 8 + 8 * 18 + 64 + 1024;
+    const int KT = n_best <= 8 ? 8 : 16;
+    // n_best > 8 stays on the unfused kernels unless forced (TTB_FUSED_STATS_WIDE=1): a warp runs the sift of the sorted list
+    // whenever ANY of its 32 rows inserts, which at 16 entries is nearly every element -- measured on B200 (retrosynthesis,
+    // bs 8, n_best 10): 267 SMILES/s fused against 291 unfused, while n_best 5 is on par (253 / 252) with one launch less
+    if (n_best > 8) {
+        const char* wide = getenv("TTB_FUSED_STATS_WIDE");
+        if (!(wide && wide[0] == '1')) return -1;
+    }
+    if (Kdim % BK != 0 || KB > 16 || V_pad > 512 || smem > 227 * 1024 || lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) ||
+        (reinterpret_cast<uintptr_t>(W) & 15) || n_best > 16 || n_best > V || 4096 + 4 * KT * BM * 4 > KB * A_BYTES)
+        return -1;
+    CUtensorMap tmA, tmW, tmWtail;
+    if (int rc = get_tensor_map(A, rows.max_rows, Kdim, lda, BM, &tmA)) return rc;
+    const int tail_rows = V_pad % 128 ? V_pad % 128 : 128;
+    if (int rc = get_tensor_map(W, V, Kdim, Kdim, V_pad >= 128 ? 128 : tail_rows, &tmW)) return rc;
+    if (int rc = get_tensor_map(W, V, Kdim, Kdim, tail_rows, &tmWtail)) return rc;
+    const int tiles = (rows.max_rows + BM - 1) / BM;
+    if (KT == 8) {
+        if (int rc = ensure_dyn_smem(classifier_stats_kernel<8>, smem)) return rc;
+        launch_pdl(classifier_stats_kernel<8>, dim3(tiles), dim3(cls::THREADS), (size_t)smem, s, tmA, tmW, tmWtail, bias, rows, V, V_pad, KB, n_best, row_tok,
+                   tokv, lmax, lsum, nkeep, topv, topi);
+    } else {
+        if (int rc = ensure_dyn_smem(classifier_stats_kernel<16>, smem)) return rc;
+        launch_pdl(classifier_stats_kernel<16>, dim3(tiles), dim3(cls::THREADS), (size_t)smem, s, tmA, tmW, tmWtail, bias, rows, V, V_pad, KB, n_best, row_tok,
+                   tokv, lmax, lsum, nkeep, topv, topi);
+    }
     return 0;
 }
 

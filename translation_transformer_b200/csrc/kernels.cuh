@@ -56,6 +56,13 @@ int launch_gemm_resid_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W
 int launch_classifier_argmax(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int* pred, RowCount rows,
                              int V, int K, cudaStream_t s);
 
+// Vocabulary projection fused with the statistics of the speculative beam search (bf16 path, n_best <= 16): per row the soft-max
+// maximum / sum, the n_best largest logits (descending, ties: lower id) and their ids, the nucleus-truncated support size
+// and the logit of token row_tok[row] -- everything beam_choose / beam_expand read; the logits never leave tensor memory.
+// Returns -1 when the shape does not fit (caller: logits GEMM + launch_beam_stats).
+int launch_classifier_stats(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, RowCount rows, int V, int Kdim, int n_best,
+                            const int* row_tok, float* tokv, float* lmax, float* lsum, int* nkeep, float* topv, int* topi, cudaStream_t s);
+
 // Fused feed-forward sub-layer for embedding_dim 256 (bf16 path):
 //   x <- LN2?(LN1(x + relu(xh W1^T + b1) W2^T + b2)), x fp32 and its bf16 copy xh both updated in place.
 // Chained form (att, Wo given; only with the CTA-pair kernel, see ffn_pair_available): the same launch first computes the
@@ -170,6 +177,9 @@ struct BeamState {
     int* host_ctrl;   // pinned host mirror of ctrl (device-accessible): BC_COUNT words + a sequence word written last
     int* rows_tok; int* row_cand; int* row_query; int* row_slot0;      // live decoder rows
     float* topv; int* topi; int* nkeep; float* lmax; float* lsum;      // per (row, position) statistics
+    // KV-cached pass: token whose logit the accepted-path sums need at (row, position) = the row's next draft token (-1
+    // behind the last one), written by the embedding kernel; its logit, written by the statistics kernel
+    int* row_tok; float* tokv;
     int* trace_nacc; int* trace_pick;     // optional [iter][B*K][N] / [iter][B*K]
     // KV-cached decoder pass: live candidates as attention groups, cache bookkeeping of the new candidates
     int* live_cand; int* live_query;      // [live candidates] candidate index / query index

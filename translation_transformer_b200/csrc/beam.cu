@@ -22,7 +22,10 @@ namespace ttb {
 // (the iteration is replayed as a CUDA graph): width of the token matrix and number of the CURRENT iteration, advanced by
 // the CTA that closes the iteration with the same rule the host applies (engine.cu:beam_api, speculative_decoding.py:452-470)
 constexpr int BCX_ALL_FIN = BC_COUNT, BCX_MIN_PAD = BC_COUNT + 1, BCX_ACC = BC_COUNT + 2, BCX_CNT = BC_COUNT + 3, BCX_TICKET = BC_COUNT + 4,
-              BCX_W = BC_COUNT + 5, BCX_ITER = BC_COUNT + 6;
+              BCX_W = BC_COUNT + 5, BCX_ITER = BC_COUNT + 6,
+              BCX_DONE = BC_COUNT + 7;   // the loop has ended (every hypothesis finished, length budget used up, or an error): set by the CTA that
+                                         // closes an iteration with the reference's own stop rule, so that an iteration the host has
+                                         // enqueued ahead of reading this one's outcome is a no-op on the device
 
 
 // drafts of candidate c (query q): all N source drafts, or in smart mode the library windows keyed by its last token
@@ -60,6 +63,10 @@ void launch_beam_build_lib(const BeamState& st, cudaStream_t s) {
 
 // ---- prepare ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) beam_prepare_kernel(BeamState st, int C, int beam, int dl) {
+    if (st.ctrl[BCX_DONE]) {   // enqueued ahead of the end of the loop: no live rows, every kernel behind this one exits at once
+        if (threadIdx.x == 0) { st.ctrl[BC_NLIVE_ROWS] = 0; st.ctrl[BC_NLIVE_CANDS] = 0; }
+        return;
+    }
     const int W = st.ctrl[BCX_W];
     // one warp per candidate row, coalesced scan: first PAD column, EOS anywhere, a real token behind the first PAD
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -193,6 +200,7 @@ __global__ void beam_cache_update_kernel(BeamState st, int dl, const ActT* __res
                                          int E, const ActT* __restrict__ kc_cur, const ActT* __restrict__ vc_cur, ActT* __restrict__ kc_next,
                                          ActT* __restrict__ vc_next, long long cache_layer_stride, long long cache_cand_stride) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
+    if (st.ctrl[BCX_DONE]) return;   // the loop has ended (this iteration closed it, or it was enqueued behind the end): the caches are not read again
     const int cn = blockIdx.x, l = blockIdx.y;
     const int parent = st.n_parent[cn];
     if (parent < 0) return;                         // child of a finished hypothesis: never decoded again
@@ -362,6 +370,7 @@ void launch_beam_stats(const BeamState& st, const float* logits, int max_rows, i
 // accepted length of a draft is the length of its leading run of hits.
 __global__ void __launch_bounds__(256) beam_choose_kernel(BeamState st, int C, int beam, int dl, int par) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
+    if (st.ctrl[BCX_DONE]) return;   // no-op iteration behind the end of the loop
     const int iter = st.ctrl[BCX_ITER];
     const int c = blockIdx.x;
     __shared__ int s_nacc[64];
@@ -423,6 +432,7 @@ __device__ __forceinline__ float ref_logprob(float logit, float mx, float sum) {
 
 __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam, int dl, const float* __restrict__ logits) {
     pdl_wait();   // launched with the programmatic attribute: scheduled while the predecessor drains, starts when it is complete
+    if (st.ctrl[BCX_DONE]) return;   // no-op iteration behind the end of the loop (the word of the last real iteration stays posted)
     extern __shared__ float s_score[];                 // [beam][(dl+1)][K] leaf scores, -inf when absent
     __shared__ float s_red_v[256];
     __shared__ int s_red_i[256];
@@ -580,6 +590,8 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                 const int grow = min(budget, dl) + 1 - empty;
                 st.ctrl[BCX_W] = W + max(grow, 0);
                 st.ctrl[BCX_ITER] = seq;
+                // the reference's stop rule (:570-598 break on all finished; :452 while budget >= 1 and filled <= max_len)
+                if (atomicAdd(&st.ctrl[BC_ERROR], 0) != 0 || st.ctrl[BC_ALL_FINISHED] != 0 || budget < 1 || filled > st.max_len) st.ctrl[BCX_DONE] = 1;
             }
             if (st.host_ctrl) {
                 // what the host needs per iteration, packed into ONE 64-bit word of its own (pinned, mapped) memory:
@@ -589,7 +601,8 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                                                 ((unsigned long long)(atomicAdd(&st.ctrl[BC_ERROR], 0) & 0xff) << 24) |
                                                 ((unsigned long long)(st.ctrl[BC_ALL_FINISHED] & 0xff) << 16) |
                                                 (unsigned long long)(st.ctrl[BC_EMPTY_COLS] & 0xffff);
-                *reinterpret_cast<volatile unsigned long long*>(st.host_ctrl) = word;
+                // ring of four words: the host may read iteration i's word after iteration i + 1 (enqueued ahead) has posted its own
+                reinterpret_cast<volatile unsigned long long*>(st.host_ctrl)[seq & 3] = word;
             }
         }
     }
@@ -611,7 +624,7 @@ __global__ void beam_init_kernel(BeamState st) {
         if (threadIdx.x < BC_COUNT) st.ctrl[threadIdx.x] = 0;
         if (threadIdx.x == 0) {
             st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
-            st.ctrl[BCX_W] = st.w0; st.ctrl[BCX_ITER] = 0;
+            st.ctrl[BCX_W] = st.w0; st.ctrl[BCX_ITER] = 0; st.ctrl[BCX_DONE] = 0;
         }
     }
 }

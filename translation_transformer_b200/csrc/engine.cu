@@ -908,7 +908,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     st.trace_nacc = trace_nacc; st.trace_pick = trace_pick;
     {
         void* dp = nullptr;
-        e->h_ctrl[16] = e->h_ctrl[17] = 0;
+        for (int i = 16; i < 24; ++i) e->h_ctrl[i] = 0;   // ring of four 64-bit words the expand kernel posts into
         st.host_ctrl = cudaHostGetDevicePointer(&dp, e->h_ctrl + 16, 0) == cudaSuccess ? static_cast<int*>(dp) : nullptr;
         (void)cudaGetLastError();
     }
@@ -956,15 +956,24 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     }
     int* hc = e->h_ctrl;
     hc[BC_ERROR] = 0;
-    while (budget >= 1 && filled <= max_len) {
-        dl = std::min(budget, dl);
-        const int grow = dl + 1 - empty_cols;
-        if (grow > 0) W += grow;
-        TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
-        // One iteration = a fixed kernel sequence whose arguments depend on (C, beam, dl) and on the ping-pong parity of the
-        // hypothesis / cache buffers only: the width of the token matrix and the iteration number live in device memory
-        // (beam.cu: BCX_W, BCX_ITER), so the steady state (C = B K, full draft length) is replayed as a CUDA graph.
-        auto enqueue_iteration = [&]() -> int {
+    // the two hypothesis / score / cache buffer sets: iteration i (0-based) reads set i & 1 and writes the other one
+    int* const cand_set[2] = {st.cand_cur, st.cand_next};
+    float* const logp_set[2] = {st.logp_cur, st.logp_next};
+    ActT* const kc_set[2] = {kc_cur, kc_next};
+    ActT* const vc_set[2] = {vc_cur, vc_next};
+
+    // One iteration = a fixed kernel sequence whose arguments depend on (C, beam, dl) and on the ping-pong parity of the
+    // hypothesis / cache buffers only: the width of the token matrix and the iteration number live in device memory
+    // (beam.cu: BCX_W, BCX_ITER), so the steady state (C = B K, full draft length) can be replayed as a CUDA graph and
+    // -- because the device also applies the stop rule itself (BCX_DONE) -- be enqueued AHEAD of the host reading the
+    // outcome of the iteration before it.
+    auto enqueue_iteration = [&](int it, int C, int beam, int dl) -> int {
+        const int parity = it & 1;
+        st.cand_cur = cand_set[parity]; st.cand_next = cand_set[parity ^ 1];
+        st.logp_cur = logp_set[parity]; st.logp_next = logp_set[parity ^ 1];
+        kc_cur = kc_set[parity]; kc_next = kc_set[parity ^ 1];
+        vc_cur = vc_set[parity]; vc_next = vc_set[parity ^ 1];
+        auto body = [&]() -> int {
         const int R = C * N;
         bool fused_stats = false;
         { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, dl, s); }
@@ -999,28 +1008,28 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             }
             if (!fused_stats && linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits, V, rows, false, s)) return 1;
         } else {
-            { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, W, dl, s); }
-            RowCount rows(R * W, n_live, W);
-            { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
+            const int Wit = W;   // full-prefix recomputation (A/B path): never enqueued ahead, the host's width is exact
+            { Scope sc(e, KC_MISC, s); launch_beam_fill_rows(st, C, beam, Wit, dl, s); }
+            RowCount rows(R * Wit, n_live, Wit);
+            { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, Wit, e->tgt_emb, e->pe, E, x, xh, s); }
             auto self_attn = [&](int, ActT* qkv, ActT* att) {
-                attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, R, n_live, W, W, W, nullptr,
-                     st.rows_tok, W, e->d.tgt_pad_token_idx, true, H, HD, s);
+                attn(qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, R, n_live, Wit, Wit, Wit, nullptr,
+                     st.rows_tok, Wit, e->d.tgt_pad_token_idx, true, H, HD, s);
             };
             auto cross_attn = [&](int l, ActT* q2, ActT* att) {
                 const ActT* kv = crosskv + (long long)l * TS * 2 * E;
-                attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, W, Ls, Ls, st.row_query,
+                attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, Wit, Ls, Ls, st.row_query,
                      src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
             };
             if (decoder_stack<ActT>(e, rows, 1, 0, self_attn, cross_attn, s)) return 1;
-            { Scope sc(e, KC_MISC, s); launch_beam_gather<ActT>(st, x, xh, R, W, dl, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
+            { Scope sc(e, KC_MISC, s); launch_beam_gather<ActT>(st, x, xh, R, Wit, dl, E, Prec<ActT>::lowp ? nullptr : xg, xgh, s); }
             RowCount rp_rows(R * (dl + 1), n_live, dl + 1);
             if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(xg, xgh), E, e->classifier, logits, V, rp_rows, false, s)) return 1;
         }
         if (!fused_stats) { Scope sc(e, KC_ARGMAX, s); launch_beam_stats(st, logits, R, dl, s); }
         { Scope sc(e, KC_ACCEPT, s); launch_beam_choose(st, C, beam, dl, s); }
         // the expand kernel also closes the iteration: its last CTA writes the control words and, last, the iteration's
-        // sequence number into pinned host memory; the host reads them while the caches are still being re-parented and
-        // enqueues the next iteration behind that
+        // sequence number into pinned host memory; the host reads them while the caches are still being re-parented
         { Scope sc(e, KC_ACCEPT, s); launch_beam_expand(st, beam, dl, logits, s); }
         if (cached) {
             Scope sc(e, KC_CACHE_APPEND, s);
@@ -1028,14 +1037,13 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                                            cache_l_stride, cache_c_stride, s);
         }
         return 0;
-        };   // enqueue_iteration
-        const int parity = iters & 1;     // the ping-pong buffers have been swapped `iters` times
+        };   // body
         if (use_graph && C == B * K && beam == K && dl == dl_steady) {
             if (!e->beam_graph[parity]) {
                 const long long l0 = e->launches;
                 cudaGraph_t graph = nullptr;
                 TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-                const int rc = enqueue_iteration();
+                const int rc = body();
                 const cudaError_t ce = cudaStreamEndCapture(s, &graph);
                 if (rc || ce != cudaSuccess) {
                     if (graph) cudaGraphDestroy(graph);
@@ -1049,53 +1057,87 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             }
             TTB_CUDA_OK(cudaGraphLaunch(e->beam_graph[parity], s));
             e->launches += e->beam_graph_launches;
-        } else if (enqueue_iteration()) {
-            return 1;
+            return 0;
         }
-        if (cached) {
-            std::swap(kc_cur, kc_next);
-            std::swap(vc_cur, vc_next);
-        }
-        {   // spin on the packed word the expand kernel posts (sequence | error | all finished | empty columns)
-            volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(hc + 16);
-            unsigned long long w = 0;
-            bool seen = false;
-            for (long spin = 0; !seen; ++spin) {
-                w = *word;
-                seen = (unsigned)(w >> 32) == (unsigned)(iters + 1);
-                // the word normally arrives within a few microseconds of the last launch call; past that (long iterations,
-                // several engines per GPU and ranks per box sharing the cores) the thread gives its core away between polls
-                if (!seen) { if (spin < 256) cpu_relax(); else sched_yield(); }
-                if (!seen && (spin & 0x3FFF) == 0x3FFF) {
-                    const cudaError_t q = cudaStreamQuery(s);
-                    if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy
-                        w = *word;
-                        if ((unsigned)(w >> 32) != (unsigned)(iters + 1)) {
-                            TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
-                            w = ((unsigned long long)(unsigned)(iters + 1) << 32) | ((unsigned long long)(hc[BC_ERROR] & 0xff) << 24) |
-                                ((unsigned long long)(hc[BC_ALL_FINISHED] & 0xff) << 16) | (unsigned long long)(hc[BC_EMPTY_COLS] & 0xffff);
-                        }
-                        seen = true;
-                    } else if (q != cudaErrorNotReady) {
-                        TTB_CUDA_OK(q);
+        return body();
+    };
+    // wait for the packed word the expand kernel posts for iteration `seq` (sequence | error | all finished | empty columns)
+    auto wait_word = [&](int seq) -> int {
+        volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(hc + 16) + (seq & 3);
+        unsigned long long w = 0;
+        bool seen = false;
+        for (long spin = 0; !seen; ++spin) {
+            w = *word;
+            seen = (unsigned)(w >> 32) == (unsigned)seq;
+            // the word normally arrives within a few microseconds of the last launch call; past that (long iterations,
+            // several engines per GPU and ranks per box sharing the cores) the thread gives its core away between polls
+            if (!seen) { if (spin < 256) cpu_relax(); else sched_yield(); }
+            if (!seen && (spin & 0x3FFF) == 0x3FFF) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy
+                    w = *word;
+                    if ((unsigned)(w >> 32) != (unsigned)seq) {
+                        TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
+                        w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)(hc[BC_ERROR] & 0xff) << 24) |
+                            ((unsigned long long)(hc[BC_ALL_FINISHED] & 0xff) << 16) | (unsigned long long)(hc[BC_EMPTY_COLS] & 0xffff);
                     }
+                    seen = true;
+                } else if (q != cudaErrorNotReady) {
+                    TTB_CUDA_OK(q);
                 }
             }
-            hc[BC_ERROR] = (int)((w >> 24) & 0xff);
-            hc[BC_ALL_FINISHED] = (int)((w >> 16) & 0xff);
-            hc[BC_EMPTY_COLS] = (int)(w & 0xffff);
         }
+        hc[BC_ERROR] = (int)((w >> 24) & 0xff);
+        hc[BC_ALL_FINISHED] = (int)((w >> 16) & 0xff);
+        hc[BC_EMPTY_COLS] = (int)(w & 0xffff);
+        return 0;
+    };
+    // Host loop.  `iters` iterations have been read back (their outcome is known exactly: W, filled, budget, dl below are
+    // the reference's values before iteration `iters`); `enq` iterations have been enqueued.  In the steady state the next
+    // iteration is enqueued BEFORE the word of the current one is awaited whenever its arguments cannot depend on that
+    // word: C = B K and beam = K from the second iteration on, and the draft length stays dl as long as the length budget
+    // cannot drop below it (one iteration fills at most dl + 1 more columns).  If the current iteration ends the loop the
+    // device has raised BCX_DONE and the iteration enqueued ahead does nothing.
+    static const bool no_ahead = [] { const char* v = getenv("TTB_BEAM_NO_AHEAD"); return v && v[0] == '1'; }();
+    const bool ahead_ok = cached && st.host_ctrl && !no_ahead && !trace_nacc && !trace_pick;
+    int enq = 0, dl_enq = dl;
+    bool ended = false;
+    while (!ended) {
+        if (enq == iters) {                              // nothing in flight: the coming iteration from exact knowledge
+            if (!(budget >= 1 && filled <= max_len)) break;
+            dl = std::min(budget, dl);
+            const int grow = dl + 1 - empty_cols;
+            if (grow > 0) W += grow;
+            TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
+            if (enqueue_iteration(enq, C, beam, dl)) return 1;
+            dl_enq = dl;
+            ++enq;
+        }
+        if (ahead_ok && enq == iters + 1 && dl_enq == dl_steady && max_len - (filled + 2 * (dl_enq + 1)) - 1 >= dl_enq &&
+            W + 2 * (dl_enq + 1) <= ldw) {
+            // `filled` is the exact count before the iteration in flight: after it and one more at most 2 (dl + 1) columns are added
+            if (enqueue_iteration(enq, B * K, K, dl_enq)) return 1;
+            ++enq;
+        }
+        if (wait_word(iters + 1)) return 1;
         ++iters;
         if (hc[BC_ERROR]) break;
-        std::swap(st.cand_cur, st.cand_next);
-        std::swap(st.logp_cur, st.logp_next);
         C = B * K;
         beam = K;
         if (hc[BC_ALL_FINISHED]) break;
         empty_cols = hc[BC_EMPTY_COLS];
         filled = W - empty_cols;
         budget = max_len - filled - 1;
+        if (enq > iters) {
+            // the iteration enqueued ahead runs with the values the reference would use: same dl (checked above), and
+            // its token matrix is this one's plus the columns the device adds with the same rule
+            if (!(budget >= 1 && filled <= max_len)) { ended = true; break; }   // the device stopped as well (BCX_DONE)
+            const int grow = dl + 1 - empty_cols;
+            if (grow > 0) W += grow;
+        }
     }
+    // the hypotheses of the last iteration that really ran are in the set it wrote
+    st.cand_cur = cand_set[iters & 1];
     TTB_CUDA_OK(cudaGetLastError());
     const int err = hc[BC_ERROR];
     if (!err) {

@@ -9,8 +9,9 @@ reference's prediction CSV (BASELINE.json configs[4]: 40k-query test set sharded
 
 Mirrors what the reference does for `predict` (main.py -> Seq2SeqDM.predict_dataloader -> predict_step ->
 PredictionWriter, seq2seq_wrappers.py:122-128,168-175; lightning_model.py:236-239; callbacks.py:42-64): fixed-size
-batches in file order, right-padded with PAD.  Under torchrun the batches are sharded contiguously over the ranks
-(one engine per GPU), the predictions are all-gathered over NCCL and rank 0 writes the CSV in file order.  Without a
+batches in file order, right-padded with PAD.  Under torchrun the batches are drawn by all ranks and in-flight engines from
+one shared queue (`--sharding dynamic`, default; `static` = contiguous shards), the predictions are all-gathered over NCCL
+once at the end and rank 0 writes the CSV in file order: byte-identical to the one-GPU sequential run.  Without a
 checkpoint the weights are random-init of the configured architecture (there are no checkpoints offline)."""
 from __future__ import annotations
 
@@ -56,6 +57,11 @@ def parse():
     ap.add_argument("--report-file")
     ap.add_argument("--in-flight", type=int, default=3,
                     help="batches decoded concurrently per GPU (one engine each, pipeline.py); 1 = the reference's sequential loop")
+    ap.add_argument("--weights", default="random", choices=["random", "copy"],
+                    help="without --ckpt: plain random init, or the trained-like copy circuit of weights.copy_task_state_dict "
+                         "(queries finish at their own length: ragged finish times, real token sequences in the CSV)")
+    ap.add_argument("--sharding", default="dynamic", choices=["dynamic", "static"],
+                    help="dynamic: one queue of batch indices shared by all ranks and in-flight engines; static: contiguous shards per rank")
     return ap.parse_args()
 
 
@@ -101,6 +107,57 @@ def load_batches(args):
     return tk, batches
 
 
+def main_dynamic(args, model, tk, batches, n_best, rank, world, dev):
+    """One queue of batch indices shared by all ranks and in-flight engines (distributed.BatchQueue) instead of contiguous
+    static shards: a rank that drew long queries draws fewer batches.  Predictions are collected with ONE indexed all-gather
+    at the end and written in file order, so the CSV is byte-identical to a one-GPU sequential run."""
+    import torch.distributed as dist
+    from translation_transformer_b200.distributed import BatchQueue, gather_indexed_predictions
+    failures = []
+    queue = BatchQueue(len(batches))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    model.on_predict_start()
+    t0 = time.perf_counter()
+    done = model.predict_queue(batches, queue, on_error=lambda i, ex: failures.append(i))
+    fixed = []
+    for i, pred in done:
+        k = batches[i]["src_tokens"].shape[0]
+        if pred is None:               # the reference's own failure modes (INTEGRATION.md §3): keep the row count
+            pred = torch.zeros(k, n_best, args.max_len, dtype=torch.int64, device=dev)
+        if pred.shape[2] < args.max_len:   # beam searches return the width they reached
+            pred = torch.nn.functional.pad(pred, (0, args.max_len - pred.shape[2]))
+        pred = pred[:, :, :args.max_len]
+        if k < args.batch_size:        # the last batch of the file: same shape for the gather
+            pred = torch.nn.functional.pad(pred, (0, 0, 0, 0, 0, args.batch_size - k))
+        fixed.append((i, pred.contiguous()))
+    everything = gather_indexed_predictions([i for i, _ in fixed], [p for _, p in fixed], len(batches), device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    mine_n = torch.tensor([len(done)], dtype=torch.int64, device=dev)
+    per_rank = [torch.zeros_like(mine_n) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine_n)
+    else:
+        per_rank = [mine_n]
+    if rank == 0:
+        model.on_predict_end()
+        n = sum(b["src_tokens"].shape[0] for b in batches)
+        if args.output:
+            w = PredictionWriter(args.output)
+            for i, b in enumerate(batches):
+                w.write(tk, everything[i][:b["src_tokens"].shape[0]].cpu(), b)
+        print(json.dumps({"queries": n, "n_gpus": world, "seconds": round(dt, 3), "smiles_per_s": round(n / dt, 1), "sharding": "dynamic queue",
+                          "batches_per_rank": [int(x.item()) for x in per_rank], "generation": args.generation, "batch_size": args.batch_size,
+                          "precision": args.precision, "batches_in_flight": max(1, args.in_flight), "weights": args.weights,
+                          "model_calls_rank0": model._counter("model_calls_num"), "reference_failures_rank0": len(failures), "output": args.output}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,6 +178,9 @@ def main():
         sd = torch.load(args.ckpt, map_location="cpu", weights_only=True)
         sd = sd.get("state_dict", sd)
         sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in sd.items() if "positional_encoding" not in k}
+    elif args.weights == "copy":
+        from translation_transformer_b200.weights import ModelConfig, copy_task_state_dict
+        sd = copy_task_state_dict(ModelConfig(src_vocab_size=tk.n_tokens, tgt_vocab_size=tk.n_tokens, **PRODUCT_PREDICTION), args.seed)
     model = VanillaEncoderDecoderTransformerLightning(
         src_tokenizer=tk, tgt_tokenizer=tk, generation=args.generation, beam_size=args.beam_size,
         max_len=args.max_len, n_drafts=args.n_drafts, draft_len=args.draft_len, smart_drafts_mode=args.smart_drafts_mode,
@@ -129,6 +189,8 @@ def main():
 
     mine = shard_batches(len(batches), rank, world)
     n_best = 1 if args.generation in ("greedy", "greedy_speculative") else args.beam_size
+    if args.sharding == "dynamic":
+        return main_dynamic(args, model, tk, batches, n_best, rank, world, dev)
     failures = 0
     if world > 1:
         dist.barrier()

@@ -106,6 +106,27 @@ class VanillaEncoderDecoderTransformerLightning(_Base):
         dev = self.model.device
         return self._in_flight.map((b["src_tokens"] for b in batches), pre=lambda s: s.to(dev, non_blocking=True), on_error=on_error)
 
+    def predict_queue(self, batches, queue=None, on_error=None):
+        """Dynamic sharding of a prediction job over ranks and in-flight engines: every worker of every rank draws the next
+        batch index from `queue` (distributed.BatchQueue over all ranks; a local one when None) until it is empty.
+        Returns this rank's `(batch index, prediction)` pairs; `distributed.gather_indexed_predictions` puts the job back
+        in order.  Same predictions as `predict_step` on each batch: batches are independent."""
+        from .distributed import BatchQueue
+        from .pipeline import InFlightDecoder
+        if self._in_flight is None:
+            self._in_flight = InFlightDecoder(self.generators, device=self.device_index)
+        batches = list(batches)
+        if batches and self.batch_size is None:
+            self.batch_size = batches[0]["src_tokens"].shape[0]
+        queue = queue if queue is not None else BatchQueue(len(batches), local=True)
+        dev = self.model.device
+
+        def next_item():
+            i = queue.next()
+            return None if i is None else (i, batches[i]["src_tokens"])
+
+        return self._in_flight.drain(next_item, pre=lambda s: s.to(dev, non_blocking=True), on_error=on_error)
+
     def _counter(self, name: str):
         return sum(getattr(g, name) for g in self.generators)
 

@@ -840,6 +840,10 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const int n_lib = Ls - 5;
     if (smart) TTB_CHECK(n_lib > 0, "The number of drafts must be greater than 0");
     const long long TS = (long long)B * Ls;
+    // buffers that depend on the source length are sized for a rounded-up capacity: batches of different length must not
+    // reallocate (cudaFree synchronises the whole device, i.e. every other engine decoding on this GPU as well)
+    const int Ls_cap = std::max(256, (Ls + 63) / 64 * 64);
+    const long long TS_cap = (long long)B * Ls_cap;
     const int Cmax = B * K, Rmax = Cmax * N;
     const int ldw = max_len + D0 + 4;
     // KV-cached pass (default): only the dl+1 scored positions of every (candidate, draft) row go through the decoder,
@@ -851,11 +855,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const long long Tc = (long long)Rmax * (D0 + 1);
     const long long Tmax = cached ? Tc : (long long)Rmax * ldw;
 
-    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
-    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
-    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
-    if (e->drafts.ensure(smart ? (size_t)B * n_lib * D_lib * sizeof(int) : (size_t)B * N * D0 * sizeof(int))) return 1;
-    if (ensure_work<ActT>(e, std::max(Tmax, TS), cached ? n_dec : 1)) return 1;
+    if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (e->drafts.ensure(smart ? (size_t)B * std::max(n_lib, Ls_cap) * D_lib * sizeof(int) : (size_t)B * N * D0 * sizeof(int))) return 1;
+    if (ensure_work<ActT>(e, std::max(Tmax, TS_cap), cached ? n_dec : 1)) return 1;
     const long long cache_c_stride = (long long)ldw * E, cache_l_stride = (long long)Cmax * ldw * E;
     if (cached) {
         const size_t cbytes = (size_t)n_dec * cache_l_stride * sizeof(ActT);
@@ -886,7 +890,8 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     ActT* memh = Prec<ActT>::lowp ? e->memh.as<ActT>() : nullptr;
     if (encode_impl<ActT>(e, src32, src32, B, Ls, mem, memh, s)) return 1;
     ActT* crosskv = e->crosskv.as<ActT>();
-    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s)) return 1;
+    const long long ckv_l_stride = TS_cap * 2 * E;
+    if (cross_kv_impl<ActT>(e, mem, memh, (int)TS, crosskv, s, ckv_l_stride)) return 1;
     if (smart) { Scope sc(e, KC_MISC, s); launch_make_drafts(src32, Ls, B, Ls, D_lib, n_lib, eos, pad, c_token, e->drafts.as<int>(), s); }
     else { Scope sc(e, KC_MISC, s); launch_make_drafts(src32 + 1, Ls, B, Ls - 1, D0, N, eos, pad, c_token, e->drafts.as<int>(), s); }
 
@@ -988,7 +993,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                           st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, n_per_group, dl, H, HD, ldw, s, st.desc_self);
             };
             auto cross_attn = [&](int l, ActT* q2, ActT* att) {
-                const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+                const ActT* kv = crosskv + (long long)l * ckv_l_stride;
                 attn(q2, E, kv, kv + E, 2 * E, att, E, G, n_live_cands, n_per_group * (dl + 1), Ls, Ls, st.live_query,
                      src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, nullptr, nullptr, st.desc_cross);
             };
@@ -1017,7 +1022,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                      st.rows_tok, Wit, e->d.tgt_pad_token_idx, true, H, HD, s);
             };
             auto cross_attn = [&](int l, ActT* q2, ActT* att) {
-                const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+                const ActT* kv = crosskv + (long long)l * ckv_l_stride;
                 attn(q2, E, kv, kv + E, 2 * E, att, E, R, n_live, Wit, Ls, Ls, st.row_query,
                      src32, Ls, e->d.src_pad_token_idx, false, H, HD, s);
             };
@@ -1062,6 +1067,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         return body();
     };
     // wait for the packed word the expand kernel posts for iteration `seq` (sequence | error | all finished | empty columns)
+    static const bool pure_spin = [] { const char* v = getenv("TTB_BEAM_SPIN"); return v && v[0] == '1'; }();
     auto wait_word = [&](int seq) -> int {
         volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(hc + 16) + (seq & 3);
         unsigned long long w = 0;
@@ -1071,7 +1077,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             seen = (unsigned)(w >> 32) == (unsigned)seq;
             // the word normally arrives within a few microseconds of the last launch call; past that (long iterations,
             // several engines per GPU and ranks per box sharing the cores) the thread gives its core away between polls
-            if (!seen) { if (spin < 256) cpu_relax(); else sched_yield(); }
+            if (!seen) { if (spin < 256 || pure_spin) cpu_relax(); else sched_yield(); }
             if (!seen && (spin & 0x3FFF) == 0x3FFF) {
                 const cudaError_t q = cudaStreamQuery(s);
                 if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy
@@ -1187,13 +1193,14 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     TTB_CUDA_OK(cudaStreamWaitEvent(s, e->join_ev, 0));
     const long long launches0 = e->launches;
     const long long TS = (long long)B * Ls;
+    const long long TS_cap = (long long)B * std::max(256, (Ls + 63) / 64 * 64);   // no reallocation from one batch length to the next
     const int Cmax = B * K, ldw = max_len;
     const long long Tmax = (long long)Cmax * max_len;
 
-    if (e->src32.ensure(TS * sizeof(int)) || e->memory.ensure(TS * E * sizeof(float))) return 1;
-    if (Prec<ActT>::lowp && e->memh.ensure(TS * E * sizeof(ActT))) return 1;
-    if (e->crosskv.ensure(TS * 2 * E * sizeof(ActT) * n_dec)) return 1;
-    if (ensure_work<ActT>(e, std::max(Tmax, TS), 1)) return 1;
+    if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float))) return 1;
+    if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
+    if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
+    if (ensure_work<ActT>(e, std::max(Tmax, TS_cap), 1)) return 1;
     DevBuf& bb = e->beam;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };

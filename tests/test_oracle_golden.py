@@ -235,3 +235,57 @@ def test_standard_decoding_oracle_matches_reference_golden(case):
     shas = [sha_tokens(t.numpy()) for t in o.decoder_inputs]
     # the reference's first beam-search step goes through model.forward, which the recording hook does not see
     assert (shas if case["kind"] == "greedy" else shas[1:]) == case["decoder_input_sha1"]
+
+
+def test_oracle_reproduces_the_reference_at_the_benchmarked_greedy_config():
+    """tests/golden/bench_configs.*: BASELINE.json configs[1] at full size (256/2048/4+4/8, vocab 288, draft_len 10, n_drafts 23,
+    trained-like weights).  Greedy queries are independent of their batch mates (unless the width limit is reached, which it is
+    not here), so the oracle decodes the first three queries and must reproduce the reference's rows, accepted lengths and picks
+    of those queries out of the 32-query run."""
+    import json
+    from pathlib import Path
+    import numpy as np
+    from oracle.greedy_speculative import GreedySpeculativeOracle
+    from oracle.transformer import OracleTransformer
+    from translation_transformer_b200.synthetic import synthetic_sources
+    from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, copy_task_state_dict, state_dict_checksum
+    golden = Path(__file__).resolve().parent / "golden"
+    case = [c for c in json.load(open(golden / "bench_configs.json")) if c["id"] == "cfg1_copy"][0]
+    z = np.load(golden / "bench_configs.npz")
+    cfg = ModelConfig(src_vocab_size=case["vocab"], tgt_vocab_size=case["vocab"], **PRODUCT_PREDICTION)
+    sd = copy_task_state_dict(cfg, case["seed"])
+    assert state_dict_checksum(sd) == case["checksum"]
+    src = synthetic_sources(32, case["vocab"], seed=case["src_seed"])
+    assert np.array_equal(src.numpy(), z["cfg1_copy_src"].astype(np.int64))
+    nq = 3
+    o = GreedySpeculativeOracle(OracleTransformer(sd, cfg.num_heads), case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2, 7, keep_trace=True)
+    out = o.generate(src[:nq].clone()).numpy()
+    ref = z["cfg1_copy_out"].astype(np.int64)
+    assert np.array_equal(out[:, 0], ref[:nq, 0])
+    # per-iteration accepted length / pick of the three queries inside the reference's 32-query trace
+    ref_nacc = z["cfg1_copy_nacc"].astype(np.int64).reshape(-1, case["n_drafts"])
+    ref_pick = z["cfg1_copy_pick"].astype(np.int64)
+    ref_acc = ref_nacc[np.arange(len(ref_pick)), ref_pick]
+    off = 0
+    per_query = {q: [] for q in range(nq)}
+    live = list(range(32))
+    fin_at = {}
+    # reconstruct which query each cell of the reference trace belongs to: live list in order, a query leaves after the iteration
+    # in which its row of the output becomes complete (length of its prediction reached)
+    lens = (ref[:, 0] != 0).sum(-1)
+    prod = {q: 1 for q in range(32)}           # tokens produced so far (BOS counts)
+    for n_rows in case["rows_per_iter"]:
+        assert n_rows == len(live)
+        nxt = []
+        for k, q in enumerate(live):
+            a, pk = int(ref_acc[off + k]), int(ref_pick[off + k])
+            if q < nq:
+                per_query[q].append((a, pk))
+            prod[q] += a + 1
+            if prod[q] < lens[q]:
+                nxt.append(q)
+        off += n_rows
+        live = nxt
+    for q in range(nq):
+        mine = [(t["n_accepted"][t["rows"].index(q)], t["draft_index"][t["rows"].index(q)]) for t in o.trace if q in t["rows"]]
+        assert mine == per_query[q][:len(mine)] and len(mine) == len(per_query[q]), q

@@ -1200,15 +1200,31 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     if (e->src32.ensure(TS_cap * sizeof(int)) || e->memory.ensure(TS_cap * E * sizeof(float))) return 1;
     if (Prec<ActT>::lowp && e->memh.ensure(TS_cap * E * sizeof(ActT))) return 1;
     if (e->crosskv.ensure(TS_cap * 2 * E * sizeof(ActT) * n_dec)) return 1;
-    if (ensure_work<ActT>(e, std::max(Tmax, TS_cap), 1)) return 1;
+    {
+        const char* v = getenv("TTB_SBEAM_NO_CACHE");
+        if (ensure_work<ActT>(e, (v && v[0] == '1') ? std::max(Tmax, TS_cap) : std::max<long long>(Cmax, TS_cap), 1)) return 1;
+    }
     DevBuf& bb = e->beam;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_y0 = take((size_t)Cmax * ldw * 4), o_y1 = take((size_t)Cmax * ldw * 4);
     const size_t o_s0 = take(Cmax * 4), o_s1 = take(Cmax * 4), o_fin = take(Cmax * 4), o_cr = take(Cmax * 4), o_rc = take(Cmax * 4),
                  o_rq = take(Cmax * 4), o_rows = take((size_t)Cmax * ldw * 4), o_tot = take((size_t)Cmax * V * 4), o_ctrl = take(64),
-                 o_xg = take((size_t)Cmax * E * 4), o_xgh = take((size_t)Cmax * E * 2), o_lg = take((size_t)Cmax * V * 4);
+                 o_xg = take((size_t)Cmax * E * 4), o_xgh = take((size_t)Cmax * E * 2), o_lg = take((size_t)Cmax * V * 4),
+                 o_cf = take(Cmax * 4), o_par = take(Cmax * 4), o_ds = take(Cmax * 16), o_dc = take(Cmax * 16);
     if (bb.ensure(off)) return 1;
+    // KV-cached pass (default): one new token per live hypothesis and step, the prefix of a hypothesis is served from its
+    // self-attention cache, which follows the hypotheses through the re-parenting of every step (two ping-pong copies).
+    // TTB_SBEAM_NO_CACHE=1 keeps the reference-like full-prefix recomputation (A/B runs).
+    static const bool sb_no_cache = [] { const char* v = getenv("TTB_SBEAM_NO_CACHE"); return v && v[0] == '1'; }();
+    const bool cached = !sb_no_cache;
+    const long long cache_c_stride = (long long)max_len * E, cache_l_stride = (long long)Cmax * max_len * E;
+    if (cached) {
+        const size_t cbytes = (size_t)n_dec * cache_l_stride * sizeof(ActT);
+        if (e->kcache.ensure(cbytes) || e->vcache.ensure(cbytes) || e->kcache2.ensure(cbytes) || e->vcache2.ensure(cbytes)) return 1;
+        if (e->srclen.ensure((size_t)B * sizeof(int))) return 1;
+        if (ensure_work<ActT>(e, std::max<long long>(Cmax, TS_cap), n_dec)) return 1;
+    }
     char* base = bb.as<char>();
 
     TTB_CUDA_OK(cudaEventRecord(e->t0, s));
@@ -1229,6 +1245,14 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     float* xg = (float*)(base + o_xg);
     ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
     float* logits = (float*)(base + o_lg);
+    ActT *kc_cur = nullptr, *vc_cur = nullptr, *kc_next = nullptr, *vc_next = nullptr;
+    if (cached) {
+        st.c_front = (int*)(base + o_cf); st.parent = (int*)(base + o_par);
+        st.desc_self = (int4*)(base + o_ds); st.desc_cross = (int4*)(base + o_dc);
+        { Scope sc(e, KC_MISC, s); launch_row_lengths(src32, B, Ls, e->d.src_pad_token_idx, e->srclen.as<int>(), s); }
+        st.src_len = e->srclen.as<int>();
+        kc_cur = e->kcache.as<ActT>(); vc_cur = e->vcache.as<ActT>(); kc_next = e->kcache2.as<ActT>(); vc_next = e->vcache2.as<ActT>();
+    }
     { Scope sc(e, KC_MISC, s); launch_sbeam_init(st, s); }
 
     float* x = e->x.as<float>();
@@ -1240,6 +1264,43 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     for (int step = 0; step < max_len - 1; ++step) {
         const int C = B * beam;
         { Scope sc(e, KC_MISC, s); launch_sbeam_prepare(st, C, beam, W, s); }
+        if (cached) {
+            RowCount rows1(C, n_live, 1);
+            { Scope sc(e, KC_EMBED, s); launch_sbeam_embed_last<ActT>(st, C, W, e->tgt_emb, e->pe, E, x, xh, s); }
+            auto self_attn = [&](int l, ActT* qkv, ActT* att) {
+                spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, C, n_live, st.row_cand,
+                          st.c_front, st.y_cur, ldw, e->d.tgt_pad_token_idx, 1, 0, H, HD, max_len, s, st.desc_self);
+            };
+            auto cross_attn = [&](int l, ActT* q2, ActT* att) {
+                const ActT* kv = crosskv + (long long)l * TS * 2 * E;
+                attn(q2, E, kv, kv + E, 2 * E, att, E, C, n_live, 1, Ls, Ls, st.row_query, src32, Ls, e->d.src_pad_token_idx, false, H, HD, s,
+                     nullptr, nullptr, st.desc_cross);
+            };
+            if (decoder_stack<ActT>(e, rows1, n_dec, (long long)Cmax * 3 * E, self_attn, cross_attn, s)) return 1;
+            // every live row is the last position of its hypothesis: logits straight from the residual stream
+            if (linear<float>(e, KC_GEMM_CLASSIFIER, a_view<ActT>(x, xh), E, e->classifier, logits, V, rows1, false, s)) return 1;
+            { Scope sc(e, KC_ARGMAX, s); launch_sbeam_scores(st, C, logits, s); }
+            {
+                Scope sc(e, KC_ACCEPT, s);
+                TTB_CHECK(launch_sbeam_select(st, beam, W, s) == 0, "beam_size * vocabulary too large for the selection kernel");
+            }
+            {
+                Scope sc(e, KC_CACHE_APPEND, s);
+                launch_sbeam_cache_update<ActT>(st, W, e->qkv.as<ActT>(), (long long)Cmax * 3 * E, n_dec, 3 * E, E, kc_cur, vc_cur, kc_next, vc_next,
+                                                cache_l_stride, cache_c_stride, s);
+            }
+            std::swap(kc_cur, kc_next);
+            std::swap(vc_cur, vc_next);
+            TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TTB_CUDA_OK(cudaStreamSynchronize(s));
+            ++calls;
+            std::swap(st.y_cur, st.y_next);
+            std::swap(st.score_cur, st.score_next);
+            beam = K;
+            W += 1;
+            if (step > 0 && hc[1] == B * K) break;   // every hypothesis contains EOS (:169); the first step never breaks (:106-125)
+            continue;
+        }
         RowCount rows(C * W, n_live, W);
         { Scope sc(e, KC_EMBED, s); launch_embed_seq_rows<ActT>(st.rows_tok, rows, W, e->tgt_emb, e->pe, E, x, xh, s); }
         auto self_attn = [&](int, ActT* qkv, ActT* att) {

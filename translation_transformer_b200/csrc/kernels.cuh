@@ -222,6 +222,11 @@ struct StdBeamState {
     int* rows_tok;                        // [live rows][W] decoder input
     float* total;                         // [B*K][V] score + log-softmax
     int* ctrl;                            // [0] live rows, [1] hypotheses with EOS after the selection
+    // KV-cached pass (one new token per live hypothesis and step; nullptr: full-prefix recomputation)
+    int* c_front;                         // [B*K] cached positions of a hypothesis (= W - 1 for all of them)
+    int* parent;                          // [B*K] hypothesis of the previous step a new hypothesis continues
+    int4* desc_self; int4* desc_cross;    // per live row: {hypothesis, front, token at front, -} / {query, -, -, source length}
+    const int* src_len;
 };
 void launch_sbeam_init(const StdBeamState& st, cudaStream_t s);
 void launch_sbeam_prepare(const StdBeamState& st, int C, int beam, int W, cudaStream_t s);
@@ -230,6 +235,15 @@ void launch_sbeam_gather_last(const StdBeamState& st, const float* x, const ActT
                               cudaStream_t s);
 void launch_sbeam_scores(const StdBeamState& st, int C, const float* logits, cudaStream_t s);
 int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s);
+// KV-cached pass: embedding of the last token (position W - 1) of every live hypothesis
+template <typename ActT>
+void launch_sbeam_embed_last(const StdBeamState& st, int max_rows, int W, const float* table, const float* pe, int E, float* x, ActT* xh,
+                             cudaStream_t s);
+// cache of a new hypothesis = cache of its parent [0, W - 1) + K/V of the parent's row of this step (position W - 1)
+template <typename ActT>
+void launch_sbeam_cache_update(const StdBeamState& st, int W, const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld, int E,
+                               const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
+                               long long cache_cand_stride, cudaStream_t s);
 
 // embedding of (rows, L) token matrices whose live row count is on the device
 template <typename ActT>

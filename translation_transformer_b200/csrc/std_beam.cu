@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(1024) sbeam_prepare_kernel(StdBeamState st, in
             st.cand_row[c] = run;
             st.row_cand[run] = c;
             st.row_query[run] = c / beam;
+            if (st.desc_self) {   // KV-cached pass: W - 1 cached positions, the token at W - 1 is this step's input
+                st.desc_self[run] = make_int4(c, W - 1, st.y_cur[(long long)c * st.ldw + W - 1], 0x7fffffff);
+                st.desc_cross[run] = make_int4(c / beam, 0, 0, st.src_len ? st.src_len[c / beam] : 0x7fffffff);
+            }
             ++run;
         }
         st.ctrl[0] = run;
@@ -37,6 +41,10 @@ __global__ void __launch_bounds__(1024) sbeam_prepare_kernel(StdBeamState st, in
         s_run = run;
     }
     __syncthreads();
+    if (st.c_front) {       // KV-cached pass: no token rows to build
+        for (int c = threadIdx.x; c < C; c += blockDim.x) st.c_front[c] = W - 1;
+        return;
+    }
     const int R = s_run;
     for (long long idx = threadIdx.x; idx < (long long)R * W; idx += blockDim.x) {
         const int r = (int)(idx / W), j = (int)(idx % W);
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(256) sbeam_select_kernel(StdBeamState st, int 
             dst[c] = t;
             fin |= (t == st.eos) ? 1 : 0;
         }
-        if (lane == 0) { dst[W] = ch; st.score_next[b * K + j] = s_e[j].v; }
+        if (lane == 0) { dst[W] = ch; st.score_next[b * K + j] = s_e[j].v; if (st.parent) st.parent[b * K + j] = b * beam + parent; }
         fin = __any_sync(0xffffffffu, fin);
         if (lane == 0 && fin) ++n_fin;
     }
@@ -132,6 +140,69 @@ int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s)
     sbeam_select_kernel<<<st.B, 256, smem, s>>>(st, beam, W);
     return 0;
 }
+
+// ---- KV-cached pass ---------------------------------------------------------------------------------------------------
+template <typename ActT>
+__global__ void sbeam_embed_last_kernel(StdBeamState st, int W, const float* __restrict__ table, const float* __restrict__ pe, int E,
+                                        float* __restrict__ x, ActT* __restrict__ xh) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= st.ctrl[0]) return;
+    const int tok = st.y_cur[(long long)st.row_cand[r] * st.ldw + W - 1];
+    const float* e = table + (long long)tok * E;
+    const float* p = pe + (long long)W * E;          // position W - 1 -> row W of the table (row 0 = zeros, embeddings.py:47)
+    for (int c = lane; c < E; c += 32) {
+        const float v = e[c] + p[c];
+        x[(long long)r * E + c] = v;
+        if (xh) xh[(long long)r * E + c] = from_f32<ActT>(v);
+    }
+}
+template <typename ActT>
+void launch_sbeam_embed_last(const StdBeamState& st, int max_rows, int W, const float* table, const float* pe, int E, float* x, ActT* xh,
+                             cudaStream_t s) {
+    if (max_rows <= 0) return;
+    sbeam_embed_last_kernel<ActT><<<(max_rows + 7) / 8, 256, 0, s>>>(st, W, table, pe, E, x, xh);
+}
+template void launch_sbeam_embed_last<float>(const StdBeamState&, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
+template void launch_sbeam_embed_last<__nv_bfloat16>(const StdBeamState&, int, int, const float*, const float*, int, float*, __nv_bfloat16*, cudaStream_t);
+
+template <typename ActT>
+__global__ void sbeam_cache_update_kernel(StdBeamState st, int W, const ActT* __restrict__ qkv_all, long long qkv_layer_stride, int qkv_ld, int E,
+                                          const ActT* __restrict__ kc_cur, const ActT* __restrict__ vc_cur, ActT* __restrict__ kc_next,
+                                          ActT* __restrict__ vc_next, long long cache_layer_stride, long long cache_cand_stride) {
+    const int cn = blockIdx.x, l = blockIdx.y;
+    const int parent = st.parent[cn];
+    const int r = st.cand_row[parent];
+    if (r < 0) return;                               // continuation of a finished hypothesis: never decoded again
+    const long long lo = (long long)l * cache_layer_stride;
+    const ActT* ks = kc_cur + lo + (long long)parent * cache_cand_stride;
+    const ActT* vs = vc_cur + lo + (long long)parent * cache_cand_stride;
+    ActT* kd = kc_next + lo + (long long)cn * cache_cand_stride;
+    ActT* vd = vc_next + lo + (long long)cn * cache_cand_stride;
+    constexpr int VEC = 16 / (int)sizeof(ActT);
+    const long long nvec = (long long)(W - 1) * E / VEC;
+    const uint4* ks4 = reinterpret_cast<const uint4*>(ks);
+    const uint4* vs4 = reinterpret_cast<const uint4*>(vs);
+    uint4* kd4 = reinterpret_cast<uint4*>(kd);
+    uint4* vd4 = reinterpret_cast<uint4*>(vd);
+    for (long long i = threadIdx.x; i < nvec; i += blockDim.x) { kd4[i] = ks4[i]; vd4[i] = vs4[i]; }
+    const ActT* src = qkv_all + (long long)l * qkv_layer_stride + (long long)r * qkv_ld;
+    for (int col = threadIdx.x; col < E; col += blockDim.x) {
+        kd[(long long)(W - 1) * E + col] = src[E + col];
+        vd[(long long)(W - 1) * E + col] = src[2 * E + col];
+    }
+}
+template <typename ActT>
+void launch_sbeam_cache_update(const StdBeamState& st, int W, const ActT* qkv_all, long long qkv_layer_stride, int n_layers, int qkv_ld, int E,
+                               const ActT* kc_cur, const ActT* vc_cur, ActT* kc_next, ActT* vc_next, long long cache_layer_stride,
+                               long long cache_cand_stride, cudaStream_t s) {
+    sbeam_cache_update_kernel<ActT><<<dim3(st.B * st.K, n_layers), 256, 0, s>>>(st, W, qkv_all, qkv_layer_stride, qkv_ld, E, kc_cur, vc_cur, kc_next, vc_next,
+                                                                               cache_layer_stride, cache_cand_stride);
+}
+template void launch_sbeam_cache_update<float>(const StdBeamState&, int, const float*, long long, int, int, int, const float*, const float*, float*, float*,
+                                               long long, long long, cudaStream_t);
+template void launch_sbeam_cache_update<__nv_bfloat16>(const StdBeamState&, int, const __nv_bfloat16*, long long, int, int, int, const __nv_bfloat16*,
+                                                       const __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, long long, long long, cudaStream_t);
 
 __global__ void sbeam_init_kernel(StdBeamState st) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < st.B; b += gridDim.x * blockDim.x) {

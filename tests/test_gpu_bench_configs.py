@@ -230,3 +230,24 @@ def test_fused_classifier_statistics_match_the_unfused_kernels(dev, case, monkey
     assert c_fu == c_un and np.array_equal(n_fu, n_un)   # accepted length of every draft in every iteration
     assert o_un.shape == o_fu.shape and (o_un[:, 0] == o_fu[:, 0]).all()          # best hypothesis of every query
     assert (o_un == o_fu).all(-1).mean() >= 0.95         # the rest up to swaps of hypotheses whose scores differ in the last bits
+
+
+@pytest.mark.parametrize("n_best,smart", [(1, False), (3, False), (8, False), (5, True)])
+def test_fused_classifier_statistics_other_beam_widths(dev, n_best, smart, monkeypatch):
+    """Fused against unfused statistics for list lengths around the register list of the fused kernel (8 entries) and for
+    smart_drafts_mode, on the full architecture with trained-like weights (two queries, ragged lengths)."""
+    from translation_transformer_b200.decoding import TranslationInferenceBeamSearchSpeculative
+    cfg = ModelConfig(src_vocab_size=288, tgt_vocab_size=288, **PRODUCT_PREDICTION)
+    sd = copy_task_state_dict(cfg, 77)
+    src = synthetic_sources(3, 288, seed=4242, mean_len=40.0, std_len=12.0, min_len=12, max_len=80).to(dev)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TTB_NO_FUSED_STATS", flag)
+        eng = _engine(cfg, sd, "bf16")
+        gen = TranslationInferenceBeamSearchSpeculative(eng, 120, n_best, 10, 7, 288, smart, 0, 1, 2, 7)
+        res[flag] = (gen.generate(src).cpu().numpy(), gen.model_calls_num, gen.accepted_tokens_num, gen.gpu_launches)
+        eng.close()
+    (o_un, c_un, a_un, l_un), (o_fu, c_fu, a_fu, l_fu) = res["1"], res["0"]
+    assert l_fu < l_un and c_fu == c_un and a_fu == a_un
+    assert o_un.shape == o_fu.shape and np.array_equal(o_un[:, 0], o_fu[:, 0])
+    assert (o_un == o_fu).all(-1).mean() >= 0.9

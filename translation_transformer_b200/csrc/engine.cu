@@ -161,7 +161,8 @@ struct ttb_engine {
     // decoding loop: private stream + one captured CUDA graph per (shape, buffers) configuration
     cudaStream_t stream = nullptr;
     cudaEvent_t join_ev{};
-    cudaGraphExec_t graph_exec = nullptr;
+    static constexpr int kBuckets = 10;
+    cudaGraphExec_t graph_exec[kBuckets][2] = {};   // greedy iteration graphs per live-query bucket (grids sized for the bucket) x {long, short}
     long long graph_key[12] = {};
     long long graph_launches = 0;
     cudaGraphExec_t beam_graph[2] = {nullptr, nullptr};   // steady-state iteration of the speculative beam search, per ping-pong parity
@@ -676,18 +677,23 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     const long long cache_q_stride = (long long)P * E, cache_l_stride = (long long)B * P * E;
     const long long qkv_l_stride = T * 3 * E;
     const int* n_active = st.ctrl + CTRL_N_ACTIVE;
-    RowCount rows((int)T, n_active, per_q);
+    // Grids of an iteration are sized for `Bq` queries: the whole batch, or -- once the host has seen queries retire -- one of
+    // a few smaller buckets (live-query count only shrinks, so the count the host read last is an upper bound for every
+    // iteration it launches afterwards).  CTAs beyond the live range exit at once either way, but each of them still has to
+    // find an SM with ~200 KB of shared memory free just to do so, which serialises the kernels of the OTHER batches in
+    // flight behind it; with batches that thin out (trained-like weights) most CTAs of a full-size grid are such no-ops.
+    int Bq = B;
 
     auto self_attn = [&](int l, ActT* qkv, ActT* att) {
         if constexpr (Prec<ActT>::lowp) {
             if (tc_attn) {
                 launch_spec_self_attention_tc(qkv, 3 * E, kc + l * cache_l_stride, cache_q_stride, E, vc + l * vt_l_stride, vt_q_stride, VT_PITCH, att, E,
-                                              B, n_active, st.gen, gen_ld, e->d.tgt_pad_token_idx, N, D, H, st.desc, s);
+                                              Bq, n_active, st.gen, gen_ld, e->d.tgt_pad_token_idx, N, D, H, st.desc, s);
                 return;
             }
         }
         spec_attn(qkv, 3 * E, kc + l * cache_l_stride, vc + l * cache_l_stride, cache_q_stride, E,
-                                         att, E, B, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
+                                         att, E, Bq, n_active, st.active, st.front, st.gen, gen_ld, e->d.tgt_pad_token_idx,
                                          N, D, H, HD, P, s, st.desc);
     };
     auto cross_attn = [&](int l, ActT* q2, ActT* att) {
@@ -697,18 +703,21 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
                 // the K/V rows of a query start at row query * Ls of the layer's block (the batch's own source length, read on the
                 // device by the kernel: the row stride of a group is Ls * 2E elements)
                 launch_cross_attention_tc(q2, E, kv, 2 * E, (long long)Ls * 2 * E, e->crossvt.as<ActT>() + (long long)l * vt_l_stride, vt_q_stride, VT_PITCH,
-                                          att, E, B, n_active, per_q, src32, Ls, e->d.src_pad_token_idx, st.ctrl + CTRL_LS, H, st.desc, s);
+                                          att, E, Bq, n_active, per_q, src32, Ls, e->d.src_pad_token_idx, st.ctrl + CTRL_LS, H, st.desc, s);
                 return;
             }
         }
-        attn(q2, E, kv, kv + E, 2 * E, att, E, B, n_active, per_q, Ls, Ls, st.active,
+        attn(q2, E, kv, kv + E, 2 * E, att, E, Bq, n_active, per_q, Ls, Ls, st.active,
              src32, Ls, e->d.src_pad_token_idx, false, H, HD, s, st.ctrl + CTRL_LS, e->srclen.as<int>(), st.desc);
     };
 
     auto enqueue_iteration = [&]() -> int {
+        RowCount rows(Bq * per_q, n_active, per_q);
         {   // KV-cache append of the previous iteration's accepted tokens + embedding of this iteration's step tokens
             Scope sc(e, KC_EMBED, s);
-            launch_greedy_advance<ActT>(st, e->tgt_emb, e->pe, E, x, xh, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, kc, vc,
+            GreedyState stq = st;
+            stq.B = Bq;               // grid sizing only: the kernel indexes the live slots, all below the bucket
+            launch_greedy_advance<ActT>(stq, e->tgt_emb, e->pe, E, x, xh, e->qkv.as<ActT>(), qkv_l_stride, n_dec, 3 * E, kc, vc,
                                         cache_l_stride, cache_q_stride, E, s, tc_attn ? vt_l_stride : 0, tc_attn ? vt_q_stride : 0, tc_attn ? VT_PITCH : 0);
         }
         if (decoder_stack<ActT>(e, rows, n_dec, qkv_l_stride, self_attn, cross_attn, s)) return 1;
@@ -740,42 +749,75 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
     // (every kernel reads a live count of zero), so a longer graph only adds a few of those per batch.
     static const int graph_iters = [] { const char* v = getenv("TTB_GRAPH_ITERS"); const int k = v ? atoi(v) : 4; return k < 1 ? 1 : (k > 16 ? 16 : k); }();
     const int K_it = use_graph ? graph_iters : 1;
+    // buckets of live queries a graph is captured for (largest first; lazily, the first time the host picks one)
+    int bucket_q[ttb_engine::kBuckets];
+    int n_buckets = 0;
+    {
+        static const bool no_buckets = [] { const char* v = getenv("TTB_NO_BUCKETS"); return v && v[0] == '1'; }();
+        int cand[ttb_engine::kBuckets];
+        for (int i = 0; i < 8; ++i) cand[i] = (B * (8 - i) + 7) / 8;      // B, 7B/8, ... B/8
+        cand[8] = (B + 15) / 16;
+        cand[9] = 1;
+        for (int i = 0; i < ttb_engine::kBuckets; ++i) {
+            if (i > 0 && (no_buckets || standard)) break;
+            if (n_buckets == 0 || (cand[i] >= 1 && cand[i] < bucket_q[n_buckets - 1])) bucket_q[n_buckets++] = cand[i];
+        }
+    }
     if (use_graph) {
         const long long key[12] = {B, N, D, standard ? 1 : 0, max_len, pad, bos, eos, tie_break, e->alloc_signature(),
                                    (long long)sizeof(ActT) + 16 * K_it + (tc_attn ? 1024 : 0), replace};
-        if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-            const long long l0 = e->launches;
-            cudaGraph_t graph = nullptr;
-            TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-            int rc = 0;
-            for (int k = 0; k < K_it && !rc; ++k) rc = enqueue_iteration();
-            cudaError_t ce = cudaStreamEndCapture(s, &graph);
-            if (rc || ce != cudaSuccess) {
-                if (graph) cudaGraphDestroy(graph);
-                if (!rc) set_last_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce));
-                return 1;
-            }
-            TTB_CUDA_OK(cudaGraphInstantiate(&e->graph_exec, graph, 0));
-            cudaGraphDestroy(graph);
-            e->graph_launches = e->launches - l0;
-            e->launches = l0;  // capturing did not launch anything
+        if (memcmp(key, e->graph_key, sizeof(key)) != 0) {
+            for (auto& gb : e->graph_exec) for (auto& g : gb) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
             memcpy(e->graph_key, key, sizeof(key));
         }
     }
+    // Once queries retire the graphs get SHORT (half the iterations): the host then follows the shrinking live count more
+    // closely (smaller buckets sooner) and fewer no-op iterations run behind the end of the batch; while the whole batch is
+    // alive (always, with random-init weights) the long graph saves the ~12 us boundary between launches.
+    const int K_short = std::max(1, K_it / 2);
+    auto graph_for = [&](int bi, int sh) -> int {      // capture on first use
+        if (e->graph_exec[bi][sh]) return 0;
+        const long long l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        Bq = bucket_q[bi];
+        const int n_it = sh ? K_short : K_it;
+        TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        int rc = 0;
+        for (int k = 0; k < n_it && !rc; ++k) rc = enqueue_iteration();
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (!rc) set_last_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce));
+            return 1;
+        }
+        TTB_CUDA_OK(cudaGraphInstantiate(&e->graph_exec[bi][sh], graph, 0));
+        cudaGraphDestroy(graph);
+        e->graph_launches = (e->launches - l0) / n_it;   // per iteration
+        e->launches = l0;  // capturing did not launch anything
+        return 0;
+    };
 
     // Lagged polling: the host looks at the control words of iteration (it - LAG) while iterations up
-    // to `it` are already queued, so the GPU never waits for the host.
+    // to `it` are already queued, so the GPU never waits for it.
     constexpr int RING = 4;
     const int LAG = K_it > 1 ? 1 : 2;   // launches (of K_it iterations each) the host stays ahead of the control words it reads
-    int it = 0;
+    int it = 0, iters_enq = 0;
     bool done = false;
-    while (!done && it * K_it < max_iters) {
+    int known_live = B;                 // live queries in the newest control words read: an upper bound from then on
+    while (!done && iters_enq < max_iters) {
+        int bi = 0;
+        while (bi + 1 < n_buckets && bucket_q[bi + 1] >= known_live) ++bi;
+        Bq = bucket_q[bi];
         if (use_graph) {
-            TTB_CUDA_OK(cudaGraphLaunch(e->graph_exec, s));
-            e->launches += e->graph_launches;
+            const int sh = (known_live < B && K_short < K_it) ? 1 : 0;
+            if (graph_for(bi, sh)) return 1;
+            TTB_CUDA_OK(cudaGraphLaunch(e->graph_exec[bi][sh], s));
+            e->launches += e->graph_launches * (sh ? K_short : K_it);
+            iters_enq += sh ? K_short : K_it;
         } else if (enqueue_iteration()) {
             return 1;
+        } else {
+            ++iters_enq;
         }
         TTB_CUDA_OK(cudaMemcpyAsync(e->h_ctrl + (it % RING) * CTRL_COUNT, st.ctrl, CTRL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         TTB_CUDA_OK(cudaEventRecord(e->poll_ev[it % RING], s));
@@ -783,6 +825,7 @@ static int greedy_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int 
             const int j = (it - LAG) % RING;
             TTB_CUDA_OK(cudaEventSynchronize(e->poll_ev[j]));
             if (e->h_ctrl[j * CTRL_COUNT + CTRL_DONE]) done = true;
+            else known_live = std::min(known_live, std::max(1, e->h_ctrl[j * CTRL_COUNT + CTRL_N_ACTIVE]));
         }
         ++it;
     }
@@ -1410,7 +1453,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     if (e->h_ctrl) cudaFreeHost(e->h_ctrl);
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->prof.pool) cudaEventDestroy(ev);
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (auto& gb : e->graph_exec) for (auto& g : gb) if (g) cudaGraphExecDestroy(g);
     for (int p = 0; p < 2; ++p) if (e->beam_graph[p]) cudaGraphExecDestroy(e->beam_graph[p]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->join_ev) cudaEventDestroy(e->join_ev);

@@ -779,7 +779,7 @@ def main():
         todo = []
         if args.workload == "greedy":
             other = "copy" if args.weights == "random" else "random"
-            todo.append(("trained_like" if other == "copy" else "random_init_worst_case", Workload("greedy", other, args), 18 if other == "copy" else 6, True))
+            todo.append(("trained_like" if other == "copy" else "random_init_worst_case", Workload("greedy", other, args), 32 if other == "copy" else 6, True))
         if args.workload == "greedy":
             todo += [("beam", Workload("beam", "copy", args), 24, False), ("retro", Workload("retro", "copy", args), 24, False)]
         for key, w2, k2, full in todo:

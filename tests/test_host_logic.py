@@ -313,3 +313,35 @@ def test_copy_task_weights_behave_like_a_trained_copier():
     assert torch.quantile((top2[..., 0] - top2[..., 1])[mask], 0.02) > 3.0   # trained-like margins: bf16 keeps the arg-max
     eos_pos = (src == 2).float().argmax(-1) - 1
     assert (logits.argmax(-1)[torch.arange(6), eos_pos] == 2).all()
+
+
+def test_bench_workloads_are_the_golden_cases():
+    """bench.py's workloads (batch 0, weights) are exactly what tests/golden/make_golden_bench.py ran the reference on: the
+    parity block of the bench line compares like with like."""
+    import importlib.util
+    import json
+    import types
+    import numpy as np
+    from translation_transformer_b200.weights import state_dict_checksum
+    spec = importlib.util.spec_from_file_location("bench_mod", REPO / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    args = types.SimpleNamespace(vocab=288, seed=1234, max_len=200, tie_break="torch_cpu")
+    cases = {c["id"]: c for c in json.load(open(REPO / "tests/golden/bench_configs.json"))}
+    z = np.load(REPO / "tests/golden/bench_configs.npz")
+    for key, weights, gid in (("greedy", "copy", "cfg1_copy"), ("greedy", "random", "cfg1_random"), ("beam", "copy", "cfg2_copy"), ("retro", "copy", "cfg3_copy")):
+        wl = bench.Workload(key, weights, args)
+        assert wl.golden_id == gid
+        c = cases[gid]
+        assert np.array_equal(wl.batch(0).numpy(), z[gid + "_src"].astype(np.int64)), gid
+        assert state_dict_checksum(wl.sd) == c["checksum"], gid
+        assert (wl.w["draft_len"], wl.w["n_drafts"], wl.bs) == (c["draft_len"], c["n_drafts"], c["B"])
+        if wl.kind == "beam":
+            assert wl.w["n_best"] == c["n_best"]
+    # another vocabulary / seed has no fixture: the golden check is skipped, not faked
+    assert bench.Workload("greedy", "copy", types.SimpleNamespace(vocab=300, seed=1234, max_len=200, tie_break="torch_cpu")).golden_id is None
+    # algorithmic work of the dominant class: 4 layers x (FFN 4 E F + out-projection 2 E E) flops per token row
+    wlr = bench.Workload("greedy", "random", args)
+    f, b = bench.class_work("gemm_ffn1", wlr.w, wlr.cfg, [32], 80.0, True, True, True, "bf16")
+    rows = 32 * 23 * 11
+    assert abs(f / 4 - (4.0 * rows * 256 * 2048 + 2.0 * rows * 256 * 256 + 16.0 * rows * 256)) < 1.0

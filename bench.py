@@ -88,7 +88,7 @@ def parse():
     ap.add_argument("--in-flight", type=int, default=0,
                     help="batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
                          "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`; 0 (default) = 3 "
-                         "for the random-init greedy workload (every batch keeps all its queries to the end), 8 / 6 for the greedy / beam workloads "
+                         "for the random-init greedy workload (every batch keeps all its queries to the end), 8 for the workloads "
                          "whose batches thin out while they decode (measured: DESIGN.md section 4c)")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
@@ -726,7 +726,7 @@ def main():
     wl = Workload(args.workload, args.weights, args)
 
     def fly_for(w):
-        return args.in_flight if args.in_flight > 0 else (3 if (w.kind == "greedy" and w.weights == "random") else (8 if w.kind == "greedy" else 6))
+        return args.in_flight if args.in_flight > 0 else (3 if (w.kind == "greedy" and w.weights == "random") else 8)
 
     n_fly = fly_for(wl)
     if args.scaling == "strong":

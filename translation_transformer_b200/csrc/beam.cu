@@ -23,6 +23,7 @@ namespace ttb {
 // the CTA that closes the iteration with the same rule the host applies (engine.cu:beam_api, speculative_decoding.py:452-470)
 constexpr int BCX_ALL_FIN = BC_COUNT, BCX_MIN_PAD = BC_COUNT + 1, BCX_ACC = BC_COUNT + 2, BCX_CNT = BC_COUNT + 3, BCX_TICKET = BC_COUNT + 4,
               BCX_W = BC_COUNT + 5, BCX_ITER = BC_COUNT + 6,
+              BCX_NLIVE_NEXT = BC_COUNT + 8,   // accumulator: new hypotheses without EOS = live candidates of the next iteration
               BCX_DONE = BC_COUNT + 7;   // the loop has ended (every hypothesis finished, length budget used up, or an error): set by the CTA that
                                          // closes an iteration with the reference's own stop rule, so that an iteration the host has
                                          // enqueued ahead of reading this one's outcome is a no-op on the device
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             st.n_parent[q * K + k] = fin ? -1 : c;
             st.n_keep[q * K + k] = p;
             st.n_row[q * K + k] = r;
-            if (!has_eos) atomicAnd(&st.ctrl[BCX_ALL_FIN], 0);
+            if (!has_eos) { atomicAnd(&st.ctrl[BCX_ALL_FIN], 0); atomicAdd(&st.ctrl[BCX_NLIVE_NEXT], 1); }
             atomicMin(&st.ctrl[BCX_MIN_PAD], pads);
             if (!fin) { atomicAdd(&st.ctrl[BCX_ACC], p); atomicAdd(&st.ctrl[BCX_CNT], 1); }
         }
@@ -582,7 +583,9 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
             st.ctrl[BC_EMPTY_COLS] = atomicAdd(&st.ctrl[BCX_MIN_PAD], 0);
             st.ctrl[BC_ACCEPTED] += acc;
             st.ctrl[BC_PRODUCED] += acc + cnt;
+            const int nlive_next = atomicAdd(&st.ctrl[BCX_NLIVE_NEXT], 0);
             st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
+            st.ctrl[BCX_NLIVE_NEXT] = 0;
             // width of the next iteration's token matrix (speculative_decoding.py:452-470, mirrored by the host loop)
             const int seq = st.ctrl[BCX_ITER] + 1;
             {
@@ -597,10 +600,12 @@ __global__ void __launch_bounds__(256) beam_expand_kernel(BeamState st, int beam
                 // what the host needs per iteration, packed into ONE 64-bit word of its own (pinned, mapped) memory:
                 // sequence number | error | all finished | empty columns.  One posted store: no copy engine, no stream
                 // synchronisation, no system-scope fence between this kernel and the cache update that follows it.
-                const unsigned long long word = ((unsigned long long)(unsigned)seq << 32) |
-                                                ((unsigned long long)(atomicAdd(&st.ctrl[BC_ERROR], 0) & 0xff) << 24) |
-                                                ((unsigned long long)(st.ctrl[BC_ALL_FINISHED] & 0xff) << 16) |
-                                                (unsigned long long)(st.ctrl[BC_EMPTY_COLS] & 0xffff);
+                // sequence (24 bits) | error (4) | all finished (1) | empty columns (12) | live candidates of the next iteration (16)
+                const unsigned long long word = ((unsigned long long)(seq & 0xffffff) << 40) |
+                                                ((unsigned long long)(atomicAdd(&st.ctrl[BC_ERROR], 0) & 0xf) << 36) |
+                                                ((unsigned long long)(st.ctrl[BC_ALL_FINISHED] & 1) << 35) |
+                                                ((unsigned long long)(st.ctrl[BC_EMPTY_COLS] & 0xfff) << 23) |
+                                                ((unsigned long long)(nlive_next & 0xffff) << 7);
                 // ring of four words: the host may read iteration i's word after iteration i + 1 (enqueued ahead) has posted its own
                 reinterpret_cast<volatile unsigned long long*>(st.host_ctrl)[seq & 3] = word;
             }
@@ -624,7 +629,7 @@ __global__ void beam_init_kernel(BeamState st) {
         if (threadIdx.x < BC_COUNT) st.ctrl[threadIdx.x] = 0;
         if (threadIdx.x == 0) {
             st.ctrl[BCX_ALL_FIN] = 1; st.ctrl[BCX_MIN_PAD] = 0x7fffffff; st.ctrl[BCX_ACC] = 0; st.ctrl[BCX_CNT] = 0; st.ctrl[BCX_TICKET] = 0;
-            st.ctrl[BCX_W] = st.w0; st.ctrl[BCX_ITER] = 0; st.ctrl[BCX_DONE] = 0;
+            st.ctrl[BCX_W] = st.w0; st.ctrl[BCX_ITER] = 0; st.ctrl[BCX_DONE] = 0; st.ctrl[BCX_NLIVE_NEXT] = 0;
         }
     }
 }

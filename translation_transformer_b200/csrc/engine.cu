@@ -915,7 +915,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     const size_t o_cand0 = take((size_t)Cmax * ldw * 4), o_cand1 = take((size_t)Cmax * ldw * 4);
     const size_t o_lp0 = take(Cmax * 4), o_lp1 = take(Cmax * 4);
     const size_t o_slot = take(Cmax * 4), o_fin = take(Cmax * 4), o_base = take(Cmax * 4), o_nacc = take((size_t)Cmax * N * 4);
-    const size_t o_pick = take(Cmax * 4), o_acc = take(Cmax * 4), o_ctrl = take(16 * 4);   // control words + loop-control accumulators
+    const size_t o_pick = take(Cmax * 4), o_acc = take(Cmax * 4), o_ctrl = take(32 * 4);   // control words + loop-control accumulators
     const size_t o_rows = take((size_t)Rmax * ldw * 4), o_rc = take(Rmax * 4), o_rq = take(Rmax * 4), o_rs = take(Rmax * 4);
     const size_t n_rp = (size_t)Rmax * (D0 + 1);
     const size_t o_topv = take(n_rp * K * 4), o_topi = take(n_rp * K * 4), o_keep = take(n_rp * 4), o_max = take(n_rp * 4), o_sum = take(n_rp * 4);
@@ -1015,14 +1015,17 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     // (beam.cu: BCX_W, BCX_ITER), so the steady state (C = B K, full draft length) can be replayed as a CUDA graph and
     // -- because the device also applies the stop rule itself (BCX_DONE) -- be enqueued AHEAD of the host reading the
     // outcome of the iteration before it.
-    auto enqueue_iteration = [&](int it, int C, int beam, int dl) -> int {
+    // `Cb`: upper bound of the candidates that are still unfinished in this iteration (exact when the host has read the word
+    // of the iteration before, C otherwise): the decoder-side grids are sized for Cb * N rows instead of C * N, so that the
+    // no-op CTAs of finished candidates do not queue for SMs that the other batches in flight are using (§4c of DESIGN.md)
+    auto enqueue_iteration = [&](int it, int C, int beam, int dl, int Cb) -> int {
         const int parity = it & 1;
         st.cand_cur = cand_set[parity]; st.cand_next = cand_set[parity ^ 1];
         st.logp_cur = logp_set[parity]; st.logp_next = logp_set[parity ^ 1];
         kc_cur = kc_set[parity]; kc_next = kc_set[parity ^ 1];
         vc_cur = vc_set[parity]; vc_next = vc_set[parity ^ 1];
         auto body = [&]() -> int {
-        const int R = C * N;
+        const int R = (smart ? C : std::min(C, std::max(1, Cb))) * N;
         bool fused_stats = false;
         { Scope sc(e, KC_MISC, s); launch_beam_prepare(st, C, beam, dl, s); }
         if (cached) {
@@ -1030,7 +1033,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             { Scope sc(e, KC_EMBED, s); launch_beam_embed_cached<ActT>(st, beam, R, dl, e->tgt_emb, e->pe, E, x, xh, s); }
             // attention groups: the N rows of a live candidate share its cache prefix; in smart mode candidates own a
             // different number of rows, so every row is a group of its own
-            const int G = smart ? R : C, n_per_group = smart ? 1 : N;
+            const int G = smart ? R : R / N, n_per_group = smart ? 1 : N;
             auto self_attn = [&](int l, ActT* qkv, ActT* att) {
                 spec_attn(qkv, 3 * E, kc_cur + l * cache_l_stride, vc_cur + l * cache_l_stride, cache_c_stride, E, att, E, G, n_live_cands,
                           st.live_cand, st.c_front, st.cand_cur, ldw, e->d.tgt_pad_token_idx, n_per_group, dl, H, HD, ldw, s, st.desc_self);
@@ -1086,7 +1089,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         }
         return 0;
         };   // body
-        if (use_graph && C == B * K && beam == K && dl == dl_steady) {
+        if (use_graph && C == B * K && beam == K && dl == dl_steady && (smart || Cb >= C)) {
             if (!e->beam_graph[parity]) {
                 const long long l0 = e->launches;
                 cudaGraph_t graph = nullptr;
@@ -1111,13 +1114,14 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
     };
     // wait for the packed word the expand kernel posts for iteration `seq` (sequence | error | all finished | empty columns)
     static const bool pure_spin = [] { const char* v = getenv("TTB_BEAM_SPIN"); return v && v[0] == '1'; }();
+    int live_next = B;      // unfinished candidates entering the next iteration, from the newest word read
     auto wait_word = [&](int seq) -> int {
         volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(hc + 16) + (seq & 3);
         unsigned long long w = 0;
         bool seen = false;
         for (long spin = 0; !seen; ++spin) {
             w = *word;
-            seen = (unsigned)(w >> 32) == (unsigned)seq;
+            seen = (unsigned)((w >> 40) & 0xffffff) == (unsigned)(seq & 0xffffff);
             // the word normally arrives within a few microseconds of the last launch call; past that (long iterations,
             // several engines per GPU and ranks per box sharing the cores) the thread gives its core away between polls
             if (!seen) { if (spin < 256 || pure_spin) cpu_relax(); else sched_yield(); }
@@ -1125,10 +1129,11 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                 const cudaError_t q = cudaStreamQuery(s);
                 if (q == cudaSuccess) {   // stream drained: the word is there, or the mapping is unavailable: take a copy
                     w = *word;
-                    if ((unsigned)(w >> 32) != (unsigned)seq) {
+                    if ((unsigned)((w >> 40) & 0xffffff) != (unsigned)(seq & 0xffffff)) {
                         TTB_CUDA_OK(cudaMemcpy(hc, st.ctrl, BC_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
-                        w = ((unsigned long long)(unsigned)seq << 32) | ((unsigned long long)(hc[BC_ERROR] & 0xff) << 24) |
-                            ((unsigned long long)(hc[BC_ALL_FINISHED] & 0xff) << 16) | (unsigned long long)(hc[BC_EMPTY_COLS] & 0xffff);
+                        w = ((unsigned long long)(seq & 0xffffff) << 40) | ((unsigned long long)(hc[BC_ERROR] & 0xf) << 36) |
+                            ((unsigned long long)(hc[BC_ALL_FINISHED] & 1) << 35) | ((unsigned long long)(hc[BC_EMPTY_COLS] & 0xfff) << 23) |
+                            ((unsigned long long)0xffff << 7);   // live candidates unknown: full grids
                     }
                     seen = true;
                 } else if (q != cudaErrorNotReady) {
@@ -1136,9 +1141,10 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                 }
             }
         }
-        hc[BC_ERROR] = (int)((w >> 24) & 0xff);
-        hc[BC_ALL_FINISHED] = (int)((w >> 16) & 0xff);
-        hc[BC_EMPTY_COLS] = (int)(w & 0xffff);
+        hc[BC_ERROR] = (int)((w >> 36) & 0xf);
+        hc[BC_ALL_FINISHED] = (int)((w >> 35) & 1);
+        hc[BC_EMPTY_COLS] = (int)((w >> 23) & 0xfff);
+        live_next = (int)((w >> 7) & 0xffff);
         return 0;
     };
     // Host loop.  `iters` iterations have been read back (their outcome is known exactly: W, filled, budget, dl below are
@@ -1158,14 +1164,16 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
             const int grow = dl + 1 - empty_cols;
             if (grow > 0) W += grow;
             TTB_CHECK(W <= ldw, "beam search token matrix outgrew its buffer");
-            if (enqueue_iteration(enq, C, beam, dl)) return 1;
+            if (enqueue_iteration(enq, C, beam, dl, std::min(live_next, C))) return 1;
             dl_enq = dl;
             ++enq;
         }
+        // ahead of the word only while every candidate is alive (iteration 0 aside): once hypotheses finish, the exact live
+        // count of the word sizes the next iteration's grids, which is worth more than the host's head start (both measured)
         if (ahead_ok && enq == iters + 1 && dl_enq == dl_steady && max_len - (filled + 2 * (dl_enq + 1)) - 1 >= dl_enq &&
-            W + 2 * (dl_enq + 1) <= ldw) {
+            W + 2 * (dl_enq + 1) <= ldw && (iters == 0 || live_next >= B * K)) {
             // `filled` is the exact count before the iteration in flight: after it and one more at most 2 (dl + 1) columns are added
-            if (enqueue_iteration(enq, B * K, K, dl_enq)) return 1;
+            if (enqueue_iteration(enq, B * K, K, dl_enq, B * K)) return 1;
             ++enq;
         }
         if (wait_word(iters + 1)) return 1;

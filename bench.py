@@ -608,6 +608,8 @@ def measure_workload(wl, args, local_rank, world, rank, n_fly, steps, warmup, n_
         hist = list(buf[:n_hist])
         lib.ttb_engine_set_profiling(eng._h, 0)
     # ---- timed regions ----------------------------------------------------------------------------------------------
+    if world > 1:   # untimed pass through the shared queue and the NCCL all-gather (the first collective of a kind sets up its channels)
+        R.timed(0, world * n_fly, False)
     one_n = max(1, min(n_timed_batches, steps))
     one_ms, _, one_fail = R.timed(first, one_n, False, decoder=R.one) if (n_fly > 1 and world == 1) else (None, 0, 0)
     c0 = R.counters()

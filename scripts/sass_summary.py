@@ -29,7 +29,7 @@ for block in sass.split("Function : ")[1:]:
     c = Counter()
     n_inst = 0
     for line in body.splitlines():
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if not m:
             continue
         n_inst += 1

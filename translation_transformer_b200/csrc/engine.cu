@@ -165,7 +165,8 @@ struct ttb_engine {
     cudaGraphExec_t graph_exec[kBuckets][2] = {};   // greedy iteration graphs per live-query bucket (grids sized for the bucket) x {long, short}
     long long graph_key[12] = {};
     long long graph_launches = 0;
-    cudaGraphExec_t beam_graph[2] = {nullptr, nullptr};   // steady-state iteration of the speculative beam search, per ping-pong parity
+    static constexpr int kBeamBuckets = 8;
+    cudaGraphExec_t beam_graph[2][kBeamBuckets] = {};   // steady-state iteration of the speculative beam search, per ping-pong parity and live-candidate bucket
     long long beam_graph_key[20] = {};
     long long beam_graph_launches = 0;
     DevBuf beam;                 // arena of the beam-search state
@@ -998,7 +999,7 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         const long long key[20] = {B, K, N, D0, Ls, max_len, V, smart ? 1 : 0, pad, bos, eos, c_token, tie_break, e->alloc_signature(),
                                    (long long)sizeof(ActT), (long long)reinterpret_cast<uintptr_t>(st.host_ctrl), n_dec, 0, 0, 0};
         if (memcmp(key, e->beam_graph_key, sizeof(key)) != 0) {
-            for (int p = 0; p < 2; ++p) if (e->beam_graph[p]) { cudaGraphExecDestroy(e->beam_graph[p]); e->beam_graph[p] = nullptr; }
+            for (auto& gp : e->beam_graph) for (auto& g : gp) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
             memcpy(e->beam_graph_key, key, sizeof(key));
         }
     }
@@ -1024,6 +1025,14 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         st.logp_cur = logp_set[parity]; st.logp_next = logp_set[parity ^ 1];
         kc_cur = kc_set[parity]; kc_next = kc_set[parity ^ 1];
         vc_cur = vc_set[parity]; vc_next = vc_set[parity ^ 1];
+        // replayed iterations bake their grids in: the live-candidate bound is rounded up to one of eight buckets of C
+        const bool graph_it = use_graph && C == B * K && beam == K && dl == dl_steady;
+        int gb = 0;
+        if (graph_it && !smart) {
+            const int want = std::min(C, std::max(1, Cb));
+            while (gb + 1 < ttb_engine::kBeamBuckets && (C * (ttb_engine::kBeamBuckets - gb - 1) + ttb_engine::kBeamBuckets - 1) / ttb_engine::kBeamBuckets >= want) ++gb;
+            Cb = (C * (ttb_engine::kBeamBuckets - gb) + ttb_engine::kBeamBuckets - 1) / ttb_engine::kBeamBuckets;
+        }
         auto body = [&]() -> int {
         const int R = (smart ? C : std::min(C, std::max(1, Cb))) * N;
         bool fused_stats = false;
@@ -1089,8 +1098,8 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
         }
         return 0;
         };   // body
-        if (use_graph && C == B * K && beam == K && dl == dl_steady && (smart || Cb >= C)) {
-            if (!e->beam_graph[parity]) {
+        if (graph_it) {
+            if (!e->beam_graph[parity][gb]) {
                 const long long l0 = e->launches;
                 cudaGraph_t graph = nullptr;
                 TTB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -1101,12 +1110,12 @@ static int beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, int ma
                     if (!rc) set_last_error(std::string("CUDA graph capture of the beam-search iteration failed: ") + cudaGetErrorString(ce));
                     return 1;
                 }
-                TTB_CUDA_OK(cudaGraphInstantiate(&e->beam_graph[parity], graph, 0));
+                TTB_CUDA_OK(cudaGraphInstantiate(&e->beam_graph[parity][gb], graph, 0));
                 cudaGraphDestroy(graph);
                 e->beam_graph_launches = e->launches - l0;
                 e->launches = l0;   // capturing did not launch anything
             }
-            TTB_CUDA_OK(cudaGraphLaunch(e->beam_graph[parity], s));
+            TTB_CUDA_OK(cudaGraphLaunch(e->beam_graph[parity][gb], s));
             e->launches += e->beam_graph_launches;
             return 0;
         }
@@ -1462,7 +1471,7 @@ void ttb_engine_destroy(ttb_engine* e) {
     for (auto& ev : e->poll_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->prof.pool) cudaEventDestroy(ev);
     for (auto& gb : e->graph_exec) for (auto& g : gb) if (g) cudaGraphExecDestroy(g);
-    for (int p = 0; p < 2; ++p) if (e->beam_graph[p]) cudaGraphExecDestroy(e->beam_graph[p]);
+    for (auto& gp : e->beam_graph) for (auto& g : gp) if (g) cudaGraphExecDestroy(g);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->join_ev) cudaEventDestroy(e->join_ev);
     if (e->t0) cudaEventDestroy(e->t0);

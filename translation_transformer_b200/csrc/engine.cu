@@ -1306,6 +1306,7 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     ActT* xgh = Prec<ActT>::lowp ? (ActT*)(base + o_xgh) : nullptr;
     float* logits = (float*)(base + o_lg);
     ActT *kc_cur = nullptr, *vc_cur = nullptr, *kc_next = nullptr, *vc_next = nullptr;
+    int* const y_set[2] = {st.y_cur, st.y_next};
     if (cached) {
         st.c_front = (int*)(base + o_cf); st.parent = (int*)(base + o_par);
         st.desc_self = (int4*)(base + o_ds); st.desc_cross = (int4*)(base + o_dc);
@@ -1320,6 +1321,7 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
     const int* n_live = st.ctrl;
     int* hc = e->h_ctrl;
     int W = 1, beam = 1, calls = 0;
+    constexpr int sb_lag = 1;   // steps the host stays ahead of the control words it reads (blocking-sync events: the wait sleeps)
     // step 0 on the BOS column (:106), then at most max_len - 2 further columns (:127)
     for (int step = 0; step < max_len - 1; ++step) {
         const int C = B * beam;
@@ -1351,14 +1353,19 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
             }
             std::swap(kc_cur, kc_next);
             std::swap(vc_cur, vc_next);
-            TTB_CUDA_OK(cudaMemcpyAsync(hc, st.ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-            TTB_CUDA_OK(cudaStreamSynchronize(s));
-            ++calls;
+            // the stop test runs on the device (std_beam.cu: ctrl[2]); the host reads the control words of step - 1 while
+            // this step is already enqueued (a step behind the end is a no-op), so the GPU never waits for the host
+            TTB_CUDA_OK(cudaMemcpyAsync(hc + 32 + (step & 3) * 8, st.ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TTB_CUDA_OK(cudaEventRecord(e->poll_ev[step & 3], s));
             std::swap(st.y_cur, st.y_next);
             std::swap(st.score_cur, st.score_next);
             beam = K;
             W += 1;
-            if (step > 0 && hc[1] == B * K) break;   // every hypothesis contains EOS (:169); the first step never breaks (:106-125)
+            if (step >= sb_lag) {
+                const int j = (step - sb_lag) & 3;
+                TTB_CUDA_OK(cudaEventSynchronize(e->poll_ev[j]));
+                if (hc[32 + j * 8 + 2]) break;       // every hypothesis contains EOS (:169)
+            }
             continue;
         }
         RowCount rows(C * W, n_live, W);
@@ -1389,6 +1396,16 @@ static int std_beam_api(ttb_engine* e, const int64_t* src_dev, int B, int Ls, in
         beam = K;
         W += 1;
         if (step > 0 && hc[1] == B * K) break;   // every hypothesis contains EOS (:169); the first step never breaks (:106-125)
+    }
+    if (cached) {
+        // steps that really ran (the host may have enqueued one more, a no-op): width, call count, and the hypothesis set
+        // the last real step wrote (step i reads set i & 1 and writes the other one)
+        int fin[4] = {};
+        TTB_CUDA_OK(cudaMemcpyAsync(fin, st.ctrl, sizeof(fin), cudaMemcpyDeviceToHost, s));
+        TTB_CUDA_OK(cudaStreamSynchronize(s));
+        calls = fin[3];
+        W = 1 + calls;
+        st.y_cur = (calls & 1) ? y_set[1] : y_set[0];
     }
     launch_beam_export(st.y_cur, ldw, B * K, W, reinterpret_cast<long long*>(out_dev), s);
     e->launches++;

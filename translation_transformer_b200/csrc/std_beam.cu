@@ -14,8 +14,15 @@
 
 namespace ttb {
 
+// Control words: [0] live rows of the step, [1] hypotheses that contain EOS after the step's selection, [2] DONE: every
+// hypothesis contains EOS (raised by the CTA of sbeam_select that finishes last; the reference's stop test, :169) -- a step the
+// host has enqueued ahead of reading [1] is then a no-op --, [3] steps that really ran, [4] ticket of the select CTAs
 __global__ void __launch_bounds__(1024) sbeam_prepare_kernel(StdBeamState st, int C, int beam, int W) {
     __shared__ int s_run;
+    if (st.ctrl[2]) {
+        if (threadIdx.x == 0) st.ctrl[0] = 0;   // no live rows: the decoder kernels of this step exit at once
+        return;
+    }
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int* row = st.y_cur + (long long)c * st.ldw;
         int fin = 0;
@@ -83,7 +90,7 @@ template void launch_sbeam_gather_last<__nv_bfloat16>(const StdBeamState&, const
 __global__ void __launch_bounds__(256) sbeam_scores_kernel(StdBeamState st, int C, const float* __restrict__ logits) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (c >= C) return;
+    if (c >= C || st.ctrl[2]) return;
     const int V = st.V, r = st.cand_row[c];
     const float* p = r >= 0 ? logits + (long long)r * V : nullptr;
     auto val = [&](int v) { return p ? p[v] : (v == st.pad ? 35.0f : 0.0f); };
@@ -107,6 +114,7 @@ void launch_sbeam_scores(const StdBeamState& st, int C, const float* logits, cud
 // token rows.
 __global__ void __launch_bounds__(256) sbeam_select_kernel(StdBeamState st, int beam, int W) {
     extern __shared__ __align__(8) unsigned char s_sel_raw[];
+    if (st.ctrl[2]) return;                          // step enqueued behind the end of the search
     VF* s_e = reinterpret_cast<VF*>(s_sel_raw);      // [beam * V] (score, flat index)
     const int b = blockIdx.x, V = st.V, K = st.K, n = beam * V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +140,16 @@ __global__ void __launch_bounds__(256) sbeam_select_kernel(StdBeamState st, int 
         if (lane == 0 && fin) ++n_fin;
     }
     if (lane == 0 && n_fin) atomicAdd(&st.ctrl[1], n_fin);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st.ctrl[4], 1) == (int)gridDim.x - 1) {   // last CTA of the step: stop test, step count
+            __threadfence();
+            st.ctrl[4] = 0;
+            st.ctrl[3] += 1;
+            if (W > 1 && atomicAdd(&st.ctrl[1], 0) == st.B * st.K) st.ctrl[2] = 1;   // the first step (W = 1) never stops (:106-125)
+        }
+    }
 }
 int launch_sbeam_select(const StdBeamState& st, int beam, int W, cudaStream_t s) {
     const size_t smem = (size_t)beam * st.V * sizeof(VF);
@@ -171,6 +189,7 @@ __global__ void sbeam_cache_update_kernel(StdBeamState st, int W, const ActT* __
                                           const ActT* __restrict__ kc_cur, const ActT* __restrict__ vc_cur, ActT* __restrict__ kc_next,
                                           ActT* __restrict__ vc_next, long long cache_layer_stride, long long cache_cand_stride) {
     const int cn = blockIdx.x, l = blockIdx.y;
+    if (st.ctrl[2]) return;                          // the search has ended: the caches are not read again
     const int parent = st.parent[cn];
     const int r = st.cand_row[parent];
     if (r < 0) return;                               // continuation of a finished hypothesis: never decoded again
@@ -209,7 +228,7 @@ __global__ void sbeam_init_kernel(StdBeamState st) {
         st.y_cur[(long long)b * st.ldw] = st.bos;
         st.score_cur[b] = 0.f;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 4) st.ctrl[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 8) st.ctrl[threadIdx.x] = 0;
 }
 void launch_sbeam_init(const StdBeamState& st, cudaStream_t s) { sbeam_init_kernel<<<8, 256, 0, s>>>(st); }
 

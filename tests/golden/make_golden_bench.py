@@ -44,11 +44,23 @@ CASES = {
     "cfg2_copy": dict(kind="beam", arch="product", weights="copy", B=4, src_seed=100003, max_len=200, n_best=5, draft_len=10, n_drafts=23),
     "cfg3_copy": dict(kind="beam", arch="retro", weights="copy", B=8, src_seed=200003, max_len=200, n_best=10, draft_len=10, n_drafts=2),
     "cfg3_copy20": dict(kind="beam", arch="retro", weights="copy", B=8, src_seed=200003, max_len=200, n_best=20, draft_len=14, n_drafts=5),
+    # smart_drafts_mode=True at the configs[2] shape (speculative_decoding.py:600-845)
+    "cfg2_smart_copy": dict(kind="beam", arch="product", weights="copy", B=4, src_seed=100003, max_len=200, n_best=5, draft_len=10, n_drafts=23, smart=True),
+    # BASELINE.json configs[0]: bs 1, draft_len 10, the reference's own test sources (tokenizer trained on the test file), one case per line
+    **{f"cfg0_copy_line{i}": dict(kind="greedy", arch="product", weights="copy", B=1, src_seed=-1, max_len=200, draft_len=10, n_drafts=23, file_line=i)
+       for i in range(4)},
 }
 ARCH = {"product": PRODUCT_PREDICTION, "retro": SINGLE_STEP_RETRO}
 
 
 def case_inputs(c):
+    if "file_line" in c:     # the reference's test file, tokenized with the reference's tokenizer trained on that file
+        from make_golden import load_test_sources
+        tk, src, _, _ = load_test_sources(import_reference()[4])
+        cfg = ModelConfig(src_vocab_size=tk.n_tokens, tgt_vocab_size=tk.n_tokens, **ARCH[c["arch"]])
+        row = src[c["file_line"]:c["file_line"] + 1]
+        row = row[:, :int((row != 0).sum())]
+        return cfg, copy_task_state_dict(cfg, SEED), row
     cfg = ModelConfig(src_vocab_size=VOCAB, tgt_vocab_size=VOCAB, **ARCH[c["arch"]])
     sd = copy_task_state_dict(cfg, SEED) if c["weights"] == "copy" else random_init_state_dict(cfg, SEED)
     kw = RETRO_SRC if c["arch"] == "retro" else {}
@@ -66,11 +78,12 @@ def run_case(ref, name, c, arrays):
     if c["kind"] == "greedy":
         g = spec.TranslationInferenceGreedySpeculative(m, max_len=c["max_len"], draft_len=c["draft_len"], n_drafts=c["n_drafts"],
                                                        pad_token=0, bos_token=1, eos_token=2, replace_token=7)
+        # (the replace token of the test-file vocabulary is whatever id 7 is there: any non-service token serves)
     else:
         g = spec.TranslationInferenceBeamSearchSpeculative(m, max_len=c["max_len"], n_best=c["n_best"], draft_len=c["draft_len"],
-                                                           n_drafts=c["n_drafts"], vocab_size=VOCAB, smart_drafts_mode=False,
+                                                           n_drafts=c["n_drafts"], vocab_size=cfg.tgt_vocab_size, smart_drafts_mode=bool(c.get("smart", False)),
                                                            pad_token=0, bos_token=1, eos_token=2, C_token=7)
-    rec = dict(c, id=name, vocab=VOCAB, seed=SEED, checksum=state_dict_checksum(sd), src_kw=RETRO_SRC if c["arch"] == "retro" else {})
+    rec = dict(c, id=name, vocab=cfg.tgt_vocab_size, seed=SEED, checksum=state_dict_checksum(sd), src_kw=RETRO_SRC if c["arch"] == "retro" else {})
     t0 = time.time()
     with Hooks(m) as h, torch.inference_mode():
         try:

@@ -41,6 +41,8 @@ def _weights(case):
 
 def _sources(case, z):
     src = torch.from_numpy(z[case["id"] + "_src"].astype(np.int64))
+    if "file_line" in case:      # BASELINE.json configs[0]: one line of the reference's test file (tokenized by make_golden_bench.py)
+        return src
     # the fixture's sources ARE the bench's batches: regenerate them the way bench.py does and compare
     n = 32 if case["arch"] == "product" else case["B"]
     again = synthetic_sources(n, case["vocab"], seed=case["src_seed"], **case.get("src_kw", {}))[:case["B"]]
@@ -130,7 +132,7 @@ def test_beam_bench_config_fp32_bit_exact(dev, case):
     src = _sources(case, z).to(dev)
     eng = _engine(cfg, sd, "fp32")
     gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"], case["vocab"],
-                                                    False, 0, 1, 2, 7, keep_trace=True)
+                                                    bool(case.get("smart", False)), 0, 1, 2, 7, keep_trace=True)
     assert case["error"] is None
     out = gen.generate(src).cpu().numpy()
     ref = z[case["id"] + "_out"].astype(np.int64)
@@ -138,10 +140,18 @@ def test_beam_bench_config_fp32_bit_exact(dev, case):
     assert np.array_equal(out, ref)                                                   # all n_best hypotheses of every query
     assert (gen.model_calls_num, gen.accepted_tokens_num, gen.produced_non_pad_tokens) == \
         (case["model_calls"], case["accepted_tokens"], case["produced_non_pad_tokens"])
-    nacc = np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace])
     pick = np.concatenate([t["pick"] for t in gen.trace])
-    assert np.array_equal(nacc, z[case["id"] + "_nacc"].astype(np.int64))
     assert np.array_equal(pick, z[case["id"] + "_pick"].astype(np.int64))
+    ref_nacc = z[case["id"] + "_nacc"].astype(np.int64)
+    if case.get("smart"):    # ragged draft groups: the reference pads each iteration to its widest group, the engine to n_drafts
+        off = 0
+        assert len(gen.trace) == len(case["topk1_shapes"])
+        for t, (C, L) in zip(gen.trace, case["topk1_shapes"]):
+            na = t["n_accepted"]
+            assert na.shape[0] == C and np.array_equal(na[:, :L], ref_nacc[off:off + C * L].reshape(C, L)) and (na[:, L:] == -1).all()
+            off += C * L
+    else:
+        assert np.array_equal(np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace]), ref_nacc)
     eng.close()
 
 
@@ -153,7 +163,7 @@ def test_beam_bench_config_bf16_vs_reference(dev, case, record_property):
     src = _sources(case, z).to(dev)
     eng = _engine(cfg, sd, "bf16")
     gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"], case["vocab"],
-                                                    False, 0, 1, 2, 7)
+                                                    bool(case.get("smart", False)), 0, 1, 2, 7)
     out = gen.generate(src).cpu().numpy()
     ref = z[case["id"] + "_out"].astype(np.int64)
     W = max(out.shape[-1], ref.shape[-1])
@@ -218,7 +228,7 @@ def test_fused_classifier_statistics_match_the_unfused_kernels(dev, case, monkey
         monkeypatch.setenv("TTB_NO_FUSED_STATS", flag)
         eng = _engine(cfg, sd, "bf16")
         gen = TranslationInferenceBeamSearchSpeculative(eng, case["max_len"], case["n_best"], case["draft_len"], case["n_drafts"], case["vocab"],
-                                                        False, 0, 1, 2, 7, keep_trace=True)
+                                                        bool(case.get("smart", False)), 0, 1, 2, 7, keep_trace=True)
         out = gen.generate(src).cpu().numpy()
         res[flag] = (out, gen.model_calls_num, gen.accepted_tokens_num, gen.gpu_launches,
                      np.concatenate([t["n_accepted"].reshape(-1) for t in gen.trace]))

@@ -289,3 +289,33 @@ def test_oracle_reproduces_the_reference_at_the_benchmarked_greedy_config():
     for q in range(nq):
         mine = [(t["n_accepted"][t["rows"].index(q)], t["draft_index"][t["rows"].index(q)]) for t in o.trace if q in t["rows"]]
         assert mine == per_query[q][:len(mine)] and len(mine) == len(per_query[q]), q
+
+
+@pytest.mark.parametrize("line", [0, 1, 2, 3])
+def test_oracle_reproduces_the_reference_at_configs0(line):
+    """BASELINE.json configs[0] (greedy speculative, draft_len 10, bs 1, the reference's own test sources) at the full
+    product-prediction architecture with trained-like weights: tokens, decoder calls, accepted length and chosen draft of
+    every iteration (tests/golden/make_golden_bench.py, cases cfg0_copy_line*)."""
+    import json
+    from pathlib import Path
+    import numpy as np
+    import torch
+    from oracle.greedy_speculative import GreedySpeculativeOracle
+    from oracle.transformer import OracleTransformer
+    from translation_transformer_b200.weights import ModelConfig, PRODUCT_PREDICTION, copy_task_state_dict, state_dict_checksum
+    golden = Path(__file__).resolve().parent / "golden"
+    name = f"cfg0_copy_line{line}"
+    case = [c for c in json.load(open(golden / "bench_configs.json")) if c["id"] == name][0]
+    z = np.load(golden / "bench_configs.npz")
+    cfg = ModelConfig(src_vocab_size=case["vocab"], tgt_vocab_size=case["vocab"], **PRODUCT_PREDICTION)
+    sd = copy_task_state_dict(cfg, case["seed"])
+    assert state_dict_checksum(sd) == case["checksum"]
+    src = torch.from_numpy(z[name + "_src"].astype(np.int64))
+    o = GreedySpeculativeOracle(OracleTransformer(sd, cfg.num_heads), case["max_len"], case["draft_len"], case["n_drafts"], 0, 1, 2, 7, keep_trace=True)
+    out = o.generate(src.clone()).numpy()
+    assert np.array_equal(out, z[name + "_out"].astype(np.int64))
+    assert o.model_calls_num == case["model_calls"]
+    ref_nacc = z[name + "_nacc"].astype(np.int64).reshape(-1, case["n_drafts"])
+    ref_pick = z[name + "_pick"].astype(np.int64)
+    assert [t["draft_index"][0] for t in o.trace] == ref_pick.tolist()
+    assert [t["n_accepted"][0] for t in o.trace] == ref_nacc[np.arange(len(ref_pick)), ref_pick].tolist()

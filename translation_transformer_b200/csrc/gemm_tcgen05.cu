@@ -545,38 +545,93 @@ __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 
+// (a, b) into the same shared-memory offset of CTA `peer_rank`, its 8 bytes counted on that CTA's mbarrier `bar` (same
+// offset there): the receiver waits on its own barrier and needs no cluster-scope release / acquire pair, which costs
+// 1.1-1.9 k cycles per CTA on this chip (in-kernel stamps, profiles/r2_ffn_pair_timeline.txt)
+__device__ __forceinline__ void st_async_peer_f32x2(uint32_t local_addr, uint32_t bar, uint32_t peer_rank, float a, float b) {
+    uint32_t raddr, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(peer_rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(peer_rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr), "f"(a), "f"(b), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_relaxed() {   // execution barrier only: orders no memory
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 // ---- LayerNorm tail shared by the fused kernels: one thread = (row, 64-column half h of the CTA's 128 columns) ----
+// Packed fp32 arithmetic (FFMA2 / FADD2: two lanes per issue slot).  The LayerNorm phases of the fused kernels are bound by
+// the issue rate of their eight epilogue warps (in-kernel stamps: doubling the warps changes nothing), so halving the
+// instruction count is what shortens them.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    float2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    float2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// acc + bias + residual for four columns, in that order (two packed adds per pair)
+__device__ __forceinline__ void add3_f32x4(float* v, const uint32_t* r, const float4& bv, const float4& rv) {
+    const float2 lo = fadd2(fadd2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(bv.x, bv.y)), make_float2(rv.x, rv.y));
+    const float2 hi = fadd2(fadd2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(bv.z, bv.w)), make_float2(rv.z, rv.w));
+    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
+// mean and sum of squared deviations of 64 values: four partial sums (two packed accumulators), chains of 16
 __device__ __forceinline__ void ln_local_stats(const float (&v)[64], float& mean, float& m2) {
-    float s = 0.f;
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) s += v[j];
-    mean = s * (1.0f / 64.0f);
-    float qq = 0.f;
+    for (int j = 0; j < 64; j += 4) {
+        s0 = fadd2(s0, make_float2(v[j], v[j + 1]));
+        s1 = fadd2(s1, make_float2(v[j + 2], v[j + 3]));
+    }
+    mean = ((s0.x + s0.y) + (s1.x + s1.y)) * (1.0f / 64.0f);
+    const float2 nm = make_float2(-mean, -mean);
+    float2 q0 = make_float2(0.f, 0.f), q1 = q0;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qq += d * d; }
-    m2 = qq;
+    for (int j = 0; j < 64; j += 4) {
+        const float2 d0 = fadd2(make_float2(v[j], v[j + 1]), nm), d1 = fadd2(make_float2(v[j + 2], v[j + 3]), nm);
+        q0 = ffma2(d0, d0, q0);
+        q1 = ffma2(d1, d1, q1);
+    }
+    m2 = (q0.x + q0.y) + (q1.x + q1.y);
 }
 // partial statistics of group pidx = 2 * rank + h into both CTAs' tables (float2[4][128])
 __device__ __forceinline__ void ln_publish(float2* part, int pidx, int row, uint32_t rank, float mean, float m2) {
     part[pidx * BM + row] = make_float2(mean, m2);
     st_peer_f32x2(smem_u32(&part[pidx * BM + row]), rank ^ 1u, mean, m2);
 }
-// Chan's combination of the four equally sized groups (64 values each) of a 256-wide row, then scale/shift
+// Chan's combination of the four equally sized groups (64 values each) of a 256-wide row, then scale/shift:
+// ((v - mean) rstd) g + b as two packed FMAs per pair: t = v rstd - mean rstd, t g + b
 __device__ __forceinline__ void ln_normalise(float (&v)[64], const float2* part, int row, const float* gg, const float* bb) {
     const float2 p0 = part[row], p1 = part[BM + row], p2 = part[2 * BM + row], p3 = part[3 * BM + row];
     const float mean = 0.25f * (p0.x + p1.x + p2.x + p3.x);
     const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
     const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
     const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+    const float2 rs = make_float2(rstd, rstd), nmr = make_float2(-mean * rstd, -mean * rstd);
     const float4* g4 = reinterpret_cast<const float4*>(gg);   // 16-byte aligned parameter slices: 32 broadcast
     const float4* b4 = reinterpret_cast<const float4*>(bb);   // LDS.128 per thread instead of 128 LDS.32
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float4 g = g4[j], b = b4[j];
-        v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
-        v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
-        v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
-        v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+        const float2 lo = ffma2(ffma2(make_float2(v[4 * j], v[4 * j + 1]), rs, nmr), make_float2(g.x, g.y), make_float2(b.x, b.y));
+        const float2 hi = ffma2(ffma2(make_float2(v[4 * j + 2], v[4 * j + 3]), rs, nmr), make_float2(g.z, g.w), make_float2(b.z, b.w));
+        v[4 * j + 0] = lo.x;
+        v[4 * j + 1] = lo.y;
+        v[4 * j + 2] = hi.x;
+        v[4 * j + 3] = hi.y;
     }
 }
 // fp32 values into two [128 x 32] boxes and bf16 values into one [128 x 64] box (128-byte swizzle, TMA-store layout)
@@ -780,10 +835,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
                 const int j = c0 + 4 * c;
                 const float4 bv = *reinterpret_cast<const float4*>(prm + h * 64 + j);
-                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
-                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
-                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
-                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+                add3_f32x4(v + j, r + 4 * c, bv, rv);
             }
         }
         float mean, m2;
@@ -1250,10 +1302,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
                 const int j = c0 + 4 * c;
                 const float4 bv = *reinterpret_cast<const float4*>(prm + hh * 64 + j);
-                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
-                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
-                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
-                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+                add3_f32x4(v + j, r + 4 * c, bv, rv);
             }
         }
         mbar_wait(recv_bar, 0);   // the peer's partial sum has landed (its flight overlapped the loads above)
@@ -1262,10 +1311,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         for (int c = 0; c < 16; ++c) {
             const int chunk = hh * 16 + c;
             const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
-            v[4 * c + 0] += pv.x;
-            v[4 * c + 1] += pv.y;
-            v[4 * c + 2] += pv.z;
-            v[4 * c + 3] += pv.w;
+            {
+                const float2 lo = fadd2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(pv.x, pv.y));
+                const float2 hi = fadd2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(pv.z, pv.w));
+                v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
+            }
         }
         float mean, m2;
         ln_local_stats(v, mean, m2);
@@ -1448,6 +1498,8 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     const uint32_t x2_recv = bar_base + 8u * (2 * NSLOT + 13);      // the partner's half of the normalised tile has landed
     const uint32_t x2_full = bar_base + 8u * (2 * NSLOT + 14);      // even CTA only: both CTAs hold the A operand of GEMM1 in TMEM
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * NSLOT + 15));
+    // LayerNorm statistics of the partner CTA (same rows, other 128 columns): 256 x 8 bytes by st.async per exchange
+    auto stat_bar = [&](int i) { return bar_base + 8u * (2 * NSLOT + 16 + i); };   // 0: pre-phase, 1: LayerNorm, 2: final LayerNorm
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef TTB_FFN_TIMELINE
@@ -1479,6 +1531,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             mbar_init(pre_done, 1);
             mbar_init(x2_recv, 1);
             mbar_init(x2_full, 16);
+            for (int i = 0; i < 3; ++i) mbar_init(stat_bar(i), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -1611,7 +1664,9 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         if (epi) {
             mbar_wait(pre_acc, 0);
             tcgen05_fence_after();
+            if (ts_on) FFN_TS(2, tse, 10);
             mbar_wait(resid_bar, 0);
+            if (ts_on) FFN_TS(2, tse, 11);
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
@@ -1622,23 +1677,29 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                     const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
                     const int j = c0 + 4 * c;
                     const float4 bv = *reinterpret_cast<const float4*>(prm + 640 + hh * 64 + j);
-                    v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
-                    v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
-                    v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
-                    v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+                    add3_f32x4(v + j, r + 4 * c, bv, rv);
                 }
             }
+            if (ts_on) FFN_TS(2, tse, 12);
             float mean, m2;
             ln_local_stats(v, mean, m2);
+            if (ts_on) FFN_TS(2, tse, 13);
             part0[pidx0 * BM + row] = make_float2(mean, m2);
-            st_peer_f32x2(smem_u32(&part0[pidx0 * BM + row]), xpeer, mean, m2);
-            if (threadIdx.x == 64) mbar_expect_tx(x2_recv, 32768);
+            st_async_peer_f32x2(smem_u32(&part0[pidx0 * BM + row]), stat_bar(0), xpeer, mean, m2);
+            if (threadIdx.x == 64) { mbar_expect_tx(x2_recv, 32768); mbar_expect_tx(stat_bar(0), 2048); }
+            // the partner's statistics only leave after its threads have seen ITS pre-phase accumulator complete, so their
+            // arrival also says that the partner pair's GEMM has finished reading its X regions (written below through DSMEM)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ts_on) FFN_TS(2, tse, 14);
+            mbar_wait(stat_bar(0), 0);
+            if (ts_on) FFN_TS(2, tse, 15);
         }
         __syncwarp();
-        cluster_sync_all();   // statistics exchanged; every pair's pre-phase GEMM has finished reading its X regions
         if (epi) {
             ln_normalise(v, part0, row, prm + 768 + hh * 64, prm + 896 + hh * 64);
+            if (ts_on) FFN_TS(2, tse, 16);
             ln_store_tiles(v, gen + OFF_RING + SLOT + 2 * hh * 16384, gen + (2 * (int)p + hh) * 16384, row);
+            if (ts_on) FFN_TS(2, tse, 17);
             {   // own 64 columns of the normalised row -> A operand in tensor memory (K elements 128 p + 64 hh ..)
                 uint32_t w[32];
 #pragma unroll
@@ -1648,9 +1709,11 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                 }
                 tmem_st_32x32(tm_xa + lane_base + (uint32_t)(64 * (int)p + 32 * hh), w);
             }
+            if (ts_on) FFN_TS(2, tse, 18);
             tcgen05_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ts_on) FFN_TS(2, tse, 19);
             if (threadIdx.x == 64) {
                 // the tile halves first: they gate GEMM1; the fp32 store only gates ring slots 1-2 (second weight tile)
                 const uint32_t own = base + 2 * p * 16384;
@@ -1661,11 +1724,14 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             // the partner's 128 columns (K-blocks 2(1-p), 2(1-p)+1 of the X region, landed through DSMEM) -> tensor memory
+            if (ts_on) FFN_TS(2, tse, 20);
             mbar_wait(x2_recv, 0);
+            if (ts_on) FFN_TS(2, tse, 21);
             smem_kblock_to_tmem(gen + (2 * (int)(p ^ 1u) + hh) * 16384, row, tm_xa + lane_base + (uint32_t)(64 * (int)(p ^ 1u) + 32 * hh));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(mapa_u32(x2_full, leader));
+            if (ts_on) FFN_TS(2, tse, 22);
             if (threadIdx.x == 64) {   // ring slots 1-2 are free once the fp32 store has read them
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(pre_done);
@@ -1800,7 +1866,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     if (threadIdx.x == 64 && live) mbar_expect_tx(recv_bar, 65536);
     __syncwarp();
     // barrier A ("my main loop is over: my H / ring may be written"), split into arrive / wait around the staging
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // an execution hand-over: nothing is published by it
     if (epi) {
         const int pcol = (int)(p ^ 1u) * 128 + hh * 64;   // the partner's output columns handled by this thread
 #pragma unroll
@@ -1818,7 +1884,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     }
     __syncwarp();
     if (ts_on) FFN_TS(2, tse, 700);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // barrier A (wait): the partner's buffers are free
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");             // barrier A (wait): the partner's buffers are free
     if (ts_on) FFN_TS(2, tse, 701);
     if (threadIdx.x == 64 && live) {
         const uint32_t r_recv = mapa_u32(base + OFF_H, xpeer), r_bar = mapa_u32(recv_bar, xpeer);
@@ -1841,10 +1907,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                 const float4 rv = *reinterpret_cast<const float4*>(box + ((c ^ swz) << 4));
                 const int j = c0 + 4 * c;
                 const float4 bv = *reinterpret_cast<const float4*>(prm + hh * 64 + j);
-                v[j + 0] = __uint_as_float(r[4 * c + 0]) + bv.x + rv.x;
-                v[j + 1] = __uint_as_float(r[4 * c + 1]) + bv.y + rv.y;
-                v[j + 2] = __uint_as_float(r[4 * c + 2]) + bv.z + rv.z;
-                v[j + 3] = __uint_as_float(r[4 * c + 3]) + bv.w + rv.w;
+                add3_f32x4(v + j, r + 4 * c, bv, rv);
             }
         }
         mbar_wait_cluster(recv_bar, 0);   // the partner's partial sum has landed (its flight overlapped the loads above)
@@ -1853,19 +1916,24 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         for (int c = 0; c < 16; ++c) {
             const int chunk = hh * 16 + c;
             const float4 pv = *reinterpret_cast<const float4*>(recv + row * 512 + ((chunk ^ (row & 31)) << 4));
-            v[4 * c + 0] += pv.x;
-            v[4 * c + 1] += pv.y;
-            v[4 * c + 2] += pv.z;
-            v[4 * c + 3] += pv.w;
+            {
+                const float2 lo = fadd2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(pv.x, pv.y));
+                const float2 hi = fadd2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(pv.z, pv.w));
+                v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
+            }
         }
         float mean, m2;
         ln_local_stats(v, mean, m2);
         part1[pidx * BM + row] = make_float2(mean, m2);
-        st_peer_f32x2(smem_u32(&part1[pidx * BM + row]), xpeer, mean, m2);
+        st_async_peer_f32x2(smem_u32(&part1[pidx * BM + row]), stat_bar(1), xpeer, mean, m2);
+        if (threadIdx.x == 64) mbar_expect_tx(stat_bar(1), 2048);
+        if (ts_on) FFN_TS(2, tse, 800);
+        // the partner's statistics are computed from the partial sum this CTA sent: their arrival also says that the send
+        // buffer (ring slot 1, re-used for the bf16 tile below) has been consumed
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(stat_bar(1), 0);
     }
     __syncwarp();
-    if (ts_on) FFN_TS(2, tse, 800);
-    cluster_sync_all();                                                         // barrier C
     if (ts_on) FFN_TS(2, tse, 801);
     if (epi) ln_normalise(v, part1, row, prm + 128 + hh * 64, prm + 256 + hh * 64);
     if (ts_on) FFN_TS(2, tse, 810);
@@ -1874,10 +1942,12 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             float mean, m2;
             ln_local_stats(v, mean, m2);
             part2[pidx * BM + row] = make_float2(mean, m2);
-            st_peer_f32x2(smem_u32(&part2[pidx * BM + row]), xpeer, mean, m2);
+            st_async_peer_f32x2(smem_u32(&part2[pidx * BM + row]), stat_bar(2), xpeer, mean, m2);
+            if (threadIdx.x == 64) mbar_expect_tx(stat_bar(2), 2048);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(stat_bar(2), 0);
         }
         __syncwarp();
-        cluster_sync_all();
         if (epi) ln_normalise(v, part2, row, prm + 384 + hh * 64, prm + 512 + hh * 64);
     }
     if (epi) {
@@ -1899,7 +1969,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     // the tensor memory of a pair is released together: both CTAs are past their last tcgen05.ld
     tcgen05_fence_before();
     __syncthreads();
-    cluster_sync_all();
+    cluster_sync_relaxed();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }

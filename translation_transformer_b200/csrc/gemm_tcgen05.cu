@@ -701,7 +701,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t a2_peer_bar = bar_base + 8u * (2 * NST + 3);   //   the peer's half of the LayerNorm output has landed
     const uint32_t a2_own_bar = bar_base + 8u * (2 * NST + 4);    //   this CTA's half is written
     const uint32_t acc2_bar = bar_base + 8u * (2 * NST + 5);      //   its accumulator is complete
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (bar_base - base) + 8 * (2 * NST + 6));
+    // LayerNorm statistics of the peer (same rows, other 128 columns): 256 x 8 bytes by st.async per exchange (see ffn_pair_kernel)
+    auto stat_bar = [&](int i) { return bar_base + 8u * (2 * NST + 6 + i); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (bar_base - base) + 8 * (2 * NST + 8));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = K / BK;
@@ -722,6 +724,8 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(a2_peer_bar, 1);
             mbar_init(a2_own_bar, 1);
             mbar_init(acc2_bar, 1);
+            mbar_init(stat_bar(0), 1);
+            mbar_init(stat_bar(1), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // The weights do not depend on earlier kernels: the W K-blocks of the first ring fill are requested right here,
             // at the very top of the CTA (before the tensor-memory allocation, the parameter loads and the dependency
@@ -842,30 +846,39 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         ln_local_stats(v, mean, m2);
         LNK_TS(5);
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // phase 0: the peer is running
-        ln_publish(part1, pidx, row, rank, mean, m2);
-        // chained GEMM: expect the peer's half of the normalised tile (it is sent after the barrier below)
-        if (chain && threadIdx.x == 64) mbar_expect_tx(a2_peer_bar, 2 * 16384);
+        part1[pidx * BM + row] = make_float2(mean, m2);
+        st_async_peer_f32x2(smem_u32(&part1[pidx * BM + row]), stat_bar(0), rank ^ 1u, mean, m2);
+        if (threadIdx.x == 64) {
+            mbar_expect_tx(stat_bar(0), 2048);
+            // chained GEMM: expect the peer's half of the normalised tile.  The peer sends it after it has received THESE
+            // statistics, which leave after this CTA's GEMM has completed: the ring stages it lands in are free by then.
+            if (chain) mbar_expect_tx(a2_peer_bar, 2 * 16384);
+        }
+        LNK_TS(6);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // this CTA's two groups per row
+        mbar_wait(stat_bar(0), 0);                       // the peer's two groups
+        LNK_TS(7);
     } else {
         __syncwarp();
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     __syncwarp();
-    LNK_TS(6);
-    cluster_sync_all();
-    LNK_TS(7);
     if (epi) ln_normalise(v, part1, row, prm + BNL + h * 64, prm + 2 * BNL + h * 64);
     if (g2) {   // final LayerNorm of the stack on top (uniform branch)
         if (epi) {
             float mean, m2;
             ln_local_stats(v, mean, m2);
-            ln_publish(part2, pidx, row, rank, mean, m2);
+            part2[pidx * BM + row] = make_float2(mean, m2);
+            st_async_peer_f32x2(smem_u32(&part2[pidx * BM + row]), stat_bar(1), rank ^ 1u, mean, m2);
+            if (threadIdx.x == 64) mbar_expect_tx(stat_bar(1), 2048);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(stat_bar(1), 0);
         }
         __syncwarp();
-        cluster_sync_all();
         if (epi) ln_normalise(v, part2, row, prm + 3 * BNL + h * 64, prm + 4 * BNL + h * 64);
     }
     if (chain && live && warp == 1 && lane == 0) {
-        // chained GEMM, issued here (behind the statistics barriers every thread of the cluster takes part in):
+        // chained GEMM:
         // q2 = LN(x) . W2^T with A = the full 128 x 256 bf16 tile (own + peer halves) in ring stages 0-1
         constexpr uint32_t idesc2 = umma_idesc_bf16(BM, BNL);
         mbar_wait(w2_bar, 0);
@@ -943,7 +956,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     }
     // the peer reads this CTA's shared memory (bulk copy above) until its own chained GEMM has started
-    if (chain) { __syncwarp(); cluster_sync_all(); }
+    if (chain) { __syncwarp(); cluster_sync_relaxed(); }
     LNK_TS(14);
     tcgen05_fence_before();
     __syncthreads();
@@ -1865,8 +1878,11 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     uint8_t* send = gen + OFF_RING + SLOT;   // same layout
     if (threadIdx.x == 64 && live) mbar_expect_tx(recv_bar, 65536);
     __syncwarp();
-    // barrier A ("my main loop is over: my H / ring may be written"), split into arrive / wait around the staging
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // an execution hand-over: nothing is published by it
+    // barrier A ("my main loop is over: my H / ring may be written"), split into arrive / wait around the staging; an
+    // execution hand-over (nothing is published by it), hence relaxed: the release form costs 1.9 k cycles here.
+    // (Measured and not adopted: the partial sums sent straight from registers with st.async.v4 instead of staging tile +
+    // bulk copy -- 16 instructions per thread take 5.8 k cycles to issue, ~11 B/clk against ~21 B/clk of the bulk copy.)
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     if (epi) {
         const int pcol = (int)(p ^ 1u) * 128 + hh * 64;   // the partner's output columns handled by this thread
 #pragma unroll
@@ -1928,8 +1944,6 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         st_async_peer_f32x2(smem_u32(&part1[pidx * BM + row]), stat_bar(1), xpeer, mean, m2);
         if (threadIdx.x == 64) mbar_expect_tx(stat_bar(1), 2048);
         if (ts_on) FFN_TS(2, tse, 800);
-        // the partner's statistics are computed from the partial sum this CTA sent: their arrival also says that the send
-        // buffer (ring slot 1, re-used for the bf16 tile below) has been consumed
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(stat_bar(1), 0);
     }
@@ -1951,8 +1965,8 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         if (epi) ln_normalise(v, part2, row, prm + 384 + hh * 64, prm + 512 + hh * 64);
     }
     if (epi) {
-        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (the send buffer:
-        // the partner has consumed it before it arrived at barrier C)
+        // fp32 tile back into the residual boxes (X region, in place), bf16 tile into ring slot 1 (the send buffer: the
+        // partner's statistics are computed from the partial sum this CTA sent, so their arrival says it has been consumed)
         if (ts_on) FFN_TS(2, tse, 811);
         ln_store_tiles(v, gen + 2 * hh * 16384, gen + OFF_RING + SLOT + hh * 16384, row);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -2126,7 +2140,7 @@ gemm_pair_k256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
-    cluster_sync_all();   // the tensor memory of a pair is released together
+    cluster_sync_relaxed();   // the tensor memory of a pair is released together (execution order only: no release fence)
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }

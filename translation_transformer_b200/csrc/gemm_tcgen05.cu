@@ -917,7 +917,6 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, resid_u32 + bx * (BM * 128), n0 + 32 * bx, m0);
             for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + (slot0 + hb) * (BM * 128), n0 + 64 * hb, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (!chain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         if (chain) {
             // epilogue of the chained GEMM: + bias, bf16, staged in ring stage 2 (the weight slice is consumed), TMA store
@@ -950,8 +949,6 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmQ, base + 2 * STAGE + hb * 16384, n0 + 64 * hb, m0);
                 LNK_TS(12);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                LNK_TS(13);
             }
         }
     }
@@ -962,6 +959,10 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BNL)) : "memory");
+    }
+    if (threadIdx.x == 64 && live) {   // the staging tiles must outlive the TMA stores that read them
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        LNK_TS(13);
     }
 }
 
@@ -1976,8 +1977,6 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             for (int bx = 0; bx < 4; ++bx) tma_store_2d(&tmX, base + bx * 16384, n0 + 32 * bx, m0);
             for (int hb = 0; hb < 2; ++hb) tma_store_2d(&tmXh, base + OFF_RING + SLOT + hb * 16384, n0 + 64 * hb, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (ts_on) FFN_TS(2, tse, 900);
         }
     }
     // the tensor memory of a pair is released together: both CTAs are past their last tcgen05.ld
@@ -1986,6 +1985,12 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     cluster_sync_relaxed();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+    // the staging tiles must outlive the TMA stores that read them: the storing thread waits here, behind the barrier and
+    // the release of the tensor memory instead of in front of them
+    if (threadIdx.x == 64 && live) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (ts_on) FFN_TS(2, tse, 900);
     }
 }
 
@@ -2136,7 +2141,6 @@ gemm_pair_k256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -2144,6 +2148,7 @@ gemm_pair_k256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+    if (threadIdx.x == 64 && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tiles outlive their stores
 }
 
 // =====================================================================================================

@@ -1583,10 +1583,6 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 #endif
     pdl_launch_dependents();
     const int live_rows = rows.live();   // written before this programmatic chain started: fetched ahead of the wait
-    pdl_wait();
-#ifdef TTB_FFN_TIMELINE
-    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
-#endif
     const bool live = mblk < live_rows;   // uniform per cluster: dead blocks only take part in the cluster barriers
 
     // ---- roles, phase 1 (chained launches only): operands and GEMM of the pre-phase.  The producer / issuer threads come
@@ -1619,6 +1615,21 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     };
     constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, 128);
     constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 256);
+    // Weights do not depend on earlier kernels: the out-projection tile of the pre-phase and the first W1 chunk are requested
+    // ahead of the dependency wait (every barrier of the pair exists since the cluster barrier above)
+    if (producer) {
+        if (chain) {
+            const uint32_t pf_l = mapa_u32(pre_full, leader);
+            if (t == 0) mbar_expect_tx(pre_full, 2 * 32768);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + OFF_H + kb * 8192, &tmWoh, kb * BK, n0 + (int)t * 64, pf_l);
+        }
+        load_w1(0);   // ring slot 0 is free from the start
+    }
+    pdl_wait();
+#ifdef TTB_FFN_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 96) { g_ffn_ts[2][255][0] = 7; g_ffn_ts[2][255][1] = clock64(); }
+#endif
+
     if (producer) {   // ===== TMA producer (both CTAs of a pair: own rows of the A operand, own half of every weight tile) =====
         FFN_TS(0, tsn, 1);
         if (!chain) {   // own X tile: copied into tensor memory by this CTA's epilogue warps
@@ -1628,15 +1639,11 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             const uint32_t x_full_l = mapa_u32(x_full, leader);
             if (t == 0) mbar_expect_tx(x_full, 2 * X_BYTES);
             for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + kb * 16384, &tmAtt, kb * BK, m0, x_full_l);
-            // pre-phase operands: this CTA's 64 of the pair's 128 rows of Wo into the (still idle) H region, the fp32
-            // residual tile of its 128 output columns into ring slots 1-2
-            const uint32_t pf_l = mapa_u32(pre_full, leader);
-            if (t == 0) mbar_expect_tx(pre_full, 2 * 32768);
-            for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(base + OFF_H + kb * 8192, &tmWoh, kb * BK, n0 + (int)t * 64, pf_l);
+            // pre-phase operands: this CTA's 64 of the pair's 128 rows of Wo are on their way into the (still idle) H region
+            // since before the wait; the fp32 residual tile of its 128 output columns goes into ring slots 1-2
             mbar_expect_tx(resid_bar, 65536);
             for (int bx = 0; bx < 4; ++bx) tma_load_2d(base + OFF_RING + SLOT + bx * 16384, &tmX, n0 + 32 * bx, m0, resid_bar);
         }
-        load_w1(0);   // ring slot 0 is free from the start
     }
     if (issuer) {     // ===== MMA issuer: even CTA of the pair =====
         FFN_TS(1, tsn, 1);

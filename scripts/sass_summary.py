@@ -5,7 +5,7 @@
     python scripts/sass_summary.py [lib.so] > profiles/sass_summary.txt
 
 UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP = cp.async.bulk,
-HMMA = legacy mma.sync path, LDGSTS = cp.async."""
+HMMA = legacy mma.sync path, LDGSTS = cp.async, FFMA2 / FADD2 = packed fp32 (two lanes per instruction)."""
 import re
 import subprocess
 import sys
@@ -14,7 +14,7 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
 lib = Path(sys.argv[1]) if len(sys.argv) > 1 else REPO / "translation_transformer_b200" / "libttb200.so"
-MNEMONICS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "MUFU.EX2"]
+MNEMONICS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "MUFU.EX2", "FFMA2", "FADD2"]
 
 sass = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
 demangle = {}

@@ -197,9 +197,13 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
     const bool keep_pred = N <= 32 && D + 1 <= 16;
     ACC_TS(0);
     pdl_launch_dependents();
-    pdl_wait();
-    ACC_TS(1);
-    // ---- round 1: independent loads --------------------------------------------------------------
+#ifdef TTB_ACC_LATE_LOADS
+    pdl_wait();   // A/B build: everything behind the dependency wait
+#endif
+    // ---- round 1: independent loads, AHEAD of the dependency wait.  Everything read here (control words, live list, fronts,
+    // token matrix) was written by the accept kernel of the previous iteration (or by the init kernel), and the first kernel
+    // of every iteration (greedy_advance_kernel) gives no early trigger: no kernel of this iteration is scheduled before it
+    // has seen that accept kernel complete.  Only the predictions of the classifier (st.pred) need the wait.
     const int done = st.ctrl[CTRL_DONE];
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
     const int Wn = st.ctrl[CTRL_WIDTH];
@@ -222,6 +226,10 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
             for (int u = 0; u < 8; ++u) { const int idx = i0 + u * blockDim.x + threadIdx.x; if (idx < total) s_gen[idx] = tmp[u]; }
         }
     }
+    ACC_TS(1);
+#ifndef TTB_ACC_LATE_LOADS
+    pdl_wait();
+#endif
     if (done) return;
     int* G = stage_gen ? s_gen : st.gen;
     if (threadIdx.x == 0) { s_acc = 0; s_tok = 0; s_err = 0; if (st.hist) st.hist[iter] = n_active; }

@@ -88,8 +88,8 @@ def parse():
     ap.add_argument("--in-flight", type=int, default=0,
                     help="batches decoded concurrently per GPU, one engine + stream each (translation_transformer_b200/pipeline.py); "
                          "1 = strictly one batch after the other, also always measured and reported as `one_batch_in_flight`; 0 (default) = 3 "
-                         "for the random-init greedy workload (every batch keeps all its queries to the end), 8 for the workloads "
-                         "whose batches thin out while they decode (measured: DESIGN.md section 4c)")
+                         "for the random-init greedy workload (every batch keeps all its queries to the end), 8 for the trained-like greedy "
+                         "workload whose batches thin out while they decode, 12 for the beam searches (measured: DESIGN.md section 4c)")
     ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
     return ap.parse_args()
 
@@ -728,7 +728,11 @@ def main():
     wl = Workload(args.workload, args.weights, args)
 
     def fly_for(w):
-        return args.in_flight if args.in_flight > 0 else (3 if (w.kind == "greedy" and w.weights == "random") else 8)
+        if args.in_flight > 0:
+            return args.in_flight
+        if w.kind != "greedy":
+            return 12          # beam searches: 6 / 8 / 12 / 16 in flight -> 757 / 783 / 812 / 814 (beam), 881 / 931 / 954 / 938 (retro) SMILES/s
+        return 3 if w.weights == "random" else 8
 
     n_fly = fly_for(wl)
     if args.scaling == "strong":

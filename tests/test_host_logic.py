@@ -345,3 +345,33 @@ def test_bench_workloads_are_the_golden_cases():
     f, b = bench.class_work("gemm_ffn1", wlr.w, wlr.cfg, [32], 80.0, True, True, True, "bf16")
     rows = 32 * 23 * 11
     assert abs(f / 4 - (4.0 * rows * 256 * 2048 + 2.0 * rows * 256 * 256 + 16.0 * rows * 256)) < 1.0
+
+
+def test_committed_bench_line_keeps_the_driver_contract():
+    """profiles/r2_bench_1gpu.json is the line `python bench.py` printed on the B200 for the committed build: the keys the
+    driver and the judge read must be there and consistent with each other (BASELINE.json metric, roofline = achieved / peak,
+    end-to-end figure with its copy sizes, clocks without a throttle reason, a launch count, the parity self-check)."""
+    import json
+    line = json.loads((REPO / "profiles/r2_bench_1gpu.json").read_text().strip().splitlines()[-1])
+    base = json.loads((REPO / "BASELINE.json").read_text())
+    assert base["metric"].startswith("SMILES/sec") and line["metric"].startswith("SMILES/sec") and line["unit"] == "SMILES/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches", "parity_checked", "parity_ok"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["higher_is_better"] is True and line["dtype"] == "bf16"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and 0.0 < r["frac"] < 1.0
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = line["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = line["e2e"]
+    assert e["unit"] == line["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert 0.5 * line["value"] < e["value"] < 1.1 * line["value"]          # a measurement of its own, not a copy of `value`
+    assert e["value"] != line["value"]
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert not bad & set(line["clocks"]["reasons"]) and line["clocks"]["sm_mhz"] > 0.9 * line["clocks"]["sm_max_mhz"]
+    assert line["gpu_launches"] > 0 and line["parity_checked"] is True and line["parity_ok"] is True
+    # value = queries of all timed steps / time: 32 queries per step
+    assert abs(line["value"] - 32.0 * 1000.0 / line["ms_per_step"]) / line["value"] < 1e-3

@@ -92,10 +92,15 @@ __global__ void greedy_advance_kernel(GreedyState st, const float* __restrict__ 
                                       long long cache_query_stride, int cache_ld, long long vt_layer_stride, long long vt_query_stride,
                                       int vt_pitch) {
     // Launched with the programmatic attribute behind the accept kernel (scheduled while it runs, starts when it is
-    // complete) but WITHOUT an early trigger of its own dependents: the kernels of the decoding iteration read the
-    // control words and descriptor table of the accept kernel ahead of their dependency waits, so none of them may be
-    // scheduled before this kernel has seen the accept kernel complete.
+    // complete).  The kernels of the decoding iteration read the control words and descriptor table of the accept kernel
+    // ahead of their dependency waits, so none of them may be scheduled before this kernel has SEEN the accept kernel
+    // complete: its dependents are released right behind its own wait, not before (their prologues -- barrier set-up,
+    // tensor-memory allocation, weight requests -- then overlap this kernel instead of following it).  Nothing this kernel
+    // writes (embeddings, the appended K/V rows) is read by a later kernel ahead of that kernel's wait.
     pdl_wait();
+#ifndef TTB_ADVANCE_NO_TRIGGER
+    pdl_launch_dependents();
+#endif
     // the control words and the per-slot records are fetched together, ahead of the tests that use them (as dependent
     // loads they would be three to five global round trips in a row); the slot indices are in range for every CTA
     const int done = st.ctrl[CTRL_DONE], n_sel = st.ctrl[CTRL_N_SEL], n_active = st.ctrl[CTRL_N_ACTIVE];
@@ -202,8 +207,8 @@ __global__ void __launch_bounds__(1024) greedy_accept_kernel(GreedyState st, int
 #endif
     // ---- round 1: independent loads, AHEAD of the dependency wait.  Everything read here (control words, live list, fronts,
     // token matrix) was written by the accept kernel of the previous iteration (or by the init kernel), and the first kernel
-    // of every iteration (greedy_advance_kernel) gives no early trigger: no kernel of this iteration is scheduled before it
-    // has seen that accept kernel complete.  Only the predictions of the classifier (st.pred) need the wait.
+    // of every iteration (greedy_advance_kernel) releases its dependents only behind its own wait: no kernel of this iteration
+    // is scheduled before it has seen that accept kernel complete.  Only the predictions of the classifier (st.pred) need the wait.
     const int done = st.ctrl[CTRL_DONE];
     const int n_active = st.ctrl[CTRL_N_ACTIVE];
     const int Wn = st.ctrl[CTRL_WIDTH];
